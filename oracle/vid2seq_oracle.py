@@ -1,0 +1,277 @@
+"""TEST INFRASTRUCTURE — CPU/torch restatement of the reference Vid2Seq train step.
+
+This is the ORACLE (checker) for the CUDA path in vidchapters_b200/.  It is a
+plain-PyTorch functional restatement of the reference algorithm over a state
+dict that uses the reference's own key names.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import it; the product package never does.
+
+PINNING: tests/test_oracle_vs_reference.py checks this file against the real,
+unmodified reference (imported through oracle/ref_shim.py) when /root/reference
+is present, and tests/golden/*.pt hold vectors minted from the real reference
+by oracle/make_golden.py, against which this file is checked everywhere.
+The reference itself ships no tests/golden vectors for this path,
+so parity is pinned to the reference's own outputs, not to reference tests.
+
+Each function cites the reference lines it restates (paths under /root/reference).
+
+Two arithmetic modes:
+  emulate_bf16=False : fp32 everywhere == the reference's numerics (tier B).
+  emulate_bf16=True  : every matmul operand (Linear input+weight, Q.K^T, P.V and
+                       their backward counterparts) is rounded to bf16 and
+                       accumulated in fp32 — what a bf16 tensor-core kernel with
+                       fp32 accumulation computes (tier A).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+NEG_MIN = torch.finfo(torch.float32).min  # HF additive mask constant, modeling_t5.py:996,1005 (third-party helper)
+
+
+def _r(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+class _EmuMatmul(torch.autograd.Function):
+    """C = A @ B with operands rounded to bf16 (forward AND backward), fp32 accumulate."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ar, br = _r(a), _r(b)
+        ctx.save_for_backward(ar, br)
+        return ar @ br
+
+    @staticmethod
+    def backward(ctx, g):
+        ar, br = ctx.saved_tensors
+        gr = _r(g)
+        return gr @ br.transpose(-1, -2), ar.transpose(-1, -2) @ gr
+
+
+class Arith:
+    def __init__(self, emulate_bf16: bool):
+        self.emu = emulate_bf16
+
+    def matmul(self, a, b):
+        if self.emu:
+            return _EmuMatmul.apply(a, b)
+        return a @ b
+
+    def linear(self, x, w, b=None):
+        y = self.matmul(x, w.t())
+        return y if b is None else y + b
+
+
+# --------------------------------------------------------------------------------------
+# model/vit.py
+# --------------------------------------------------------------------------------------
+def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, ar: Arith, pfx="visual_encoder.") -> torch.Tensor:
+    """model/vit.py:117-133 (VisionTransformer.forward), :73-76 (Block), :38-55 (Attention), :16-22 (Mlp)."""
+    B, N, C = x.shape
+    H = cfg["heads"]
+    pos = sd[pfx + "pos_embed"]
+    if N != pos.shape[1]:  # vit.py:119-123 nearest interpolation of the time embedding
+        pos = F.interpolate(pos.transpose(1, 2), size=N, mode="nearest").transpose(1, 2)
+    x = x + pos
+    for i in range(cfg["depth"]):
+        p = f"{pfx}blocks.{i}."
+        h = F.layer_norm(x, (C,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+        qkv = ar.linear(h, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"])
+        qkv = qkv.reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        attn = ar.matmul(q, k.transpose(-2, -1)) * ((C // H) ** -0.5)  # vit.py:47
+        attn = attn.softmax(dim=-1)
+        o = ar.matmul(attn, v).transpose(1, 2).reshape(B, N, C)
+        x = x + ar.linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])
+        h = F.layer_norm(x, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+        h = ar.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
+        h = F.gelu(h)  # nn.GELU() exact erf, vit.py:9,19
+        x = x + ar.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    return F.layer_norm(x, (C,), sd[pfx + "norm.weight"], sd[pfx + "norm.bias"], 1e-5)
+
+
+# --------------------------------------------------------------------------------------
+# model/modeling_t5.py
+# --------------------------------------------------------------------------------------
+def t5_layer_norm(x, w, eps=1e-6):
+    """modeling_t5.py:254-277 (T5LayerNorm): RMS norm, fp32 statistics, no mean, no bias."""
+    var = x.to(torch.float32).pow(2).mean(-1, keepdim=True)
+    return w * (x * torch.rsqrt(var + eps))
+
+
+def relative_position_bucket(relative_position, bidirectional=True, num_buckets=32, max_distance=128):
+    """modeling_t5.py:397-443.  Integer bucket of (memory_pos - query_pos); fp32 log then truncation."""
+    relative_buckets = torch.zeros_like(relative_position)
+    if bidirectional:
+        num_buckets //= 2
+        relative_buckets = relative_buckets + (relative_position > 0).to(torch.long) * num_buckets
+        relative_position = torch.abs(relative_position)
+    else:
+        relative_position = -torch.min(relative_position, torch.zeros_like(relative_position))
+    max_exact = num_buckets // 2
+    is_small = relative_position < max_exact
+    large = max_exact + (
+        torch.log(relative_position.float() / max_exact) / math.log(max_distance / max_exact) * (num_buckets - max_exact)
+    ).to(torch.long)
+    large = torch.min(large, torch.full_like(large, num_buckets - 1))
+    return relative_buckets + torch.where(is_small, relative_position, large)
+
+
+def compute_bias(table: torch.Tensor, qlen: int, klen: int, bidirectional: bool) -> torch.Tensor:
+    """modeling_t5.py:445-460 -> (1,H,q,k)."""
+    ctx = torch.arange(qlen, dtype=torch.long, device=table.device)[:, None]
+    mem = torch.arange(klen, dtype=torch.long, device=table.device)[None, :]
+    bucket = relative_position_bucket(mem - ctx, bidirectional=bidirectional)
+    return table[bucket].permute(2, 0, 1).unsqueeze(0)
+
+
+def t5_attention(sd, p, H, dkv, x, kv, position_bias, ar: Arith):
+    """modeling_t5.py:462-588 (no cache, no head mask, no dropout): UNSCALED q.k^T + bias, fp32 softmax."""
+    B, Lq, _ = x.shape
+    Lk = kv.shape[1]
+    q = ar.linear(x, sd[p + "q.weight"]).view(B, Lq, H, dkv).transpose(1, 2)
+    k = ar.linear(kv, sd[p + "k.weight"]).view(B, Lk, H, dkv).transpose(1, 2)
+    v = ar.linear(kv, sd[p + "v.weight"]).view(B, Lk, H, dkv).transpose(1, 2)
+    scores = ar.matmul(q, k.transpose(3, 2))
+    scores = scores + position_bias
+    w = F.softmax(scores.float(), dim=-1)
+    o = ar.matmul(w, v).transpose(1, 2).contiguous().view(B, Lq, H * dkv)
+    return ar.linear(o, sd[p + "o.weight"])
+
+
+def t5_ff(sd, p, x, ar: Arith):
+    """modeling_t5.py:339-354 + :296-311 (T5LayerFF / T5DenseActDense, ReLU)."""
+    h = t5_layer_norm(x, sd[p + "layer_norm.weight"])
+    h = ar.linear(h, sd[p + "DenseReluDense.wi.weight"])
+    h = torch.relu(h)
+    return x + ar.linear(h, sd[p + "DenseReluDense.wo.weight"])
+
+
+def t5_encoder(sd, cfg, embeds, mask, ar: Arith, pfx="t5_model.encoder."):
+    """modeling_t5.py:930-1138 (T5Stack.forward, encoder), :659-769 (T5Block)."""
+    H, dkv = cfg["num_heads"], cfg["d_kv"]
+    B, L, _ = embeds.shape
+    ext = (1.0 - mask[:, None, None, :].to(torch.float32)) * NEG_MIN  # get_extended_attention_mask (HF)
+    table = sd[pfx + "block.0.layer.0.SelfAttention.relative_attention_bias.weight"]
+    bias = compute_bias(table, L, L, True) + ext  # modeling_t5.py:543-559 (layer 0 builds, others reuse :1092-1097)
+    x = embeds
+    for i in range(cfg["num_layers"]):
+        p = f"{pfx}block.{i}."
+        h = t5_layer_norm(x, sd[p + "layer.0.layer_norm.weight"])
+        x = x + t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, bias, ar)
+        x = t5_ff(sd, p + "layer.1.", x, ar)
+    return t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"])
+
+
+def shift_right(labels):
+    """modeling_t5.py:845-868: prepend decoder_start_token_id=0, -100 -> pad 0."""
+    s = labels.new_zeros(labels.shape)
+    s[..., 1:] = labels[..., :-1].clone()
+    s[..., 0] = 0
+    return s.masked_fill(s == -100, 0)
+
+
+def t5_decoder(sd, cfg, dec_ids, dec_mask, enc_h, enc_mask, ar: Arith, pfx="t5_model.decoder."):
+    """modeling_t5.py:930-1138 (decoder stack): causal self-attn (+rel bias), cross-attn (zero bias), FF."""
+    H, dkv = cfg["num_heads"], cfg["d_kv"]
+    B, S = dec_ids.shape
+    x = sd["t5_model.shared.weight"][dec_ids]  # modeling_t5.py:972
+    causal = torch.tril(torch.ones(S, S, device=x.device))[None, :, :] * dec_mask[:, None, :].to(torch.float32)
+    ext = (1.0 - causal[:, None, :, :]) * NEG_MIN  # create_extended_attention_mask_for_decoder (HF)
+    table = sd[pfx + "block.0.layer.0.SelfAttention.relative_attention_bias.weight"]
+    self_bias = compute_bias(table, S, S, False) + ext
+    cross_bias = (1.0 - enc_mask[:, None, None, :].to(torch.float32)) * NEG_MIN  # invert_attention_mask + zeros :544-547
+    for i in range(cfg["num_layers"]):
+        p = f"{pfx}block.{i}."
+        h = t5_layer_norm(x, sd[p + "layer.0.layer_norm.weight"])
+        x = x + t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, self_bias, ar)
+        h = t5_layer_norm(x, sd[p + "layer.1.layer_norm.weight"])
+        x = x + t5_attention(sd, p + "layer.1.EncDecAttention.", H, dkv, h, enc_h, cross_bias, ar)
+        x = t5_ff(sd, p + "layer.2.", x, ar)
+    return t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"])
+
+
+def vid2seq_forward(sd, cfg, video, input_ids, input_mask, output_ids, output_mask, *, emulate_bf16=False,
+                    label_smoothing=0.1, video_is_cached=False):
+    """model/vid2seq.py:58-98 (+ modeling_t5.py:1587-1738).  Dropout-free (p=0 / eval) restatement.
+
+    Returns dict(loss, logits (B,S,V), video (B,T,d), memory (B,T+L,d)).
+    """
+    ar = Arith(emulate_bf16)
+    d = cfg["d_model"]
+    if video_is_cached:
+        vid = video
+    else:
+        vid = vit_forward(sd, cfg, video, ar)
+        if d != 768:  # vid2seq.py:54-56,64-65
+            vid = ar.linear(vid, sd["proj_v2t.weight"], sd["proj_v2t.bias"])
+    atts_vis = torch.ones(vid.shape[:2], dtype=torch.long, device=vid.device)
+    text = sd["t5_model.shared.weight"][input_ids]  # vid2seq.py:71
+    enc = t5_encoder(sd, cfg, text, input_mask, ar)
+    memory = torch.cat([vid, enc], dim=1)  # vid2seq.py:78
+    mem_mask = torch.cat([atts_vis, input_mask.to(torch.long)], dim=1)
+    targets = output_ids.masked_fill(output_ids == 0, -100)  # vid2seq.py:86-88
+    dec_in = shift_right(targets)
+    seq = t5_decoder(sd, cfg, dec_in, output_mask, memory, mem_mask, ar)
+    seq = seq * (d ** -0.5)  # modeling_t5.py:1709-1712 (tied embeddings)
+    logits = ar.linear(seq, sd["t5_model.shared.weight"])  # lm_head tied to shared, F9
+    loss = F.cross_entropy(logits.view(-1, logits.size(-1)), targets.view(-1), ignore_index=-100,
+                           label_smoothing=label_smoothing)  # modeling_t5.py:1721
+    return {"loss": loss, "logits": logits, "video": vid, "memory": memory}
+
+
+# --------------------------------------------------------------------------------------
+# dvc.py step tail
+# --------------------------------------------------------------------------------------
+def clip_adam_renorm_(params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], state: dict, *, lr=3e-4,
+                      betas=(0.9, 0.999), eps=1e-8, clip_max_norm=1.0, num_bins=100):
+    """dvc.py:112-126: clip_grad_norm_ (global L2), torch.optim.Adam (wd 0), time-token renorm.  In place."""
+    names = list(params.keys())
+    total = torch.sqrt(sum((grads[n].double() ** 2).sum() for n in names)).float()
+    coef = 1.0
+    if clip_max_norm > 0:
+        coef = torch.clamp(clip_max_norm / (total + 1e-6), max=1.0)  # torch clip_grad_norm_
+    state["step"] = state.get("step", 0) + 1
+    t = state["step"]
+    b1, b2 = betas
+    for n in names:
+        g = grads[n] * coef
+        m = state.setdefault("m." + n, torch.zeros_like(params[n]))
+        v = state.setdefault("v." + n, torch.zeros_like(params[n]))
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        bc1 = 1 - b1 ** t
+        bc2 = 1 - b2 ** t
+        denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+        params[n].addcdiv_(m, denom, value=-lr / bc1)
+    if num_bins:
+        w = params["t5_model.shared.weight"]  # lm_head is the same tensor (tied): renorm applies twice, dvc.py:118-126
+        for _ in range(2):
+            frozen = torch.norm(w[:-num_bins], dim=1).mean(0)
+            w[-num_bins:].div_(torch.norm(w[-num_bins:], dim=1).mean(0) / frozen)
+    return total
+
+
+def greedy_decode(sd, cfg, memory, mem_mask, max_new_tokens=256, emulate_bf16=False):
+    """Greedy restatement of vid2seq.py:150-162 with num_beams=1 (HF-4.28 generate semantics):
+    start id 0, argmax, per-sequence stop at eos=1 then emit pad 0, stop when all done.  Uncached (O(S^2))."""
+    ar = Arith(emulate_bf16)
+    B = memory.shape[0]
+    ids = torch.zeros(B, 1, dtype=torch.long, device=memory.device)
+    done = torch.zeros(B, dtype=torch.bool, device=memory.device)
+    d = cfg["d_model"]
+    for _ in range(max_new_tokens):
+        mask = torch.ones_like(ids, dtype=torch.bool)
+        seq = t5_decoder(sd, cfg, ids, mask, memory, mem_mask, ar)[:, -1:] * (d ** -0.5)
+        nxt = ar.linear(seq, sd["t5_model.shared.weight"])[:, 0].argmax(-1)
+        nxt = torch.where(done, torch.zeros_like(nxt), nxt)
+        ids = torch.cat([ids, nxt[:, None]], 1)
+        done = done | (nxt == 1)
+        if bool(done.all()):
+            break
+    return ids
