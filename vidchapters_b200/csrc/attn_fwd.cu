@@ -1,0 +1,262 @@
+// Fused attention forward on tcgen05 (sm_100a), head_dim 64.
+//
+// Replaces T5Attention.forward's score/softmax/PV chain (reference model/modeling_t5.py:539-580: UNSCALED q.k^T +
+// position_bias (+ additive key mask), fp32 softmax, .v) and the ViT attention (model/vit.py:47-51: scale 1/8, no
+// mask).  The (B,H,Lq,Lk) score / probability tensors of the reference never exist in HBM.
+//
+// One CTA = one (batch, head, 128-query tile); 2 CTAs per SM (112 KB smem, 256 TMEM columns each) so one CTA's
+// softmax overlaps the other's MMAs.  192 threads:
+//   warp 0 lane 0 : TMA producer (Q once; K,V 128-key tiles through a 2-stage ring), 3-D maps zero-fill past Lq/Lk
+//   warp 1        : TMEM alloc; lane 0 issues  S = Q.K^T (128x128x64)  and  O_j = P.V (128x64x128)
+//   warps 2..5    : softmax: thread = one query row.  Pass 1 row max, pass 2 p = exp2(s2 - m) -> bf16 P tile written
+//                   into 128B-swizzled smem (the A operand of the PV MMA); running (m, l) online softmax; the PV
+//                   partial product is read back from TMEM and accumulated in registers with the usual rescale.
+// Scores are handled in the log2 domain: s2 = (acc*scale + bias) * log2(e).  Masked keys (key-padding or causal)
+// take the reference's additive finfo.min semantics (a fully masked row degenerates to uniform, like the reference);
+// columns past Lk are excluded exactly.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vc {
+
+constexpr int kTQ = 128, kTK = 128, kD = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kMasked = -3.0e38f;  // stands for the reference's (1-mask)*finfo(float32).min after the add
+
+struct AttnFwdParams {
+  int B, H, Lq, Lk;
+  int q_col, k_col, v_col;
+  __nv_bfloat16* out;
+  long long ldo;
+  float* lse2;            // [B,H,Lq] log2-domain logsumexp of s2
+  const float* bias_rel;  // [H][Lq+Lk-1] or null; index (k - q + Lq - 1)
+  const uint8_t* kmask;   // [B][Lk] or null
+  int causal;
+  float scale_log2e;
+};
+
+constexpr int kAttnFwdSmem = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768 /*P*/ + 512 /*barriers*/;
+
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = sK + 2 * 16384;
+  uint8_t* sP = sV + 2 * 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint64_t* o_read = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * kTQ;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) __trap();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_read, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // 128 columns
+  const uint32_t tmem_O = tmem_base + 128;  // 64 columns
+
+  // number of key tiles this query tile visits (causal: skip tiles entirely above the diagonal)
+  int nkt = (p.Lk + kTK - 1) / kTK;
+  if (p.causal) nkt = min(nkt, (q0 + kTQ - 1) / kTK + 1);
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_arrive_expect_tx(q_full, 16384);
+    tma_load_3d(sQ, &tmQ, q_full, p.q_col + h * kD, q0, b);
+    for (int j = 0; j < nkt; ++j) {
+      const int st = j & 1;
+      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+      mbar_arrive_expect_tx(&kv_full[st], 32768);
+      tma_load_3d(sK + st * 16384, &tmK, &kv_full[st], p.k_col + h * kD, j * kTK, b);
+      tma_load_3d(sV + st * 16384, &tmV, &kv_full[st], p.v_col + h * kD, j * kTK, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S: A=Q K-major, B=K K-major, N=128
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);   // O: A=P K-major, B=V MN-major, N=64
+    mbar_wait(q_full, 0);
+    const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+    for (int j = 0; j < nkt; ++j) {
+      const int st = j & 1;
+      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + st * 16384), 0, 1024);
+#pragma unroll
+      for (int k = 0; k < kD / 16; ++k) tc_mma_bf16(tmem_S, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0);
+      tc_commit(s_full);
+      // P(j) written and S(j) consumed; O(j-1) read back
+      mbar_wait(p_full, j & 1);
+      if (j > 0) mbar_wait(o_read, (j - 1) & 1);
+      tc_fence_after();
+      const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + st * 16384), 0, 1024);
+#pragma unroll
+      for (int k = 0; k < kTK / 16; ++k) {
+        const uint64_t pd = make_smem_desc_sw128(smem_u32(sP + (k >> 2) * 16384) + (k & 3) * 32, 0, 1024);
+        tc_mma_bf16(tmem_O, pd, vdesc + (uint64_t)(k * 128), idesc_o, k > 0);
+      }
+      tc_commit(&kv_empty[st]);
+      tc_commit(o_full);
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax / epilogue =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // row in tile == TMEM lane
+    const int q = q0 + r;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float* brow = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) + (p.Lq - 1 - q) : nullptr;
+    const uint8_t* mrow = p.kmask ? p.kmask + (long long)b * p.Lk : nullptr;
+    float m_run = -INFINITY, l_run = 0.0f;
+    float o_acc[kD];
+#pragma unroll
+    for (int i = 0; i < kD; ++i) o_acc[i] = 0.0f;
+
+    for (int j = 0; j < nkt; ++j) {
+      const int k0 = j * kTK;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // ---- pass 1: row max of s2 over the tile
+      float m_tile = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = k0 + c * 32 + i;
+          float s2 = v[i] * p.scale_log2e;
+          if (brow && k < p.Lk) s2 += __ldg(brow + k) * kLog2e;
+          bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[k]);
+          s2 = masked ? kMasked : s2;
+          s2 = (k < p.Lk) ? s2 : -INFINITY;
+          m_tile = fmaxf(m_tile, s2);
+        }
+      }
+      const float m_new = fmaxf(m_run, m_tile);
+      const float corr = fast_exp2(m_run - m_new);  // m_run=-inf on first tile -> 0
+      // ---- pass 2: p = exp2(s2 - m_new), write bf16 P (swizzled, K-major A operand), row sum
+      float l_tile = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = k0 + c * 32 + i;
+          float s2 = v[i] * p.scale_log2e;
+          if (brow && k < p.Lk) s2 += __ldg(brow + k) * kLog2e;
+          bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[k]);
+          s2 = masked ? kMasked : s2;
+          const float pv = (k < p.Lk) ? fast_exp2(s2 - m_new) : 0.0f;
+          l_tile += pv;
+          v[i] = pv;
+        }
+        // 32 columns = 4 x 16-byte chunks of this row; chunk index within the 64-wide atom: (c&1)*4 + g
+        uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ch = ((c & 1) * 4 + g) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + ch * 16) =
+              make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                         pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full);
+      l_run = l_run * corr + l_tile;
+      m_run = m_new;
+      // ---- accumulate O_j
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld32(tmem_O + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * corr + v[i];
+      }
+      tc_fence_before();
+      mbar_arrive(o_read);
+    }
+    if (q < p.Lq) {
+      const float inv = 1.0f / l_run;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * p.Lq + q) * p.ldo + h * kD);
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        dst[g] = make_uint4(pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv),
+                            pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv),
+                            pack_bf16x2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv),
+                            pack_bf16x2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv));
+      if (p.lse2) p.lse2[((long long)b * p.H + h) * p.Lq + q] = m_run + log2f(l_run);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace vc
+
+using namespace vc;
+
+extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
+  VC_CHECK(a != nullptr, "vc_attn_fwd: null args");
+  VC_CHECK(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "vc_attn_fwd: bad dims");
+  VC_CHECK(a->head_dim == 64, "vc_attn_fwd: head_dim must be 64 (got %d)", a->head_dim);
+  VC_CHECK(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "vc_attn_fwd: strides must be x8");
+  VC_CHECK(a->q_col % 8 == 0 && a->k_col % 8 == 0 && a->v_col % 8 == 0, "vc_attn_fwd: column offsets must be x8");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap tmQ, tmK, tmV;
+  int s;
+  if ((s = make_tmap_3d(&tmQ, a->q, a->ldq, a->Lq, a->B, a->ldq, (uint64_t)a->Lq * a->ldq, 64, kTQ)) != VC_OK) return s;
+  if ((s = make_tmap_3d(&tmK, a->k, a->ldk, a->Lk, a->B, a->ldk, (uint64_t)a->Lk * a->ldk, 64, kTK)) != VC_OK) return s;
+  if ((s = make_tmap_3d(&tmV, a->v, a->ldv, a->Lk, a->B, a->ldv, (uint64_t)a->Lk * a->ldv, 64, kTK)) != VC_OK) return s;
+  AttnFwdParams p;
+  p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
+  p.q_col = a->q_col; p.k_col = a->k_col; p.v_col = a->v_col;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
+  p.lse2 = a->lse2; p.bias_rel = a->bias_rel; p.kmask = a->kmask; p.causal = a->causal;
+  p.scale_log2e = a->scale * kLog2e;
+  static bool attr = false;
+  if (!attr) {
+    VC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwdSmem));
+    attr = true;
+  }
+  dim3 grid((a->Lq + kTQ - 1) / kTQ, a->H, a->B);
+  attn_fwd_kernel<<<grid, 192, kAttnFwdSmem, st>>>(tmQ, tmK, tmV, p);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}

@@ -1,0 +1,38 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and TMA tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vidchap.h"
+
+namespace vc {
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define VC_CHECK(cond, ...)            \
+  do {                                 \
+    if (!(cond)) {                     \
+      vc::set_error(__VA_ARGS__);      \
+      return VC_ERR_INVALID;           \
+    }                                  \
+  } while (0)
+#define VC_CUDA(call)                                      \
+  do {                                                     \
+    int _s = vc::check_cuda((call), #call);                \
+    if (_s != VC_OK) return _s;                            \
+  } while (0)
+
+// bf16 tensor maps, SWIZZLE_128B, zero OOB fill.  Box inner extent is always 64 elements (128 B).
+//  2D: tensor [outer][inner] with row stride `row_stride_elems`.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                 uint32_t box_inner, uint32_t box_outer);
+//  3D: tensor [d2][d1][inner] with element strides s1 (between d1 rows) and s2 (between d2 slabs).
+int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2, uint64_t s1_elems,
+                 uint64_t s2_elems, uint32_t box_inner, uint32_t box_d1);
+
+int num_sms();
+
+}  // namespace vc

@@ -1,0 +1,214 @@
+// Row-wise normalisation kernels (HBM-bound): T5 RMS LayerNorm and nn.LayerNorm, forward and backward.
+//
+// Reference: model/modeling_t5.py:254-277 (T5LayerNorm: x * rsqrt(mean(x^2) + eps) * w, fp32 statistics, no mean
+// subtraction, no bias) and torch.nn.LayerNorm as used by model/vit.py:64,70,96 (eps 1e-5, affine).
+// Residual stream x is fp32 in HBM; the normalised output feeds a tensor-core GEMM and is therefore written as bf16
+// (optionally into a strided/batched destination so the encoder's final norm lands directly inside the decoder's
+// concatenated [video ; text] memory, model/vid2seq.py:78).
+//
+// One warp per row, float4 loads (row = D/128 float4 per lane), warp-shuffle reductions; grid = enough CTAs to cover
+// the SMs several times, grid-stride over rows.  Backward accumulates dw (and db) per warp in registers across its
+// rows, reduces across the CTA's warps in shared memory, then one atomicAdd per column per CTA.
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vc {
+
+constexpr int kMaxV4 = 8;  // D <= 1024
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct RowMap {  // destination row of logical row r: (r / rows_per_batch) * batch_stride + row_offset + r % rows_per_batch
+  int rows_per_batch, batch_stride, row_offset;
+  __device__ __forceinline__ long long operator()(int r) const {
+    return rows_per_batch > 0 ? (long long)(r / rows_per_batch) * batch_stride + row_offset + (r % rows_per_batch) : r;
+  }
+};
+
+template <bool LAYERNORM>
+__global__ void __launch_bounds__(256)
+norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, float* __restrict__ rstd_out,
+                float* __restrict__ mean_out, int M, int D, float eps, float out_scale, RowMap map) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D / 128;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps_total) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+    float4 v[kMaxV4];
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+      if (i < nv) {
+        v[i] = xr[lane + 32 * i];
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+        ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      }
+    }
+    float mean = 0.f, rstd;
+    if (LAYERNORM) {
+      mean = warp_sum(s) / D;
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < kMaxV4; ++i) {
+        if (i < nv) {
+          const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+          var += a * a + b * b + c * c + d * d;
+        }
+      }
+      rstd = rsqrtf(warp_sum(var) / D + eps);
+    } else {
+      rstd = rsqrtf(warp_sum(ss) / D + eps);
+    }
+    if (lane == 0) {
+      if (rstd_out) rstd_out[row] = rstd;
+      if (LAYERNORM && mean_out) mean_out[row] = mean;
+    }
+    const long long orow = map(row);
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+      if (i < nv) {
+        const int c = (lane + 32 * i) * 4;
+        const float4 wv = *reinterpret_cast<const float4*>(w + c);
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * wv.x; y.y = (v[i].y - mean) * rstd * wv.y;
+        y.z = (v[i].z - mean) * rstd * wv.z; y.w = (v[i].w - mean) * rstd * wv.w;
+        if (LAYERNORM) {
+          const float4 bv = *reinterpret_cast<const float4*>(bias + c);
+          y.x += bv.x; y.y += bv.y; y.z += bv.z; y.w += bv.w;
+        }
+        y.x *= out_scale; y.y *= out_scale; y.z *= out_scale; y.w *= out_scale;
+        if (out)
+          *reinterpret_cast<uint2*>(out + orow * D + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + orow * D + c) = y;
+      }
+    }
+  }
+}
+
+// Backward.  g = dL/dy (fp32, read through the same RowMap as the forward output), y = ((x-mean)*rstd*w + b)*scale.
+//   dxhat = g*w*scale;  dx = rstd*(dxhat - mean(dxhat) [LN only] - xhat*mean(dxhat*xhat));  dx_accum (+)= dx
+//   dw += sum_rows g*xhat*scale;  db += sum_rows g*scale
+template <bool LAYERNORM>
+__global__ void __launch_bounds__(256)
+norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
+                const float* __restrict__ rstd_in, const float* __restrict__ mean_in, float* __restrict__ dx,
+                int accumulate_dx, float* __restrict__ dw, float* __restrict__ db, int M, int D, float scale, RowMap map) {
+  __shared__ float red[8][kMaxV4 * 128 + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = D / 128;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  float4 dw_acc[kMaxV4], db_acc[kMaxV4];
+#pragma unroll
+  for (int i = 0; i < kMaxV4; ++i) { dw_acc[i] = make_float4(0, 0, 0, 0); db_acc[i] = make_float4(0, 0, 0, 0); }
+  for (int row = blockIdx.x * (blockDim.x >> 5) + warp; row < M; row += warps_total) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+    const float4* gr = reinterpret_cast<const float4*>(g + map(row) * D);
+    const float rstd = rstd_in[row];
+    const float mean = LAYERNORM ? mean_in[row] : 0.f;
+    float4 xh[kMaxV4], dh[kMaxV4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+      if (i < nv) {
+        const float4 xv = xr[lane + 32 * i];
+        const float4 gv = gr[lane + 32 * i];
+        const float4 wv = *reinterpret_cast<const float4*>(w + (lane + 32 * i) * 4);
+        xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd; xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
+        const float gx = gv.x * scale, gy = gv.y * scale, gz = gv.z * scale, gw = gv.w * scale;
+        dh[i].x = gx * wv.x; dh[i].y = gy * wv.y; dh[i].z = gz * wv.z; dh[i].w = gw * wv.w;
+        dw_acc[i].x += gx * xh[i].x; dw_acc[i].y += gy * xh[i].y; dw_acc[i].z += gz * xh[i].z; dw_acc[i].w += gw * xh[i].w;
+        if (LAYERNORM) { db_acc[i].x += gx; db_acc[i].y += gy; db_acc[i].z += gz; db_acc[i].w += gw; }
+        s1 += dh[i].x + dh[i].y + dh[i].z + dh[i].w;
+        s2 += dh[i].x * xh[i].x + dh[i].y * xh[i].y + dh[i].z * xh[i].z + dh[i].w * xh[i].w;
+      }
+    }
+    const float m1 = LAYERNORM ? warp_sum(s1) / D : 0.f;
+    const float m2 = warp_sum(s2) / D;
+    float4* dxr = reinterpret_cast<float4*>(dx + (long long)row * D);
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+      if (i < nv) {
+        float4 o;
+        o.x = rstd * (dh[i].x - m1 - xh[i].x * m2); o.y = rstd * (dh[i].y - m1 - xh[i].y * m2);
+        o.z = rstd * (dh[i].z - m1 - xh[i].z * m2); o.w = rstd * (dh[i].w - m1 - xh[i].w * m2);
+        if (accumulate_dx) {
+          const float4 old = dxr[lane + 32 * i];
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        dxr[lane + 32 * i] = o;
+      }
+    }
+  }
+  // cross-warp reduction of dw / db, then one atomic per column per CTA
+  for (int pass = 0; pass < (LAYERNORM ? 2 : 1); ++pass) {
+    if (pass == 1 && !db) break;
+    if (pass == 0 && !dw) continue;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+      if (i < nv) {
+        const float4 a = pass == 0 ? dw_acc[i] : db_acc[i];
+        float* dst = &red[warp][(lane + 32 * i) * 4];
+        dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+      }
+    }
+    __syncthreads();
+    float* target = pass == 0 ? dw : db;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) t += red[wv][c];
+      atomicAdd(target + c, t);
+    }
+  }
+}
+
+static int norm_grid(int M) {
+  const int blocks = (M + 7) / 8;
+  const int cap = num_sms() * 4;
+  return blocks < cap ? blocks : cap;
+}
+
+}  // namespace vc
+
+using namespace vc;
+
+extern "C" int vc_norm_fwd(int kind, const float* x, const float* w, const float* bias, void* out_bf16, float* out_f32,
+                           float* rstd, float* mean, int M, int D, float eps, float out_scale, int rows_per_batch,
+                           int out_batch_stride, int out_row_offset, void* stream) {
+  VC_CHECK(M > 0 && D > 0 && D % 128 == 0 && D <= 1024, "vc_norm_fwd: D=%d must be a multiple of 128 and <= 1024", D);
+  VC_CHECK(kind == 0 || kind == 1, "vc_norm_fwd: kind 0=rms 1=layernorm");
+  VC_CHECK(kind == 0 || bias != nullptr, "vc_norm_fwd: layernorm needs bias");
+  RowMap map{rows_per_batch, out_batch_stride, out_row_offset};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (kind == 0)
+    norm_fwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
+                                                         eps, out_scale, map);
+  else
+    norm_fwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
+                                                        eps, out_scale, map);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+extern "C" int vc_norm_bwd(int kind, const float* g, const float* x, const float* w, const float* rstd, const float* mean,
+                           float* dx, int accumulate_dx, float* dw, float* db, int M, int D, float scale,
+                           int rows_per_batch, int g_batch_stride, int g_row_offset, void* stream) {
+  VC_CHECK(M > 0 && D > 0 && D % 128 == 0 && D <= 1024, "vc_norm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
+  VC_CHECK(kind == 0 || kind == 1, "vc_norm_bwd: kind 0=rms 1=layernorm");
+  RowMap map{rows_per_batch, g_batch_stride, g_row_offset};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (kind == 0)
+    norm_bwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, accumulate_dx, dw, db, M, D, scale, map);
+  else
+    norm_bwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, accumulate_dx, dw, db, M, D, scale, map);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
