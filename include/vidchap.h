@@ -43,6 +43,7 @@ typedef struct vc_gemm_args {
   void* pre_out;
   const void* aux; int64_t ld_aux;
   float alpha;
+  const float* alpha_dev;   /* optional device scalar multiplied into alpha (upstream loss gradient) */
   int32_t splits;
   int32_t tile_n;   /* 0 = auto, else 64/128/256 */
 } vc_gemm_args;
@@ -68,6 +69,69 @@ typedef struct vc_attn_args {
   float scale;
 } vc_attn_args;
 int vc_attn_fwd(const vc_attn_args* args, void* stream);
+
+/* ---- Fused attention backward (autograd of the block above).  `fwd` repeats the forward arguments (fwd.out = O and
+ * fwd.lse2 as saved by the forward).  dout: bf16 dL/dO [B*Lq, ld_do], head h at cols do_col + 64h.  delta: scratch
+ * [B,H,Lq].  dq_acc: ZEROED fp32 [B*Lq, ld_dq] accumulated with atomics (head h at cols 64h).  dk/dv: bf16
+ * [B*Lk, ld], head h at cols d*_col + 64h (fully written).  dbias_rel: fp32 [H, Lq+Lk-1] accumulated with atomics
+ * (NULL when the bias is not a parameter); bucket_lut [Lq+Lk-1] lets tiles inside one bucket take a fast path. */
+typedef struct vc_attn_bwd_args {
+  vc_attn_args fwd;
+  const void* dout; int64_t ld_do; int32_t do_col;
+  float* delta;
+  float* dq_acc; int64_t ld_dq;
+  void* dk; int64_t ld_dk; int32_t dk_col;
+  void* dv; int64_t ld_dv; int32_t dv_col;
+  float* dbias_rel;
+  const int32_t* bucket_lut;
+} vc_attn_bwd_args;
+int vc_attn_bwd(const vc_attn_bwd_args* args, void* stream);
+
+/* ---- Normalisation.  kind 0: T5LayerNorm / RMS (modeling_t5.py:254-277, eps 1e-6, no bias); kind 1: nn.LayerNorm
+ * (vit.py:64,70,96, eps 1e-5).  x fp32 [M,D]; y = (xhat*w (+bias)) * out_scale written as bf16 (out_bf16) and/or fp32
+ * (out_f32) at row (r/rows_per_batch)*out_batch_stride + out_row_offset + r%rows_per_batch (rows_per_batch=0: row r).
+ * rstd (and mean for kind 1) [M] are saved for the backward. */
+int vc_norm_fwd(int kind, const float* x, const float* w, const float* bias, void* out_bf16, float* out_f32, float* rstd,
+                float* mean, int M, int D, float eps, float out_scale, int rows_per_batch, int out_batch_stride,
+                int out_row_offset, void* stream);
+/* g = dL/dy fp32, read through the same row map.  dx (+)= d/dx; dx_bf16 (optional) = bf16 copy of the final dx;
+ * dw/db accumulated with atomics (db only for kind 1; either may be NULL). */
+int vc_norm_bwd(int kind, const float* g, const float* x, const float* w, const float* rstd, const float* mean, float* dx,
+                void* dx_bf16, int accumulate_dx, float* dw, float* db, int M, int D, float scale, int rows_per_batch,
+                int g_batch_stride, int g_row_offset, void* stream);
+
+/* ---- Embedding (vid2seq.py:71, modeling_t5.py:972) and its scatter-add backward into the tied table. */
+int vc_embed_fwd(const int64_t* ids, const float* table, float* out, int n, int d, int V, void* stream);
+int vc_embed_bwd(const int64_t* ids, const float* dout, float* dtable, int n, int d, int V, void* stream);
+/* ---- labels = ids with pad->-100 (vid2seq.py:86-88); dec_in = shift_right(labels) (modeling_t5.py:845-868);
+ * n_valid[0] = number of non-pad targets. */
+int vc_prepare_targets(const int64_t* out_ids, int64_t* dec_in, int64_t* labels, float* n_valid, int B, int S,
+                       int64_t pad_id, void* stream);
+/* ---- out[h][r] = table[lut[r]][h] (modeling_t5.py:445-460 with lut = _relative_position_bucket :397-443 built on the
+ * host with the reference's exact ops) and its backward dtable[lut[r]][h] += drel[h][r]. */
+int vc_bias_expand(const float* table, const int32_t* lut, float* out, int H, int R, void* stream);
+int vc_bias_fold(const float* drel, const int32_t* lut, float* dtable, int H, int R, void* stream);
+/* ---- x + pos_embed with nearest interpolation when T != P (vit.py:119-127), and d(pos_embed). */
+int vc_add_pos(const float* x, const float* pos, float* out, int B, int T, int C, int P, void* stream);
+int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C, int P, void* stream);
+/* ---- F.cross_entropy(ignore_index=-100, label_smoothing) (modeling_t5.py:1721): loss_out[0] = mean over valid rows;
+ * dlogits (bf16, optional) = d loss / d logits for upstream gradient 1. */
+int vc_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, const float* n_valid, float smoothing,
+                     float* loss_out, void* dlogits_bf16, int64_t ldd, int n, int V, void* stream);
+/* ---- helpers: column sums (bias gradients), strided fp32->bf16 cast, row-block copy into the [video;text] memory. */
+int vc_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream);
+int vc_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int M, int N, float scale, void* stream);
+int vc_copy_rows_bf16(const void* src, void* dst, int B, int T, int C, int E, int row_off, void* stream);
+
+/* ---- Optimiser tail over the flat parameter buffer (dvc.py:112-126). */
+int vc_sumsq(const float* g, int64_t n, float* out_accum, void* stream);               /* out_accum[0] += |g|^2 */
+/* clip_grad_norm_ (coef from *norm_sq, skipped if clip_max_norm<=0 or norm_sq NULL) + torch.optim.Adam step +
+ * bf16 shadow re-pack, one pass.  grad_scale multiplies g first (1/world_size for data parallel averaging). */
+int vc_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int step, const float* norm_sq, float clip_max_norm, float grad_scale, void* stream);
+/* rows [V-num_bins, V) /= mean||rows|| / mean||rows [0, V-num_bins)||  (dvc.py:118-126); scratch2 = 2 floats. */
+int vc_renorm_time_tokens(float* w, void* w_bf16, int V, int d, int num_bins, float* scratch2, void* stream);
+int vc_cast_flat_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,266 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point vs the plain-torch restatement (oracle/torch_ops.py)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def gen(seed=0):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+# bf16 output rounding alone is ~1.7e-3 rel-L2; fp32 outputs should be ~1e-6.
+BF16_TOL, F32_TOL = 4e-3, 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,tile_n", [
+    (128, 64, 64, 0, 0, 64), (256, 256, 256, 0, 0, 256), (1600, 776, 768, 0, 0, 0), (1000, 2304, 768, 0, 0, 0),
+    (256, 256, 256, 0, 1, 256), (1001, 768, 3072, 0, 1, 0), (128, 128, 128, 1, 0, 128), (384, 512, 1000, 1, 1, 0),
+])
+def test_gemm_layouts(cuda_ops, torch_ops, M, N, K, a_mn, b_mn, tile_n):
+    g = gen(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    B = (torch.randn(N, K, generator=g) * 0.5).to(DEV).bfloat16()
+    A_st = A.t().contiguous() if a_mn else A
+    B_st = B.t().contiguous() if b_mn else B
+    for dt, tol in ((torch.float32, F32_TOL), (torch.bfloat16, BF16_TOL)):
+        out = torch.empty(M, N, device=DEV, dtype=dt)
+        ref = torch.empty(M, N, device=DEV, dtype=dt)
+        cuda_ops.gemm(A_st, B_st, out, a_mn=bool(a_mn), b_mn=bool(b_mn), tile_n=tile_n)
+        torch_ops.gemm(A_st, B_st, ref, a_mn=bool(a_mn), b_mn=bool(b_mn))
+        assert rel(out, ref) < tol
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3, 4])
+def test_gemm_epilogues(cuda_ops, torch_ops, act):
+    M, N, K = 520, 2048, 768
+    g = gen(act)
+    A = (torch.randn(M, K, generator=g) * 0.3).to(DEV).bfloat16()
+    B = (torch.randn(N, K, generator=g) * 0.3).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    resid = torch.randn(M, N, generator=g).to(DEV)
+    aux = torch.randn(M, N, generator=g).to(DEV).bfloat16()
+    adev = torch.tensor([0.7], device=DEV)
+    kw = dict(bias=bias, residual=resid, act=act, aux=aux if act >= 3 else None, alpha=0.5, alpha_dev=adev)
+    out = torch.empty(M, N, device=DEV)
+    ref = torch.empty(M, N, device=DEV)
+    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16) if act == 2 else None
+    pre_ref = torch.empty_like(pre) if act == 2 else None
+    cuda_ops.gemm(A, B, out, pre_out=pre, **kw)
+    torch_ops.gemm(A, B, ref, pre_out=pre_ref, **kw)
+    assert rel(out, ref) < 1e-4
+    if act == 2:
+        assert rel(pre, pre_ref) < BF16_TOL
+
+
+def test_gemm_splitk_atomic(cuda_ops, torch_ops):
+    M, N, K = 768, 3072, 4096  # wgrad-shaped: dW[N_out=768... reduction over tokens
+    g = gen(5)
+    A = (torch.randn(K, M, generator=g) * 0.3).to(DEV).bfloat16()
+    B = (torch.randn(K, N, generator=g) * 0.3).to(DEV).bfloat16()
+    out = torch.ones(M, N, device=DEV)
+    ref = torch.ones(M, N, device=DEV)
+    cuda_ops.gemm(A, B, out, a_mn=True, b_mn=True, atomic=True, splits=7)
+    torch_ops.gemm(A, B, ref, a_mn=True, b_mn=True, atomic=True)
+    assert rel(out, ref) < F32_TOL
+
+
+def _attn_case(B, H, Lq, Lk, causal, with_bias, with_mask, scale, self_attn, seed=0):
+    g = gen(seed)
+    inner = H * 64
+    if self_attn:
+        qkv = (torch.randn(B * Lq, 3 * inner, generator=g) * 0.5).to(DEV).bfloat16()
+        q = k = v = qkv
+        cols = dict(q_col=0, k_col=inner, v_col=2 * inner)
+    else:
+        q = (torch.randn(B * Lq, inner, generator=g) * 0.5).to(DEV).bfloat16()
+        k = v = (torch.randn(B * Lk, 2 * inner, generator=g) * 0.5).to(DEV).bfloat16()
+        cols = dict(q_col=0, k_col=0, v_col=inner)
+    bias = (torch.randn(H, Lq + Lk - 1, generator=g)).to(DEV) if with_bias else None
+    kmask = None
+    if with_mask:
+        lens = torch.randint(max(1, Lk // 2), Lk + 1, (B,), generator=g)
+        kmask = (torch.arange(Lk)[None, :] < lens[:, None]).to(torch.uint8).to(DEV)
+    return q, k, v, cols, bias, kmask
+
+
+ATTN_CASES = [
+    # B,H,Lq,Lk,causal,bias,mask,scale,self
+    (2, 12, 100, 100, False, False, False, 0.125, True),     # ViT
+    (2, 12, 1000, 1000, False, True, True, 1.0, True),       # T5 encoder
+    (2, 12, 256, 256, True, True, True, 1.0, True),          # T5 decoder self
+    (2, 12, 256, 1100, False, False, True, 1.0, False),      # cross
+    (1, 4, 37, 130, False, True, True, 1.0, False),          # ragged
+    (1, 2, 10, 10, False, False, False, 0.125, True),        # tiny (config 1 ViT)
+    (1, 2, 32, 32, True, True, False, 1.0, True),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attn_fwd(cuda_ops, torch_ops, case):
+    B, H, Lq, Lk, causal, wb, wm, scale, sa = case
+    q, k, v, cols, bias, kmask = _attn_case(B, H, Lq, Lk, causal, wb, wm, scale, sa)
+    out = torch.zeros(B * Lq, H * 64, device=DEV, dtype=torch.bfloat16)
+    ref = torch.zeros_like(out)
+    lse = torch.zeros(B, H, Lq, device=DEV)
+    lse_ref = torch.zeros_like(lse)
+    kw = dict(B=B, H=H, Lq=Lq, Lk=Lk, bias_rel=bias, kmask=kmask, causal=causal, scale=scale, **cols)
+    cuda_ops.attn_fwd(q, k, v, out=out, lse2=lse, **kw)
+    torch_ops.attn_fwd(q, k, v, out=ref, lse2=lse_ref, **kw)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 8e-3, rel(out, ref)
+    assert (lse - lse_ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attn_bwd(cuda_ops, torch_ops, case):
+    B, H, Lq, Lk, causal, wb, wm, scale, sa = case
+    q, k, v, cols, bias, kmask = _attn_case(B, H, Lq, Lk, causal, wb, wm, scale, sa, seed=3)
+    inner = H * 64
+    g = gen(11)
+    dout = (torch.randn(B * Lq, inner, generator=g) * 0.5).to(DEV).bfloat16()
+    out = torch.zeros(B * Lq, inner, device=DEV, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, Lq, device=DEV)
+    kw = dict(B=B, H=H, Lq=Lq, Lk=Lk, bias_rel=bias, kmask=kmask, causal=causal, scale=scale, **cols)
+    cuda_ops.attn_fwd(q, k, v, out=out, lse2=lse, **kw)
+    lut = None
+    if wb:
+        lut = (torch.arange(Lq + Lk - 1) // 7).to(torch.int32).to(DEV)  # any monotone bucketisation exercises both paths
+    res = []
+    for ops in (cuda_ops, torch_ops):
+        delta = torch.zeros(B, H, Lq, device=DEV)
+        dq = torch.zeros(B * Lq, inner, device=DEV)
+        dk = torch.zeros(B * Lk, 2 * inner, device=DEV, dtype=torch.bfloat16)
+        dv = dk
+        db = torch.zeros(H, Lq + Lk - 1, device=DEV) if wb else None
+        ops.attn_bwd(q, k, v, out=out, lse2=lse, dout=dout, do_col=0, delta=delta, dq_acc=dq, dk=dk, dk_col=0, dv=dv,
+                     dv_col=inner, dbias_rel=db, bucket_lut=lut, **kw)
+        res.append((dq, dk.clone(), db, delta))
+    torch.cuda.synchronize()
+    (dq, dkv, db, dl), (dq_r, dkv_r, db_r, dl_r) = res
+    assert rel(dl, dl_r) < 1e-4
+    assert rel(dq, dq_r) < 1.5e-2, rel(dq, dq_r)
+    assert rel(dkv, dkv_r) < 1.5e-2, rel(dkv, dkv_r)
+    if wb:
+        if lut is not None:  # compare in bucket space (the uniform-tile fast path only preserves bucket sums)
+            nb = int(lut.max().item()) + 1
+            f = torch.zeros(nb, H, device=DEV).index_add_(0, lut.long(), db.t().contiguous())
+            f_r = torch.zeros(nb, H, device=DEV).index_add_(0, lut.long(), db_r.t().contiguous())
+            assert rel(f, f_r) < 1.5e-2, rel(f, f_r)
+
+
+@pytest.mark.parametrize("kind,D", [(0, 768), (1, 768), (0, 1024), (0, 256)])
+def test_norms(cuda_ops, torch_ops, kind, D):
+    g = gen(kind + D)
+    B, L, T = 3, 50, 10
+    M = B * L
+    x = torch.randn(M, D, generator=g).to(DEV)
+    w = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(D, generator=g)).to(DEV) if kind else None
+    E = T + L
+    outs = []
+    for ops in (cuda_ops, torch_ops):
+        ob = torch.zeros(B * E, D, device=DEV, dtype=torch.bfloat16)
+        of = torch.zeros(B * E, D, device=DEV)
+        rstd = torch.zeros(M, device=DEV)
+        mean = torch.zeros(M, device=DEV)
+        ops.norm_fwd(kind, x, w, b, out_bf16=ob, out_f32=of, rstd=rstd, mean=mean, eps=1e-5 if kind else 1e-6,
+                     out_scale=0.5, rows_per_batch=L, out_batch_stride=E, out_row_offset=T)
+        gy = torch.randn(B * E, D, generator=gen(7)).to(DEV)
+        dx = torch.ones(M, D, device=DEV)
+        dxb = torch.zeros(M, D, device=DEV, dtype=torch.bfloat16)
+        dw = torch.zeros(D, device=DEV)
+        db = torch.zeros(D, device=DEV)
+        ops.norm_bwd(kind, gy, x, w, rstd, mean, dx=dx, dx_bf16=dxb, accumulate_dx=True, dw=dw, db=db if kind else None,
+                     scale=0.5, rows_per_batch=L, g_batch_stride=E, g_row_offset=T)
+        outs.append((ob, of, rstd, mean, dx, dxb, dw, db))
+    a, r = outs
+    assert rel(a[1], r[1]) < 1e-5 and rel(a[0], r[0]) < BF16_TOL and rel(a[2], r[2]) < 1e-5
+    assert rel(a[4], r[4]) < 1e-4 and rel(a[5], r[5]) < BF16_TOL and rel(a[6], r[6]) < 1e-4
+    if kind:
+        assert rel(a[7], r[7]) < 1e-4 and rel(a[3], r[3]) < 1e-4
+
+
+def test_small_ops(cuda_ops, torch_ops):
+    g = gen(3)
+    V, d, n = 1100, 768, 300
+    table = torch.randn(V, d, generator=g).to(DEV)
+    ids = torch.randint(0, V, (n,), generator=g).to(DEV)
+    B, S = 4, 33
+    oids = torch.randint(0, 5, (B, S), generator=g).to(DEV)
+    H, R = 12, 199
+    lut = torch.randint(0, 32, (R,), generator=g).to(torch.int32).to(DEV)
+    btab = torch.randn(32, H, generator=g).to(DEV)
+    drel = torch.randn(H, R, generator=g).to(DEV)
+    vid = torch.randn(B, 10, d, generator=g).to(DEV)
+    pos = torch.randn(1, 100, d, generator=g).to(DEV)
+    dvid = torch.randn(B * 10, d, generator=g).to(DEV)
+    xb = torch.randn(300, 520, generator=g).to(DEV).bfloat16()
+    res = []
+    for ops in (cuda_ops, torch_ops):
+        e = torch.zeros(n, d, device=DEV); ops.embed_fwd(ids, table, e)
+        dt = torch.zeros(V, d, device=DEV); ops.embed_bwd(ids, e, dt)
+        di = torch.zeros_like(oids); lb = torch.zeros_like(oids); nv = torch.zeros(1, device=DEV)
+        ops.prepare_targets(oids, di, lb, nv)
+        be = torch.zeros(H, R, device=DEV); ops.bias_expand(btab, lut, be)
+        bf = torch.zeros(32, H, device=DEV); ops.bias_fold(drel, lut, bf)
+        ap = torch.zeros_like(vid); ops.add_pos(vid, pos, ap, 100)
+        dp = torch.zeros(1, 100, d, device=DEV); ops.add_pos_bwd(dvid, dp, B, 10, d, 100)
+        cs = torch.zeros(520, device=DEV); ops.colsum_bf16(xb, cs)
+        cb = torch.zeros(n, 2 * d, device=DEV, dtype=torch.bfloat16); ops.cast_f32_bf16(e, cb[:, d:], 0.5)
+        mem = torch.zeros(B * 30, d, device=DEV, dtype=torch.bfloat16)
+        ops.copy_rows_bf16(cb[:B * 10, :d].contiguous(), mem, B, 10, d, 30, 5)
+        res.append((e, dt, di, lb, nv, be, bf, ap, dp, cs, cb, mem))
+    for i, (a, r) in enumerate(zip(*res)):
+        if a.dtype in (torch.int64,):
+            assert torch.equal(a, r), i
+        else:
+            assert rel(a, r) < 1e-5 or (a - r).abs().max() < 1e-6, (i, rel(a, r))
+
+
+def test_cross_entropy(cuda_ops, torch_ops):
+    g = gen(9)
+    n, V = 64, 32200
+    logits = (torch.randn(n, V, generator=g) * 3).to(DEV)
+    labels = torch.randint(0, V, (n,), generator=g).to(DEV)
+    labels[::5] = -100
+    nv = torch.tensor([float((labels != -100).sum())], device=DEV)
+    out = []
+    for ops in (cuda_ops, torch_ops):
+        loss = torch.zeros(1, device=DEV)
+        dl = torch.zeros(n, V, device=DEV, dtype=torch.bfloat16)
+        ops.cross_entropy(logits, labels, nv, 0.1, loss, dl)
+        out.append((loss, dl))
+    ref = torch.nn.functional.cross_entropy(logits, labels, ignore_index=-100, label_smoothing=0.1)
+    assert abs(out[0][0].item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert abs(out[1][0].item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert rel(out[0][1], out[1][1]) < BF16_TOL
+
+
+def test_optimizer_tail(cuda_ops, torch_ops):
+    g = gen(4)
+    n = 1100 * 768 + 4096
+    p0 = torch.randn(n, generator=g).to(DEV)
+    gr = (torch.randn(n, generator=g) * 0.01).to(DEV)
+    res = []
+    for ops in (cuda_ops, torch_ops):
+        p = p0.clone(); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+        pb = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+        for step in (1, 2, 3):
+            ns = torch.zeros(1, device=DEV)
+            ops.sumsq(gr, ns)
+            ops.adam_step(p, gr, m, v, pb, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, step=step, norm_sq=ns,
+                          clip_max_norm=0.1, grad_scale=0.5)
+        w = p[:1100 * 768].view(1100, 768)
+        ops.renorm_time_tokens(w, pb[:1100 * 768].view(1100, 768), 100, torch.zeros(2, device=DEV))
+        res.append((p, m, v, pb, ns))
+    for a, r in zip(*res):
+        assert rel(a, r) < 2e-5 if a.dtype == torch.float32 else rel(a, r) < BF16_TOL

@@ -1,0 +1,355 @@
+// Fused attention backward on tcgen05 (sm_100a), head_dim 64: dQ, dK, dV and the relative-position-bias gradient.
+//
+// Replaces autograd through modeling_t5.py:539-580 / vit.py:47-51.  Probabilities are recomputed from the saved
+// log-sum-exp (flash-attention style); nothing of size Lq x Lk touches HBM.
+//
+// One CTA = one (batch, head, 128-key tile), looping over the 128-query tiles that see it.  1 CTA / SM
+// (160 KB smem, 448 TMEM columns).  192 threads:
+//   warp 0 lane 0 : TMA: K,V tile once; (Q_i, dO_i) through a 2-stage ring
+//   warp 1        : TMEM alloc; lane 0 issues per query tile
+//                     S  = Q_i.K^T        dP = dO_i.V^T                       (128x128x64 each, fresh)
+//                     dV += P^T.dO_i      dK += dS^T.Q_i     dQ_i = dS.K      (accumulate / accumulate / fresh)
+//   warps 2..5    : thread = one query row: p = exp2(s2 - lse2), ds = p*(dP - delta); writes bf16 P and scale*dS tiles
+//                   (128B-swizzled; each tile serves as MN-major A for dV/dK and dS also as K-major A for dQ);
+//                   accumulates d(bias) by relative position in shared memory; reads dQ_i from TMEM and
+//                   atomically adds it to the fp32 dQ accumulator; finally stores dK, dV (bf16).
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vc {
+
+constexpr int kBT = 128, kBD = 64;
+constexpr float kBLog2e = 1.4426950408889634f;
+constexpr float kBMasked = -3.0e38f;
+
+struct AttnBwdParams {
+  int B, H, Lq, Lk;
+  int q_col, k_col, v_col, do_col;
+  const float* lse2;      // [B,H,Lq]
+  const float* delta;     // [B,H,Lq] rowsum(dO*O)
+  const float* bias_rel;  // [H][Lq+Lk-1] or null
+  const int* bucket_lut;  // [Lq+Lk-1] bucket id per relative position (uniform-tile test), or null
+  const uint8_t* kmask;   // [B][Lk] or null
+  int causal;
+  float scale, scale_log2e;
+  float* dq_acc;          // fp32 [B*Lq][ld_dq], head h at cols 64h   (atomicAdd)
+  long long ld_dq;
+  __nv_bfloat16* dk; long long ld_dk; int dk_col;  // bf16 [B*Lk][ld], head h at cols dk_col + 64h
+  __nv_bfloat16* dv; long long ld_dv; int dv_col;
+  float* dbias_rel;       // fp32 [H][Lq+Lk-1] (atomicAdd) or null
+};
+
+constexpr int kBwdSmemTiles = 16384 * 2 /*K,V*/ + 2 * 16384 /*Q ring*/ + 2 * 16384 /*dO ring*/ + 32768 /*P*/ + 32768 /*dS*/;
+constexpr int kBwdRelMax = 2304;  // floats of d(bias) scratch: Lq + 128 <= 2304
+constexpr int kAttnBwdSmem = kBwdSmemTiles + kBwdRelMax * 4 + 256;
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + 16384;
+  uint8_t* sQ = sV + 16384;        // [2]
+  uint8_t* sDO = sQ + 2 * 16384;   // [2]
+  uint8_t* sP = sDO + 2 * 16384;   // 32 KB
+  uint8_t* sDS = sP + 32768;       // 32 KB
+  float* s_rel = reinterpret_cast<float*>(sDS + 32768);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rel + kBwdRelMax);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qd_full = bars + 1;   // [2]
+  uint64_t* qd_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint64_t* dq_read = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = kt * kBT;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) __trap();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_read, 128);
+    fence_barrier_init();
+  }
+  const int n_rel = p.Lq + kBT;  // relative positions touched by this CTA: (k - q + Lq - 1) - rel_base in [0, Lq+127)
+  const int rel_base = k0;       // slot = (k - k0) + (Lq - 1 - q)
+  if (p.dbias_rel)
+    for (int i = threadIdx.x; i < n_rel; i += blockDim.x) s_rel[i] = 0.f;
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
+
+  const int nqt_all = (p.Lq + kBT - 1) / kBT;
+  const int qt0 = p.causal ? min(kt, nqt_all) : 0;  // causal: query tiles before the key tile see nothing of it
+  const int nqt = nqt_all - qt0;
+
+  if (warp == 0 && lane == 0) {
+    mbar_arrive_expect_tx(kv_full, 32768);
+    tma_load_3d(sK, &tmK, kv_full, p.k_col + h * kBD, k0, b);
+    tma_load_3d(sV, &tmV, kv_full, p.v_col + h * kBD, k0, b);
+    for (int i = 0; i < nqt; ++i) {
+      const int st = i & 1;
+      mbar_wait(&qd_empty[st], ((i >> 1) & 1) ^ 1);
+      mbar_arrive_expect_tx(&qd_full[st], 32768);
+      tma_load_3d(sQ + st * 16384, &tmQ, &qd_full[st], p.q_col + h * kBD, (qt0 + i) * kBT, b);
+      tma_load_3d(sDO + st * 16384, &tmDO, &qd_full[st], p.do_col + h * kBD, (qt0 + i) * kBT, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);   // S, dP : A K-major, B K-major, N=128
+    constexpr uint32_t id_t = make_idesc_bf16(128, 64, 1, 1);    // dV, dK: A MN-major (P^T / dS^T), B MN-major, N=64
+    constexpr uint32_t id_q = make_idesc_bf16(128, 64, 0, 1);    // dQ    : A K-major (dS), B MN-major (K), N=64
+    mbar_wait(kv_full, 0);
+    const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK), 0, 1024);
+    const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 0, 1024);
+    for (int i = 0; i < nqt; ++i) {
+      const int st = i & 1;
+      mbar_wait(&qd_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + st * 16384), 0, 1024);
+      const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sDO + st * 16384), 0, 1024);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc_mma_bf16(tS, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), id_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc_mma_bf16(tDP, dodesc + (uint64_t)(k * 2), vdesc + (uint64_t)(k * 2), id_s, k > 0);
+      tc_commit(s_full);
+      mbar_wait(pds_full, i & 1);
+      if (i > 0) mbar_wait(dq_read, (i - 1) & 1);
+      tc_fence_after();
+      // MN-major A over the [q rows][kv cols] tiles: 2 atoms of 64 kv (LBO = 16384), 8-row groups 1024 B, +2048 B per 16 q.
+      const uint64_t pT = make_smem_desc_sw128(smem_u32(sP), 16384, 1024);
+      const uint64_t dsT = make_smem_desc_sw128(smem_u32(sDS), 16384, 1024);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tc_mma_bf16(tDV, pT + (uint64_t)(k * 128), dodesc + (uint64_t)(k * 128), id_t, (i > 0 || k > 0));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tc_mma_bf16(tDK, dsT + (uint64_t)(k * 128), qdesc + (uint64_t)(k * 128), id_t, (i > 0 || k > 0));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint64_t dsK = make_smem_desc_sw128(smem_u32(sDS + (k >> 2) * 16384) + (k & 3) * 32, 0, 1024);
+        tc_mma_bf16(tDQ, dsK, kdesc + (uint64_t)(k * 128), id_q, k > 0);
+      }
+      tc_commit(&qd_empty[st]);
+      tc_commit(dq_full);
+    }
+  } else if (warp >= 2) {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint8_t* mrow = p.kmask ? p.kmask + (long long)b * p.Lk : nullptr;
+    for (int i = 0; i < nqt; ++i) {
+      const int q0 = (qt0 + i) * kBT;
+      const int q = q0 + r;
+      const bool q_ok = q < p.Lq;
+      const long long stat_idx = ((long long)b * p.H + h) * p.Lq + (q_ok ? q : 0);
+      const float lse2 = p.lse2[stat_idx];
+      const float delta = p.delta[stat_idx];
+      const float* brow = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) + (p.Lq - 1 - q) : nullptr;
+      // d(bias): is the whole tile inside one bucket?  then one add per row instead of one per element
+      bool uniform = false;
+      if (p.dbias_rel && p.bucket_lut) {
+        const int rel_lo = max(k0 - (q0 + kBT - 1) + p.Lq - 1, 0);
+        const int rel_hi = min(k0 + kBT - 1 - q0 + p.Lq - 1, p.Lq + p.Lk - 2);
+        uniform = (p.bucket_lut[rel_lo] == p.bucket_lut[rel_hi]);
+      }
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      float ds_rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float sv[32], dp[32];
+        tmem_ld32(tS + lane_off + c * 32, sv);
+        tmem_ld32(tDP + lane_off + c * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int k = k0 + c * 32 + j;
+          float s2 = sv[j] * p.scale_log2e;
+          if (brow && k < p.Lk) s2 += __ldg(brow + k) * kBLog2e;
+          const bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[k]);
+          s2 = masked ? kBMasked : s2;
+          const float pj = (q_ok && k < p.Lk) ? fast_exp2(s2 - lse2) : 0.0f;
+          const float dsj = pj * (dp[j] - delta);
+          sv[j] = pj;
+          dp[j] = dsj;
+        }
+        if (p.dbias_rel) {
+          if (uniform) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ds_rowsum += dp[j];
+          } else if (q_ok) {
+            float* slot = s_rel + (c * 32) + (p.Lq - 1 - q);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(slot + j, dp[j]);
+          }
+        }
+        uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
+        uint8_t* drow = sDS + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int ch = (((c & 1) * 4 + g) ^ (r & 7)) * 16;
+          *reinterpret_cast<uint4*>(prow + ch) =
+              make_uint4(pack_bf16x2(sv[g * 8 + 0], sv[g * 8 + 1]), pack_bf16x2(sv[g * 8 + 2], sv[g * 8 + 3]),
+                         pack_bf16x2(sv[g * 8 + 4], sv[g * 8 + 5]), pack_bf16x2(sv[g * 8 + 6], sv[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(drow + ch) =
+              make_uint4(pack_bf16x2(dp[g * 8 + 0] * p.scale, dp[g * 8 + 1] * p.scale),
+                         pack_bf16x2(dp[g * 8 + 2] * p.scale, dp[g * 8 + 3] * p.scale),
+                         pack_bf16x2(dp[g * 8 + 4] * p.scale, dp[g * 8 + 5] * p.scale),
+                         pack_bf16x2(dp[g * 8 + 6] * p.scale, dp[g * 8 + 7] * p.scale));
+        }
+      }
+      if (p.dbias_rel && uniform && q_ok) atomicAdd(s_rel + (p.Lq - 1 - q), ds_rowsum);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+      // ---- dQ_i: TMEM -> fp32 atomics
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld32(tDQ + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (q_ok) {
+          float4* dst = reinterpret_cast<float4*>(p.dq_acc + ((long long)b * p.Lq + q) * p.ld_dq + h * kBD + c * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) atomicAdd(dst + g, make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_read);
+    }
+    // ---- dV, dK: rows = keys of this tile.  (The last dq_full wait above also covers the final dV/dK MMAs.)
+    const int kk = k0 + r;
+    if (nqt > 0) {
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
+        const long long ld = which == 0 ? p.ld_dv : p.ld_dk;
+        const int col = which == 0 ? p.dv_col : p.dk_col;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+          tmem_ld32((which == 0 ? tDV : tDK) + lane_off + c * 32, v);
+          tmem_ld_wait();
+          if (kk < p.Lk) {
+            uint4* dst = reinterpret_cast<uint4*>(base + ((long long)b * p.Lk + kk) * ld + col + h * kBD + c * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              dst[g] = make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                  pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+          }
+        }
+      }
+    } else if (kk < p.Lk) {  // no query tile sees this key tile: zero gradients
+      for (int which = 0; which < 2; ++which) {
+        __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
+        const long long ld = which == 0 ? p.ld_dv : p.ld_dk;
+        const int col = which == 0 ? p.dv_col : p.dk_col;
+        uint4* dst = reinterpret_cast<uint4*>(base + ((long long)b * p.Lk + kk) * ld + col + h * kBD);
+        for (int g = 0; g < 8; ++g) dst[g] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.dbias_rel) {
+    float* dst = p.dbias_rel + (long long)h * (p.Lq + p.Lk - 1) + rel_base;
+    const int lim = p.Lq + p.Lk - 1 - rel_base;
+    for (int i = threadIdx.x; i < n_rel && i < lim; i += blockDim.x) {
+      const float g = s_rel[i];
+      if (g != 0.f) atomicAdd(dst + i, g);
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (the "D" term of the softmax backward)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout, long long lddo,
+                  int do_col, float* __restrict__ delta, int B, int H, int Lq) {
+  // one warp per (row, 4 heads at a time): lane handles 8 consecutive elements of a 256-wide slab
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)B * Lq) return;
+  const int b = (int)(row / Lq), q = (int)(row % Lq);
+  for (int h0 = 0; h0 < H; h0 += 4) {
+    const int col = h0 * 64 + lane * 8;
+    float s = 0.f;
+    if (col < H * 64) {
+      const uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + col);
+      const uint4 g = *reinterpret_cast<const uint4*>(dout + row * lddo + do_col + col);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s += bf16_lo(aw[e]) * bf16_lo(gw[e]) + bf16_hi(aw[e]) * bf16_hi(gw[e]);
+    }
+    // reduce over the 8 lanes that share a head
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const int hh = h0 + (lane >> 3);
+    if ((lane & 7) == 0 && hh < H) delta[((long long)b * H + hh) * Lq + q] = s;
+  }
+}
+
+}  // namespace vc
+
+using namespace vc;
+
+extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
+  VC_CHECK(a != nullptr, "vc_attn_bwd: null args");
+  const vc_attn_args* f = &a->fwd;
+  VC_CHECK(f->B > 0 && f->H > 0 && f->Lq > 0 && f->Lk > 0 && f->head_dim == 64, "vc_attn_bwd: bad dims");
+  VC_CHECK(f->Lq + kBT <= kBwdRelMax, "vc_attn_bwd: Lq=%d too long for the d(bias) scratch", f->Lq);
+  VC_CHECK(f->lse2 && a->delta && a->dq_acc && a->dk && a->dv && a->dout, "vc_attn_bwd: null buffers");
+  VC_CHECK(a->ld_dq % 4 == 0 && a->ld_dk % 8 == 0 && a->ld_dv % 8 == 0 && a->ld_do % 8 == 0, "vc_attn_bwd: strides");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // delta = rowsum(dO * O)
+  {
+    const long long rows = (long long)f->B * f->Lq;
+    attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)f->out, f->ldo,
+                                                                 (const __nv_bfloat16*)a->dout, a->ld_do, a->do_col,
+                                                                 a->delta, f->B, f->H, f->Lq);
+    VC_CUDA(cudaGetLastError());
+  }
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  int s;
+  if ((s = make_tmap_3d(&tmQ, f->q, f->ldq, f->Lq, f->B, f->ldq, (uint64_t)f->Lq * f->ldq, 64, kBT)) != VC_OK) return s;
+  if ((s = make_tmap_3d(&tmK, f->k, f->ldk, f->Lk, f->B, f->ldk, (uint64_t)f->Lk * f->ldk, 64, kBT)) != VC_OK) return s;
+  if ((s = make_tmap_3d(&tmV, f->v, f->ldv, f->Lk, f->B, f->ldv, (uint64_t)f->Lk * f->ldv, 64, kBT)) != VC_OK) return s;
+  if ((s = make_tmap_3d(&tmDO, a->dout, a->ld_do, f->Lq, f->B, a->ld_do, (uint64_t)f->Lq * a->ld_do, 64, kBT)) != VC_OK) return s;
+  AttnBwdParams p;
+  p.B = f->B; p.H = f->H; p.Lq = f->Lq; p.Lk = f->Lk;
+  p.q_col = f->q_col; p.k_col = f->k_col; p.v_col = f->v_col; p.do_col = a->do_col;
+  p.lse2 = f->lse2; p.delta = a->delta; p.bias_rel = f->bias_rel; p.bucket_lut = a->bucket_lut; p.kmask = f->kmask;
+  p.causal = f->causal; p.scale = f->scale; p.scale_log2e = f->scale * kBLog2e;
+  p.dq_acc = a->dq_acc; p.ld_dq = a->ld_dq;
+  p.dk = (__nv_bfloat16*)a->dk; p.ld_dk = a->ld_dk; p.dk_col = a->dk_col;
+  p.dv = (__nv_bfloat16*)a->dv; p.ld_dv = a->ld_dv; p.dv_col = a->dv_col;
+  p.dbias_rel = a->dbias_rel;
+  static bool attr = false;
+  if (!attr) {
+    VC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
+    attr = true;
+  }
+  dim3 grid((f->Lk + kBT - 1) / kBT, f->H, f->B);
+  attn_bwd_kernel<<<grid, 192, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, p);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}

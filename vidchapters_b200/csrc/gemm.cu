@@ -42,6 +42,7 @@ struct GemmParams {
   const __nv_bfloat16* aux;  // bf16 [M][ld_aux] for act 3/4
   long long ld_aux;
   float alpha;
+  const float* alpha_dev;  // optional device scalar multiplied into alpha
 };
 
 template <int BN>
@@ -180,6 +181,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
+      const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
@@ -189,7 +191,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (row_ok && col0 < p.N) {
           const int ncols = min(32, p.N - col0);  // N is a multiple of 8 (checked on host)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          for (int j = 0; j < 32; ++j) v[j] *= alpha;
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
@@ -330,6 +332,7 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   p.pre_out = reinterpret_cast<__nv_bfloat16*>(a->pre_out);
   p.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux); p.ld_aux = a->ld_aux;
   p.alpha = a->alpha;
+  p.alpha_dev = a->alpha_dev;
 
   CUtensorMap tmA, tmB;
   int s;

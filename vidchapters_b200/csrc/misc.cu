@@ -1,0 +1,312 @@
+// Small HBM-bound kernels of the Vid2Seq step: embedding gather / scatter-add, target preparation, relative-position
+// bias expansion, positional-embedding add, label-smoothed cross-entropy (+ its gradient), column sums, casts.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vc {
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- embedding gather: out[i,:] = table[ids[i],:]   (model/vid2seq.py:71, modeling_t5.py:972)
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                                       float* __restrict__ out, int n, int d, int V) {
+  const int lane = threadIdx.x & 31;
+  const int wt = gridDim.x * (blockDim.x >> 5);
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += wt) {
+    long long id = ids[i];
+    if (id < 0 || id >= V) id = 0;
+    const float4* src = reinterpret_cast<const float4*>(table + id * d);
+    float4* dst = reinterpret_cast<float4*>(out + (long long)i * d);
+    for (int c = lane; c < d / 4; c += 32) dst[c] = __ldg(src + c);
+  }
+}
+// ---- embedding backward: dtable[ids[i],:] += dout[i,:]   (autograd of nn.Embedding; tied table)
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dout,
+                                                       float* __restrict__ dtable, int n, int d, int V) {
+  const int lane = threadIdx.x & 31;
+  const int wt = gridDim.x * (blockDim.x >> 5);
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += wt) {
+    long long id = ids[i];
+    if (id < 0 || id >= V) continue;
+    const float4* src = reinterpret_cast<const float4*>(dout + (long long)i * d);
+    float4* dst = reinterpret_cast<float4*>(dtable + id * d);
+    for (int c = lane; c < d / 4; c += 32) atomicAdd(dst + c, src[c]);
+  }
+}
+
+// ---- targets: labels = ids (pad -> -100) (vid2seq.py:86-88); dec_in = shift_right(labels) (modeling_t5.py:845-868);
+//      n_valid = #labels != -100 (denominator of F.cross_entropy's mean, modeling_t5.py:1721)
+__global__ void prepare_targets_kernel(const long long* __restrict__ out_ids, long long* __restrict__ dec_in,
+                                       long long* __restrict__ labels, float* __restrict__ n_valid, int B, int S,
+                                       long long pad_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int valid = 0;
+  if (i < B * S) {
+    const int s = i % S;
+    const long long id = out_ids[i];
+    labels[i] = (id == pad_id) ? -100 : id;
+    valid = (id != pad_id);
+    long long prev = 0;  // decoder_start_token_id = 0
+    if (s > 0) {
+      prev = out_ids[i - 1];
+      if (prev == pad_id) prev = 0;  // -100 -> pad_token_id (=0)
+    }
+    dec_in[i] = prev;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, valid);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_valid, (float)__popc(bal));
+}
+
+// ---- relative position bias: out[h][r] = table[lut[r]][h]   (modeling_t5.py:445-460; lut = bucket of r-(Lq-1))
+__global__ void bias_expand_kernel(const float* __restrict__ table, const int* __restrict__ lut, float* __restrict__ out,
+                                   int H, int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H * R) {
+    const int h = i / R, r = i % R;
+    out[i] = table[lut[r] * H + h];
+  }
+}
+// backward: dtable[lut[r]][h] += drel[h][r]
+__global__ void bias_fold_kernel(const float* __restrict__ drel, const int* __restrict__ lut, float* __restrict__ dtable,
+                                 int H, int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H * R) {
+    const int h = i / R, r = i % R;
+    const float g = drel[i];
+    if (g != 0.0f) atomicAdd(dtable + lut[r] * H + h, g);
+  }
+}
+
+// ---- x + pos_embed (model/vit.py:119-127; nearest interpolation when T != num_features)
+__global__ void add_pos_kernel(const float* __restrict__ x, const float* __restrict__ pos, float* __restrict__ out, int B,
+                               int T, int C, int P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  const long long total = (long long)B * T * C / 4;
+  if (i < total) {
+    const int c4 = (int)(i % (C / 4));
+    const int t = (int)((i / (C / 4)) % T);
+    const int src_t = (T == P) ? t : (int)floorf((float)t * ((float)P / (float)T));
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 b = __ldg(reinterpret_cast<const float4*>(pos) + (long long)src_t * (C / 4) + c4);
+    reinterpret_cast<float4*>(out)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+__global__ void add_pos_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B, int T, int C, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over T*C
+  if (i < T * C) {
+    const int t = i / C, c = i % C;
+    const int src_t = (T == P) ? t : (int)floorf((float)t * ((float)P / (float)T));
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dx[((long long)b * T + t) * C + c];
+    atomicAdd(dpos + src_t * C + c, s);
+  }
+}
+
+// ---- label-smoothed cross entropy over fp32 logits (modeling_t5.py:1721: F.cross_entropy(ignore_index=-100,
+//      label_smoothing=eps), mean over valid rows) and its gradient (w.r.t. logits, for upstream grad 1):
+//      loss_row = (1-eps)*(lse - z_y) + eps*(lse - mean_c z_c);  dz_c = (softmax_c - (1-eps)[c==y] - eps/V) / n_valid
+__global__ void __launch_bounds__(256)
+cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
+                     const float* __restrict__ n_valid_p, float eps, float* __restrict__ loss_out,
+                     __nv_bfloat16* __restrict__ dlogits, long long ldd, int V) {
+  __shared__ float red[8];
+  __shared__ float bcast[2];
+  const int row = blockIdx.x;
+  const long long y = labels[row];
+  const float* z = logits + (long long)row * ld;
+  __nv_bfloat16* dz = dlogits ? dlogits + (long long)row * ldd : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (y < 0) {  // ignore_index: zero gradient row
+    if (dz) for (int c = tid * 8; c < V; c += 256 * 8) *reinterpret_cast<uint4*>(dz + c) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  float mx = -INFINITY;
+  for (int c = tid * 4; c < V; c += 256 * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(z + c);
+    mx = fmaxf(fmaxf(fmaxf(mx, v.x), fmaxf(v.y, v.z)), v.w);
+  }
+  mx = warp_max_f(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) { float m = red[0]; for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]); bcast[0] = m; }
+  __syncthreads();
+  mx = bcast[0];
+  float se = 0.f, sz = 0.f;
+  for (int c = tid * 4; c < V; c += 256 * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(z + c);
+    se += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+    sz += v.x + v.y + v.z + v.w;
+  }
+  se = warp_sum_f(se); sz = warp_sum_f(sz);
+  __syncthreads();
+  if (lane == 0) red[warp] = se;
+  __syncthreads();
+  if (tid == 0) { float s = 0; for (int i = 0; i < 8; ++i) s += red[i]; bcast[0] = s; }
+  __syncthreads();
+  se = bcast[0];
+  __syncthreads();
+  if (lane == 0) red[warp] = sz;
+  __syncthreads();
+  if (tid == 0) { float s = 0; for (int i = 0; i < 8; ++i) s += red[i]; bcast[1] = s; }
+  __syncthreads();
+  sz = bcast[1];
+  const float lse = mx + logf(se);
+  const float nv = *n_valid_p;
+  if (tid == 0) {
+    const float nll = lse - z[y];
+    const float smooth = lse - sz / (float)V;
+    atomicAdd(loss_out, ((1.0f - eps) * nll + eps * smooth) / nv);
+  }
+  if (dz) {
+    const float inv_nv = 1.0f / nv, inv_se = 1.0f / se, sm = eps / (float)V;
+    for (int c = tid * 8; c < V; c += 256 * 8) {
+      const float4 a = *reinterpret_cast<const float4*>(z + c);
+      const float4 b = *reinterpret_cast<const float4*>(z + c + 4);
+      float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        g[j] = (__expf(g[j] - mx) * inv_se - sm - ((c + j) == y ? (1.0f - eps) : 0.0f)) * inv_nv;
+      }
+      *reinterpret_cast<uint4*>(dz + c) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                                                     pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+    }
+  }
+}
+
+// ---- column sums of a bf16 matrix (bias gradients of the ViT Linears): out[n] += sum_m x[m][n]
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+                                                         float* __restrict__ out, int M, int N, int rows_per_block) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  if (c < N) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += __bfloat162float(x[(long long)r * ld + c]);
+    atomicAdd(out + c, s);
+  }
+}
+
+// ---- fp32 -> bf16 cast with independent row strides (e.g. dQ accumulator -> the q columns of the dQKV matrix)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                                     long long ldd, int M, int N, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // index over M * N/4
+  const int n4 = N / 4;
+  if (i < (long long)M * n4) {
+    const int r = (int)(i / n4), c = (int)(i % n4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * lds + c);
+    *reinterpret_cast<uint2*>(dst + (long long)r * ldd + c) =
+        make_uint2(pack_bf16x2(v.x * scale, v.y * scale), pack_bf16x2(v.z * scale, v.w * scale));
+  }
+}
+
+// ---- copy a bf16 [B,T,C] tensor into rows [row_off, row_off+T) of every batch of a [B,E,C] tensor (memory concat)
+__global__ void copy_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int T,
+                                      int C, int E, int row_off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // uint4 (8 elems) index
+  const int c8 = C / 8;
+  if (i < (long long)B * T * c8) {
+    const int c = (int)(i % c8);
+    const int t = (int)((i / c8) % T);
+    const int b = (int)(i / ((long long)c8 * T));
+    reinterpret_cast<uint4*>(dst)[((long long)b * E + row_off + t) * c8 + c] = reinterpret_cast<const uint4*>(src)[i];
+  }
+}
+
+static inline int cap_grid(long long blocks) {
+  const long long cap = (long long)num_sms() * 8;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+}  // namespace vc
+
+using namespace vc;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int vc_embed_fwd(const int64_t* ids, const float* table, float* out, int n, int d, int V, void* stream) {
+  VC_CHECK(n > 0 && d % 4 == 0, "vc_embed_fwd: bad dims");
+  embed_fwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, table, out, n, d, V);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_embed_bwd(const int64_t* ids, const float* dout, float* dtable, int n, int d, int V, void* stream) {
+  VC_CHECK(n > 0 && d % 4 == 0, "vc_embed_bwd: bad dims");
+  embed_bwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, dout, dtable, n, d, V);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_prepare_targets(const int64_t* out_ids, int64_t* dec_in, int64_t* labels, float* n_valid, int B, int S,
+                                  int64_t pad_id, void* stream) {
+  VC_CHECK(B > 0 && S > 0, "vc_prepare_targets: bad dims");
+  VC_CUDA(cudaMemsetAsync(n_valid, 0, sizeof(float), ST(stream)));
+  prepare_targets_kernel<<<(B * S + 255) / 256, 256, 0, ST(stream)>>>((const long long*)out_ids, (long long*)dec_in,
+                                                                     (long long*)labels, n_valid, B, S, pad_id);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_bias_expand(const float* table, const int32_t* lut, float* out, int H, int R, void* stream) {
+  bias_expand_kernel<<<(H * R + 255) / 256, 256, 0, ST(stream)>>>(table, lut, out, H, R);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_bias_fold(const float* drel, const int32_t* lut, float* dtable, int H, int R, void* stream) {
+  bias_fold_kernel<<<(H * R + 255) / 256, 256, 0, ST(stream)>>>(drel, lut, dtable, H, R);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_add_pos(const float* x, const float* pos, float* out, int B, int T, int C, int P, void* stream) {
+  VC_CHECK(C % 4 == 0, "vc_add_pos: C must be x4");
+  const long long total = (long long)B * T * C / 4;
+  add_pos_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(x, pos, out, B, T, C, P);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C, int P, void* stream) {
+  add_pos_bwd_kernel<<<(T * C + 255) / 256, 256, 0, ST(stream)>>>(dx, dpos, B, T, C, P);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, const float* n_valid, float smoothing,
+                                float* loss_out, void* dlogits_bf16, int64_t ldd, int n, int V, void* stream) {
+  VC_CHECK(n > 0 && V % 8 == 0 && ld % 4 == 0 && ldd % 8 == 0, "vc_cross_entropy: V/ld alignment");
+  VC_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ST(stream)));
+  cross_entropy_kernel<<<n, 256, 0, ST(stream)>>>(logits, ld, (const long long*)labels, n_valid, smoothing, loss_out,
+                                                  (__nv_bfloat16*)dlogits_bf16, ldd, V);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream) {
+  const int rpb = 64;
+  dim3 grid((N + 255) / 256, (M + rpb - 1) / rpb);
+  colsum_bf16_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, ld, out, M, N, rpb);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int M, int N, float scale,
+                                void* stream) {
+  VC_CHECK(N % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "vc_cast_f32_bf16: alignment");
+  const long long total = (long long)M * (N / 4);
+  cast_f32_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(src, lds, (__nv_bfloat16*)dst, ldd, M, N,
+                                                                               scale);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_copy_rows_bf16(const void* src, void* dst, int B, int T, int C, int E, int row_off, void* stream) {
+  VC_CHECK(C % 8 == 0, "vc_copy_rows_bf16: C must be x8");
+  const long long total = (long long)B * T * (C / 8);
+  copy_rows_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>((const __nv_bfloat16*)src,
+                                                                                (__nv_bfloat16*)dst, B, T, C, E, row_off);
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}

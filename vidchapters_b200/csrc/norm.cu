@@ -99,7 +99,8 @@ template <bool LAYERNORM>
 __global__ void __launch_bounds__(256)
 norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ rstd_in, const float* __restrict__ mean_in, float* __restrict__ dx,
-                int accumulate_dx, float* __restrict__ dw, float* __restrict__ db, int M, int D, float scale, RowMap map) {
+                __nv_bfloat16* __restrict__ dx_bf16, int accumulate_dx, float* __restrict__ dw, float* __restrict__ db,
+                int M, int D, float scale, RowMap map) {
   __shared__ float red[8][kMaxV4 * 128 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = D / 128;
@@ -143,6 +144,9 @@ norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const 
           o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
         }
         dxr[lane + 32 * i] = o;
+        if (dx_bf16)
+          *reinterpret_cast<uint2*>(dx_bf16 + (long long)row * D + (lane + 32 * i) * 4) =
+              make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
     }
   }
@@ -199,16 +203,16 @@ extern "C" int vc_norm_fwd(int kind, const float* x, const float* w, const float
 }
 
 extern "C" int vc_norm_bwd(int kind, const float* g, const float* x, const float* w, const float* rstd, const float* mean,
-                           float* dx, int accumulate_dx, float* dw, float* db, int M, int D, float scale,
+                           float* dx, void* dx_bf16, int accumulate_dx, float* dw, float* db, int M, int D, float scale,
                            int rows_per_batch, int g_batch_stride, int g_row_offset, void* stream) {
   VC_CHECK(M > 0 && D > 0 && D % 128 == 0 && D <= 1024, "vc_norm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
   VC_CHECK(kind == 0 || kind == 1, "vc_norm_bwd: kind 0=rms 1=layernorm");
   RowMap map{rows_per_batch, g_batch_stride, g_row_offset};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (kind == 0)
-    norm_bwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, accumulate_dx, dw, db, M, D, scale, map);
+    norm_bwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map);
   else
-    norm_bwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, accumulate_dx, dw, db, M, D, scale, map);
+    norm_bwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

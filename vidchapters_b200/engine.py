@@ -1,0 +1,561 @@
+"""Host orchestration of the Vid2Seq train step over the op table (vidchapters_b200.ops.CudaOps).
+
+This is the Python "host code calling hand-written sm_100a CUDA through a thin C-ABI extension" of BASELINE.json's
+north_star: every arithmetic step below is one call into libvidchap.so; torch is used for device memory (torch.empty),
+streams and integer/mask plumbing only.
+
+Reference call graph being replaced (paths under /root/reference):
+  model/vid2seq.py:58-98   Vid2Seq.forward            -> Vid2SeqEngine.forward
+  model/vit.py:117-133     VisionTransformer.forward  -> _vit_fwd / _vit_bwd
+  model/modeling_t5.py:930-1138 T5Stack.forward       -> _enc_fwd / _dec_fwd (+ _bwd)
+  model/modeling_t5.py:1587-1738 lm_head + CE         -> _head_fwd / _head_bwd
+  autograd backward of all of the above (dvc.py:113)  -> Vid2SeqEngine.backward
+  dvc.py:114-126 clip / Adam / time-token renorm      -> Vid2SeqEngine.optimizer_step
+
+Memory plan (HBM): parameters live in ONE fp32 buffer (`flat_p`) laid out by config.param_shapes, shadowed by a bf16
+copy (`flat_pb`, what the GEMMs read through TMA), one fp32 gradient buffer (`flat_g`, accumulated into by atomics,
+the single tensor the data-parallel all-reduce sends) and Adam m/v.  q,k,v weights are adjacent so the fused-QKV
+[3*inner, d] matrix is a plain view.  The residual stream is fp32 [tokens, d]; every tensor that feeds a tensor-core
+GEMM is stored bf16; activations needed by the backward are kept (4 GB at config 2 — no recompute on a 180 GB part).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from .config import param_shapes, vocab_size
+from .ops import ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD
+
+_ALIGN = 64  # elements; keeps every parameter 256 B (fp32) / 128 B (bf16) aligned for TMA
+
+
+def relative_position_bucket(relative_position, bidirectional=True, num_buckets=32, max_distance=128):
+    """Host-side bucket function, same torch ops as the reference (modeling_t5.py:397-443): fp32 log then truncation.
+    Evaluated once per (Lq, Lk) into a LUT that the kernels index; the device never recomputes the log."""
+    relative_buckets = torch.zeros_like(relative_position)
+    if bidirectional:
+        num_buckets //= 2
+        relative_buckets = relative_buckets + (relative_position > 0).to(torch.long) * num_buckets
+        relative_position = torch.abs(relative_position)
+    else:
+        relative_position = -torch.min(relative_position, torch.zeros_like(relative_position))
+    max_exact = num_buckets // 2
+    is_small = relative_position < max_exact
+    if_large = max_exact + (
+        torch.log(relative_position.float() / max_exact) / math.log(max_distance / max_exact) * (num_buckets - max_exact)
+    ).to(torch.long)
+    if_large = torch.min(if_large, torch.full_like(if_large, num_buckets - 1))
+    return relative_buckets + torch.where(is_small, relative_position, if_large)
+
+
+@dataclass
+class _Sub:
+    """One residual sub-layer's parameter names and static attributes."""
+    kind: int            # 0 = T5 RMS norm (eps 1e-6), 1 = nn.LayerNorm (eps 1e-5)
+    norm_w: str
+    norm_b: Optional[str]
+    H: int = 0
+    scale: float = 1.0
+    qkv_w: str = ""      # first of the adjacent q,k,v weights (or the fused ViT qkv)
+    qkv_b: Optional[str] = None
+    q_w: str = ""        # cross attention: separate q, fused k,v
+    kv_w: str = ""
+    o_w: str = ""
+    o_b: Optional[str] = None
+    w1: str = ""
+    b1: Optional[str] = None
+    w2: str = ""
+    b2: Optional[str] = None
+    act: int = ACT_RELU
+
+    @property
+    def eps(self):
+        return 1e-5 if self.kind == 1 else 1e-6
+
+
+class Vid2SeqEngine:
+    @staticmethod
+    def layout_of(cfg: dict):
+        layout, off = {}, 0
+        for name, shape in param_shapes(cfg):
+            n = 1
+            for s in shape:
+                n *= s
+            layout[name] = (off, tuple(shape), n)
+            off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
+        return layout, off
+
+    def __init__(self, cfg: dict, ops, device, label_smoothing: float = 0.1, use_video=True, use_speech=True,
+                 flat_p: Optional[torch.Tensor] = None):
+        self.cfg, self.ops, self.device = cfg, ops, torch.device(device)
+        self.label_smoothing = label_smoothing
+        self.use_video, self.use_speech = use_video, use_speech
+        self.d, self.H, self.dff = cfg["d_model"], cfg["num_heads"], cfg["d_ff"]
+        self.inner = self.H * cfg["d_kv"]
+        assert cfg["d_kv"] == 64, "kernels are specialised for head_dim 64 (t5-base / t5-large / the ViT)"
+        self.C, self.Hv, self.mlp = cfg["embed_dim"], cfg["heads"], cfg["mlp_dim"]
+        assert self.C // self.Hv == 64
+        self.V = vocab_size(cfg)
+        self.layout, self.total = self.layout_of(cfg)
+        dev = self.device
+        if flat_p is not None:
+            assert flat_p.numel() == self.total and flat_p.dtype == torch.float32 and flat_p.device == dev
+            self.flat_p = flat_p
+        else:
+            self.flat_p = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.flat_pb = torch.zeros(self.total, dtype=torch.bfloat16, device=dev)
+        self.flat_g = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.adam_m = None
+        self.adam_v = None
+        self.adam_step_count = 0
+        self._scratch = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._luts: Dict[tuple, torch.Tensor] = {}
+        self._one = torch.ones(1, dtype=torch.float32, device=dev)
+        self._build_specs()
+
+    # ------------------------------------------------------------------ parameter views
+    def p(self, name):
+        o, shape, n = self.layout[name]
+        return self.flat_p[o:o + n].view(shape)
+
+    def g(self, name):
+        o, shape, n = self.layout[name]
+        return self.flat_g[o:o + n].view(shape)
+
+    def pb(self, name, rows=None):
+        """bf16 shadow as a 2-D matrix; rows= spans adjacent parameters (fused q,k,v)."""
+        o, shape, n = self.layout[name]
+        cols = shape[-1]
+        r = rows if rows is not None else n // cols
+        return self.flat_pb[o:o + r * cols].view(r, cols)
+
+    def g2(self, name, rows=None):
+        o, shape, n = self.layout[name]
+        cols = shape[-1]
+        r = rows if rows is not None else n // cols
+        return self.flat_g[o:o + r * cols].view(r, cols)
+
+    def gv(self, name):
+        return None if name is None else self.g(name).view(-1)
+
+    def pv(self, name):
+        return None if name is None else self.p(name).view(-1)
+
+    def sync_bf16(self):
+        """Refresh the bf16 shadow from the fp32 masters (after load_state_dict / external optimiser steps)."""
+        self.ops.cast_flat_bf16(self.flat_p, self.flat_pb)
+
+    def _build_specs(self):
+        cfg = self.cfg
+        self.vit_blocks: List[tuple] = []
+        for i in range(cfg["depth"]):
+            p = f"visual_encoder.blocks.{i}."
+            sa = _Sub(kind=1, norm_w=p + "norm1.weight", norm_b=p + "norm1.bias", H=self.Hv, scale=64 ** -0.5,
+                      qkv_w=p + "attn.qkv.weight", qkv_b=p + "attn.qkv.bias", o_w=p + "attn.proj.weight",
+                      o_b=p + "attn.proj.bias")
+            ff = _Sub(kind=1, norm_w=p + "norm2.weight", norm_b=p + "norm2.bias", w1=p + "mlp.fc1.weight",
+                      b1=p + "mlp.fc1.bias", w2=p + "mlp.fc2.weight", b2=p + "mlp.fc2.bias", act=ACT_GELU)
+            self.vit_blocks.append((sa, ff))
+        self.enc_blocks, self.dec_blocks = [], []
+        for i in range(cfg["num_layers"]):
+            p = f"t5_model.encoder.block.{i}.layer."
+            sa = _Sub(kind=0, norm_w=p + "0.layer_norm.weight", norm_b=None, H=self.H, scale=1.0,
+                      qkv_w=p + "0.SelfAttention.q.weight", o_w=p + "0.SelfAttention.o.weight")
+            ff = _Sub(kind=0, norm_w=p + "1.layer_norm.weight", norm_b=None, w1=p + "1.DenseReluDense.wi.weight",
+                      w2=p + "1.DenseReluDense.wo.weight", act=ACT_RELU)
+            self.enc_blocks.append((sa, ff))
+            p = f"t5_model.decoder.block.{i}.layer."
+            sa = _Sub(kind=0, norm_w=p + "0.layer_norm.weight", norm_b=None, H=self.H, scale=1.0,
+                      qkv_w=p + "0.SelfAttention.q.weight", o_w=p + "0.SelfAttention.o.weight")
+            ca = _Sub(kind=0, norm_w=p + "1.layer_norm.weight", norm_b=None, H=self.H, scale=1.0,
+                      q_w=p + "1.EncDecAttention.q.weight", kv_w=p + "1.EncDecAttention.k.weight",
+                      o_w=p + "1.EncDecAttention.o.weight")
+            ff = _Sub(kind=0, norm_w=p + "2.layer_norm.weight", norm_b=None, w1=p + "2.DenseReluDense.wi.weight",
+                      w2=p + "2.DenseReluDense.wo.weight", act=ACT_RELU)
+            self.dec_blocks.append((sa, ca, ff))
+        self.enc_bias_name = "t5_model.encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"
+        self.dec_bias_name = "t5_model.decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"
+
+    def lut(self, Lq, Lk, bidirectional):
+        key = (Lq, Lk, bidirectional)
+        if key not in self._luts:
+            rel = torch.arange(Lq + Lk - 1, dtype=torch.long) - (Lq - 1)
+            self._luts[key] = relative_position_bucket(rel, bidirectional).to(torch.int32).to(self.device)
+        return self._luts[key]
+
+    # ------------------------------------------------------------------ allocation helpers
+    def _e(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def _z(self, *shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def _splits(self, n_out, k_out, red):
+        tiles = ((n_out + 127) // 128) * ((k_out + 255) // 256)
+        s = max(1, min((red + 63) // 64 // 2, -(-296 // tiles)))
+        return s
+
+    # ------------------------------------------------------------------ sub-layers: forward
+    def _sa_fwd(self, x0, sp: _Sub, B, L, bias_rel, kmask, causal, tape):
+        ops, M, D = self.ops, x0.shape[0], x0.shape[1]
+        inner = sp.H * 64
+        bf = torch.bfloat16
+        h = self._e(M, D, dtype=bf)
+        rstd = self._e(M)
+        mean = self._e(M) if sp.kind == 1 else None
+        ops.norm_fwd(sp.kind, x0, self.pv(sp.norm_w), self.pv(sp.norm_b), out_bf16=h, rstd=rstd, mean=mean, eps=sp.eps)
+        qkv = self._e(M, 3 * inner, dtype=bf)
+        ops.gemm(h, self.pb(sp.qkv_w, 3 * inner), qkv, bias=self.pv(sp.qkv_b))
+        ctx = self._e(M, inner, dtype=bf)
+        lse = self._e(B, sp.H, L)
+        ops.attn_fwd(qkv, qkv, qkv, q_col=0, k_col=inner, v_col=2 * inner, B=B, H=sp.H, Lq=L, Lk=L, out=ctx, lse2=lse,
+                     bias_rel=bias_rel, kmask=kmask, causal=causal, scale=sp.scale)
+        x1 = self._e(M, D)
+        ops.gemm(ctx, self.pb(sp.o_w), x1, bias=self.pv(sp.o_b), residual=x0)
+        tape.append(dict(t="sa", sp=sp, x0=x0, h=h, rstd=rstd, mean=mean, qkv=qkv, ctx=ctx, lse=lse, B=B, L=L,
+                         bias_rel=bias_rel, kmask=kmask, causal=causal))
+        return x1
+
+    def _ca_fwd(self, y1, sp: _Sub, B, S, memory, E, mem_mask, tape):
+        ops, M, D = self.ops, y1.shape[0], y1.shape[1]
+        inner = sp.H * 64
+        bf = torch.bfloat16
+        h = self._e(M, D, dtype=bf)
+        rstd = self._e(M)
+        ops.norm_fwd(0, y1, self.pv(sp.norm_w), None, out_bf16=h, rstd=rstd, eps=sp.eps)
+        qc = self._e(M, inner, dtype=bf)
+        ops.gemm(h, self.pb(sp.q_w), qc)
+        kv = self._e(B * E, 2 * inner, dtype=bf)
+        ops.gemm(memory, self.pb(sp.kv_w, 2 * inner), kv)
+        ctx = self._e(M, inner, dtype=bf)
+        lse = self._e(B, sp.H, S)
+        ops.attn_fwd(qc, kv, kv, q_col=0, k_col=0, v_col=inner, B=B, H=sp.H, Lq=S, Lk=E, out=ctx, lse2=lse,
+                     bias_rel=None, kmask=mem_mask, causal=False, scale=1.0)
+        y2 = self._e(M, D)
+        ops.gemm(ctx, self.pb(sp.o_w), y2, residual=y1)
+        tape.append(dict(t="ca", sp=sp, x0=y1, h=h, rstd=rstd, qc=qc, kv=kv, ctx=ctx, lse=lse, B=B, S=S, E=E,
+                         mem_mask=mem_mask))
+        return y2
+
+    def _ff_fwd(self, x1, sp: _Sub, tape):
+        ops, M, D = self.ops, x1.shape[0], x1.shape[1]
+        bf = torch.bfloat16
+        h = self._e(M, D, dtype=bf)
+        rstd = self._e(M)
+        mean = self._e(M) if sp.kind == 1 else None
+        ops.norm_fwd(sp.kind, x1, self.pv(sp.norm_w), self.pv(sp.norm_b), out_bf16=h, rstd=rstd, mean=mean, eps=sp.eps)
+        w1 = self.pb(sp.w1)
+        act = self._e(M, w1.shape[0], dtype=bf)
+        pre = self._e(M, w1.shape[0], dtype=bf) if sp.act == ACT_GELU else None
+        ops.gemm(h, w1, act, bias=self.pv(sp.b1), act=sp.act, pre_out=pre)
+        x2 = self._e(M, D)
+        ops.gemm(act, self.pb(sp.w2), x2, bias=self.pv(sp.b2), residual=x1)
+        tape.append(dict(t="ff", sp=sp, x0=x1, h=h, rstd=rstd, mean=mean, act=act, pre=pre))
+        return x2
+
+    # ------------------------------------------------------------------ sub-layers: backward
+    def _wgrad(self, dy, x, gname, rows=None):
+        """g[N,K] += dy[M,N]^T @ x[M,K]  (reduction over the token dimension, split-K with fp32 atomics)."""
+        out = self.g2(gname, rows)
+        self.ops.gemm(dy, x, out, a_mn=True, b_mn=True, atomic=True,
+                      splits=self._splits(out.shape[0], out.shape[1], dy.shape[0]))
+
+    def _ff_bwd(self, r, dx, dxb, ws):
+        ops, sp = self.ops, r["sp"]
+        M, D = dx.shape
+        dff = r["act"].shape[1]
+        if sp.b2:
+            ops.colsum_bf16(dxb, self.gv(sp.b2))
+        self._wgrad(dxb, r["act"], sp.w2)
+        dact = ws["dact"][:M * dff].view(M, dff)
+        if sp.act == ACT_GELU:
+            ops.gemm(dxb, self.pb(sp.w2), dact, b_mn=True, act=ACT_GELU_BWD, aux=r["pre"])
+        else:
+            ops.gemm(dxb, self.pb(sp.w2), dact, b_mn=True, act=ACT_RELU_BWD, aux=r["act"])
+        if sp.b1:
+            ops.colsum_bf16(dact, self.gv(sp.b1))
+        self._wgrad(dact, r["h"], sp.w1)
+        dh = ws["dh"][:M * D].view(M, D)
+        ops.gemm(dact, self.pb(sp.w1), dh, b_mn=True)
+        ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
+                     accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b))
+
+    def _sa_bwd(self, r, dx, dxb, ws, dbias_rel, lut):
+        ops, sp = self.ops, r["sp"]
+        M, D = dx.shape
+        B, L, H = r["B"], r["L"], sp.H
+        inner = H * 64
+        if sp.o_b:
+            ops.colsum_bf16(dxb, self.gv(sp.o_b))
+        self._wgrad(dxb, r["ctx"], sp.o_w)
+        dctx = ws["dctx"][:M * inner].view(M, inner)
+        ops.gemm(dxb, self.pb(sp.o_w), dctx, b_mn=True)
+        dqkv = ws["dqkv"][:M * 3 * inner].view(M, 3 * inner)
+        dq_acc = ws["dq_acc"][:M * inner].view(M, inner)
+        dq_acc.zero_()
+        delta = ws["delta"][:B * H * L].view(B, H, L)
+        qkv = r["qkv"]
+        ops.attn_bwd(qkv, qkv, qkv, q_col=0, k_col=inner, v_col=2 * inner, B=B, H=H, Lq=L, Lk=L, out=r["ctx"],
+                     lse2=r["lse"], bias_rel=r["bias_rel"], kmask=r["kmask"], causal=r["causal"], scale=sp.scale,
+                     dout=dctx, do_col=0, delta=delta, dq_acc=dq_acc, dk=dqkv, dk_col=inner, dv=dqkv, dv_col=2 * inner,
+                     dbias_rel=dbias_rel, bucket_lut=lut)
+        ops.cast_f32_bf16(dq_acc, dqkv[:, :inner])
+        if sp.qkv_b:
+            ops.colsum_bf16(dqkv, self.gv(sp.qkv_b))
+        self._wgrad(dqkv, r["h"], sp.qkv_w, rows=3 * inner)
+        dh = ws["dh"][:M * D].view(M, D)
+        ops.gemm(dqkv, self.pb(sp.qkv_w, 3 * inner), dh, b_mn=True)
+        ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
+                     accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b))
+
+    def _ca_bwd(self, r, dx, dxb, ws, memory, dmem):
+        ops, sp = self.ops, r["sp"]
+        M, D = dx.shape
+        B, S, E, H = r["B"], r["S"], r["E"], sp.H
+        inner = H * 64
+        self._wgrad(dxb, r["ctx"], sp.o_w)
+        dctx = ws["dctx"][:M * inner].view(M, inner)
+        ops.gemm(dxb, self.pb(sp.o_w), dctx, b_mn=True)
+        dq_acc = ws["dq_acc"][:M * inner].view(M, inner)
+        dq_acc.zero_()
+        dq = ws["dqkv"][:M * inner].view(M, inner)
+        dkv = ws["dkv"][:B * E * 2 * inner].view(B * E, 2 * inner)
+        delta = ws["delta"][:B * H * S].view(B, H, S)
+        ops.attn_bwd(r["qc"], r["kv"], r["kv"], q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=S, Lk=E, out=r["ctx"],
+                     lse2=r["lse"], bias_rel=None, kmask=r["mem_mask"], causal=False, scale=1.0, dout=dctx, do_col=0,
+                     delta=delta, dq_acc=dq_acc, dk=dkv, dk_col=0, dv=dkv, dv_col=inner, dbias_rel=None, bucket_lut=None)
+        ops.cast_f32_bf16(dq_acc, dq)
+        self._wgrad(dq, r["h"], sp.q_w)
+        dh = ws["dh"][:M * D].view(M, D)
+        ops.gemm(dq, self.pb(sp.q_w), dh, b_mn=True)
+        ops.norm_bwd(0, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], None, dx=dx, dx_bf16=dxb, accumulate_dx=True,
+                     dw=self.gv(sp.norm_w))
+        self._wgrad(dkv, memory, sp.kv_w, rows=2 * inner)
+        ops.gemm(dkv, self.pb(sp.kv_w, 2 * inner), dmem, b_mn=True, residual=dmem)  # dmem += dkv @ Wkv
+
+    # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _mask_u8(mask):
+        m = mask if mask.dtype == torch.bool else (mask != 0)
+        return m.contiguous().view(torch.uint8)
+
+    def forward(self, video, input_ids, input_mask, output_ids, output_mask, video_cached: bool = False,
+                want_logits: bool = False):
+        """One Vid2Seq forward (vid2seq.py:58-98).  Returns (loss[1] device tensor, ctx) — ctx feeds backward().
+        `video` is (B,T,768) features, or the cached projected output (B,T,d) when video_cached."""
+        ops, cfg, d = self.ops, self.cfg, self.d
+        bf = torch.bfloat16
+        tape: List[dict] = []
+        ctx = {"tape": tape}
+        B = output_ids.shape[0]
+        T = video.shape[1] if self.use_video else 0
+        L = input_ids.shape[1] if self.use_speech else 0
+        S = output_ids.shape[1]
+        E = T + L
+        ctx.update(B=B, T=T, L=L, S=S, E=E, video_cached=video_cached)
+        memory = self._e(B * E, d, dtype=bf)
+        vid_f32 = None
+        # ---------------- visual encoder (vit.py:117-133)
+        if self.use_video:
+            if video_cached:
+                vid_f32 = video.reshape(B * T, d).contiguous().float()
+                tmp = self._e(B * T, d, dtype=bf)
+                ops.cast_f32_bf16(vid_f32, tmp)
+                ops.copy_rows_bf16(tmp, memory, B, T, d, E, 0)
+            else:
+                C = self.C
+                xv = self._e(B * T, C)
+                ops.add_pos(video.contiguous().float(), self.p("visual_encoder.pos_embed"), xv.view(B, T, C),
+                            cfg["num_features"])
+                for sa, ff in self.vit_blocks:
+                    xv = self._sa_fwd(xv, sa, B, T, None, None, False, tape)
+                    xv = self._ff_fwd(xv, ff, tape)
+                rstd, mean = self._e(B * T), self._e(B * T)
+                if d == 768 and C == 768:
+                    vid_f32 = self._e(B * T, C)
+                    # final LayerNorm lands directly in the decoder memory rows [b, 0:T)
+                    ops.norm_fwd(1, xv, self.pv("visual_encoder.norm.weight"), self.pv("visual_encoder.norm.bias"),
+                                 out_bf16=memory, rstd=rstd, mean=mean, eps=1e-5, rows_per_batch=T, out_batch_stride=E,
+                                 out_row_offset=0)
+                    ops.norm_fwd(1, xv, self.pv("visual_encoder.norm.weight"), self.pv("visual_encoder.norm.bias"),
+                                 out_f32=vid_f32, eps=1e-5)
+                    vn = None
+                else:  # proj_v2t (vid2seq.py:54-56,64-65)
+                    vn = self._e(B * T, C, dtype=bf)
+                    ops.norm_fwd(1, xv, self.pv("visual_encoder.norm.weight"), self.pv("visual_encoder.norm.bias"),
+                                 out_bf16=vn, rstd=rstd, mean=mean, eps=1e-5)
+                    vid_f32 = self._e(B * T, d)
+                    ops.gemm(vn, self.pb("proj_v2t.weight"), vid_f32, bias=self.pv("proj_v2t.bias"))
+                    tmp = self._e(B * T, d, dtype=bf)
+                    ops.cast_f32_bf16(vid_f32, tmp)
+                    ops.copy_rows_bf16(tmp, memory, B, T, d, E, 0)
+                ctx.update(vit_x=xv, vit_rstd=rstd, vit_mean=mean, vit_vn=vn)
+        ctx["n_vit_tape"] = len(tape)
+        # ---------------- text encoder (modeling_t5.py:930-1138)
+        if self.use_speech:
+            ids = input_ids.contiguous()
+            x = self._e(B * L, d)
+            ops.embed_fwd(ids, self.p("t5_model.shared.weight"), x)
+            lut_e = self.lut(L, L, True)
+            bias_e = self._e(self.H, 2 * L - 1)
+            ops.bias_expand(self.p(self.enc_bias_name), lut_e, bias_e)
+            kmask_e = self._mask_u8(input_mask)
+            for sa, ff in self.enc_blocks:
+                x = self._sa_fwd(x, sa, B, L, bias_e, kmask_e, False, tape)
+                x = self._ff_fwd(x, ff, tape)
+            rstd_e = self._e(B * L)
+            ops.norm_fwd(0, x, self.pv("t5_model.encoder.final_layer_norm.weight"), None, out_bf16=memory, rstd=rstd_e,
+                         eps=1e-6, rows_per_batch=L, out_batch_stride=E, out_row_offset=T)
+            ctx.update(enc_x=x, enc_rstd=rstd_e, enc_ids=ids, lut_e=lut_e)
+        ctx["n_enc_tape"] = len(tape)
+        parts = []
+        if self.use_video:
+            parts.append(torch.ones(B, T, dtype=torch.uint8, device=self.device))
+        if self.use_speech:
+            parts.append(self._mask_u8(input_mask))
+        mem_mask = torch.cat(parts, dim=1).contiguous()
+        # ---------------- decoder
+        out_ids = output_ids.contiguous()
+        dec_in, labels = torch.empty_like(out_ids), torch.empty_like(out_ids)
+        n_valid = self._e(1)
+        ops.prepare_targets(out_ids, dec_in, labels, n_valid, 0)
+        y = self._e(B * S, d)
+        ops.embed_fwd(dec_in, self.p("t5_model.shared.weight"), y)
+        lut_d = self.lut(S, S, False)
+        bias_d = self._e(self.H, 2 * S - 1)
+        ops.bias_expand(self.p(self.dec_bias_name), lut_d, bias_d)
+        kmask_d = self._mask_u8(output_mask)
+        for sa, ca, ff in self.dec_blocks:
+            y = self._sa_fwd(y, sa, B, S, bias_d, kmask_d, True, tape)
+            y = self._ca_fwd(y, ca, B, S, memory, E, mem_mask, tape)
+            y = self._ff_fwd(y, ff, tape)
+        # ---------------- head: final norm * d^-0.5 (tied), lm_head, label-smoothed CE (modeling_t5.py:1709-1721)
+        seq = self._e(B * S, d, dtype=bf)
+        rstd_d = self._e(B * S)
+        ops.norm_fwd(0, y, self.pv("t5_model.decoder.final_layer_norm.weight"), None, out_bf16=seq, rstd=rstd_d, eps=1e-6,
+                     out_scale=d ** -0.5)
+        logits = self._e(B * S, self.V)
+        ops.gemm(seq, self.pb("t5_model.shared.weight"), logits)
+        loss = self._e(1)
+        dlogits = self._e(B * S, self.V, dtype=bf)
+        ops.cross_entropy(logits, labels.view(-1), n_valid, self.label_smoothing, loss, dlogits)
+        ctx.update(memory=memory, mem_mask=mem_mask, dec_in=dec_in, dec_x=y, dec_rstd=rstd_d, seq=seq, dlogits=dlogits,
+                   lut_d=lut_d, vid_f32=vid_f32)
+        if want_logits:
+            ctx["logits"] = logits
+        return loss, ctx
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, ctx, grad_loss: Optional[torch.Tensor] = None, grad_video: Optional[torch.Tensor] = None):
+        """Accumulates d(loss)/d(params) * grad_loss into flat_g.  Returns d/d(cached video) when the forward consumed
+        a cached visual-encoder output (so it can flow back to the pass that produced it), else None."""
+        ops, d = self.ops, self.d
+        bf = torch.bfloat16
+        tape = ctx["tape"]
+        B, T, L, S, E = ctx["B"], ctx["T"], ctx["L"], ctx["S"], ctx["E"]
+        gl = self._one if grad_loss is None else grad_loss.reshape(1).float().contiguous()
+        Mmax = B * max(T, L, S)
+        inner_max = max(self.inner, self.C)
+        ws = dict(
+            dact=self._e(Mmax * max(self.dff, self.mlp), dtype=bf), dh=self._e(Mmax * max(d, self.C)),
+            dctx=self._e(Mmax * inner_max, dtype=bf), dqkv=self._e(Mmax * 3 * inner_max, dtype=bf),
+            dq_acc=self._e(Mmax * inner_max), delta=self._e(B * max(self.H, self.Hv) * max(T, L, S)),
+            dkv=self._e(B * E * 2 * self.inner, dtype=bf))
+        # ---- head
+        seq, dlogits = ctx["seq"], ctx["dlogits"]
+        ops.gemm(dlogits, seq, self.g2("t5_model.shared.weight"), a_mn=True, b_mn=True, atomic=True, alpha_dev=gl,
+                 splits=self._splits(self.V, d, B * S))
+        dseq = ws["dh"][:B * S * d].view(B * S, d)
+        ops.gemm(dlogits, self.pb("t5_model.shared.weight"), dseq, b_mn=True, alpha_dev=gl)
+        dy = self._e(B * S, d)
+        dyb = self._e(B * S, d, dtype=bf)
+        ops.norm_bwd(0, dseq, ctx["dec_x"], self.pv("t5_model.decoder.final_layer_norm.weight"), ctx["dec_rstd"], None,
+                     dx=dy, dx_bf16=dyb, accumulate_dx=False, dw=self.gv("t5_model.decoder.final_layer_norm.weight"),
+                     scale=d ** -0.5)
+        # ---- decoder blocks (reverse)
+        dmem = self._z(B * E, d)
+        drel_d = self._z(self.H, 2 * S - 1)
+        i = len(tape)
+        for _ in range(len(self.dec_blocks)):
+            self._ff_bwd(tape[i - 1], dy, dyb, ws)
+            self._ca_bwd(tape[i - 2], dy, dyb, ws, ctx["memory"], dmem)
+            self._sa_bwd(tape[i - 3], dy, dyb, ws, drel_d, ctx["lut_d"])
+            i -= 3
+        ops.bias_fold(drel_d, ctx["lut_d"], self.g(self.dec_bias_name))
+        ops.embed_bwd(ctx["dec_in"].view(-1), dy, self.g("t5_model.shared.weight"))
+        if grad_video is not None and self.use_video:
+            dmem.view(B, E, d)[:, :T].add_(grad_video.reshape(B, T, d).to(dmem.dtype))
+        # ---- text encoder
+        if self.use_speech:
+            dx = self._e(B * L, d)
+            dxb = self._e(B * L, d, dtype=bf)
+            ops.norm_bwd(0, dmem, ctx["enc_x"], self.pv("t5_model.encoder.final_layer_norm.weight"), ctx["enc_rstd"], None,
+                         dx=dx, dx_bf16=dxb, accumulate_dx=False, dw=self.gv("t5_model.encoder.final_layer_norm.weight"),
+                         rows_per_batch=L, g_batch_stride=E, g_row_offset=T)
+            drel_e = self._z(self.H, 2 * L - 1)
+            for _ in range(len(self.enc_blocks)):
+                self._ff_bwd(tape[i - 1], dx, dxb, ws)
+                self._sa_bwd(tape[i - 2], dx, dxb, ws, drel_e, ctx["lut_e"])
+                i -= 2
+            ops.bias_fold(drel_e, ctx["lut_e"], self.g(self.enc_bias_name))
+            ops.embed_bwd(ctx["enc_ids"].view(-1), dx, self.g("t5_model.shared.weight"))
+        # ---- visual encoder
+        dvideo_out = None
+        if self.use_video:
+            if ctx["video_cached"]:
+                dvideo_out = dmem.view(B, E, d)[:, :T].contiguous()
+            else:
+                C = self.C
+                dxv = self._e(B * T, C)
+                dxvb = self._e(B * T, C, dtype=bf)
+                if ctx["vit_vn"] is None:
+                    ops.norm_bwd(1, dmem, ctx["vit_x"], self.pv("visual_encoder.norm.weight"), ctx["vit_rstd"],
+                                 ctx["vit_mean"], dx=dxv, dx_bf16=dxvb, accumulate_dx=False,
+                                 dw=self.gv("visual_encoder.norm.weight"), db=self.gv("visual_encoder.norm.bias"),
+                                 rows_per_batch=T, g_batch_stride=E, g_row_offset=0)
+                else:
+                    dvid = dmem.view(B, E, d)[:, :T].reshape(B * T, d).contiguous()
+                    dvb = self._e(B * T, d, dtype=bf)
+                    ops.cast_f32_bf16(dvid, dvb)
+                    ops.colsum_bf16(dvb, self.gv("proj_v2t.bias"))
+                    self._wgrad(dvb, ctx["vit_vn"], "proj_v2t.weight")
+                    dvn = ws["dh"][:B * T * C].view(B * T, C)
+                    ops.gemm(dvb, self.pb("proj_v2t.weight"), dvn, b_mn=True)
+                    ops.norm_bwd(1, dvn, ctx["vit_x"], self.pv("visual_encoder.norm.weight"), ctx["vit_rstd"],
+                                 ctx["vit_mean"], dx=dxv, dx_bf16=dxvb, accumulate_dx=False,
+                                 dw=self.gv("visual_encoder.norm.weight"), db=self.gv("visual_encoder.norm.bias"))
+                for _ in range(len(self.vit_blocks)):
+                    self._ff_bwd(tape[i - 1], dxv, dxvb, ws)
+                    self._sa_bwd(tape[i - 2], dxv, dxvb, ws, None, None)
+                    i -= 2
+                ops.add_pos_bwd(dxv, self.g("visual_encoder.pos_embed"), B, T, C, self.cfg["num_features"])
+        assert i == 0, i
+        return dvideo_out
+
+    # ------------------------------------------------------------------ optimiser tail (dvc.py:114-126)
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def optimizer_step(self, lr, betas=(0.9, 0.999), eps=1e-8, clip_max_norm=1.0, grad_scale=1.0, renorm=True):
+        ops = self.ops
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.flat_p)
+            self.adam_v = torch.zeros_like(self.flat_p)
+        self.adam_step_count += 1
+        norm_sq = None
+        if clip_max_norm > 0:
+            norm_sq = self._scratch[0:1]
+            norm_sq.zero_()
+            ops.sumsq(self.flat_g, norm_sq)
+        ops.adam_step(self.flat_p, self.flat_g, self.adam_m, self.adam_v, self.flat_pb, lr=lr, beta1=betas[0],
+                      beta2=betas[1], eps=eps, step=self.adam_step_count, norm_sq=norm_sq, clip_max_norm=clip_max_norm,
+                      grad_scale=grad_scale)
+        if renorm and self.cfg["num_bins"]:
+            w = self.p("t5_model.shared.weight")
+            wb = self.pb("t5_model.shared.weight")
+            for _ in range(2):  # shared and lm_head are the same tensor: the reference renormalises it twice
+                ops.renorm_time_tokens(w, wb, self.cfg["num_bins"], self._scratch[2:4])
+        return norm_sq

@@ -26,10 +26,66 @@ class GemmArgs(C.Structure):
         ("pre_out", C.c_void_p),
         ("aux", C.c_void_p), ("ld_aux", C.c_int64),
         ("alpha", C.c_float),
+        ("alpha_dev", C.c_void_p),
         ("splits", C.c_int32),
         ("tile_n", C.c_int32),
     ]
 
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64),
+        ("q_col", C.c_int32), ("k_col", C.c_int32), ("v_col", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32), ("head_dim", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("lse2", C.c_void_p),
+        ("bias_rel", C.c_void_p),
+        ("kmask", C.c_void_p),
+        ("causal", C.c_int32),
+        ("scale", C.c_float),
+    ]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("fwd", AttnArgs),
+        ("dout", C.c_void_p), ("ld_do", C.c_int64), ("do_col", C.c_int32),
+        ("delta", C.c_void_p),
+        ("dq_acc", C.c_void_p), ("ld_dq", C.c_int64),
+        ("dk", C.c_void_p), ("ld_dk", C.c_int64), ("dk_col", C.c_int32),
+        ("dv", C.c_void_p), ("ld_dv", C.c_int64), ("dv_col", C.c_int32),
+        ("dbias_rel", C.c_void_p),
+        ("bucket_lut", C.c_void_p),
+    ]
+
+
+P, I, I64, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+SIGNATURES = {
+    "vc_gemm_bf16": [C.POINTER(GemmArgs), P],
+    "vc_attn_fwd": [C.POINTER(AttnArgs), P],
+    "vc_attn_bwd": [C.POINTER(AttnBwdArgs), P],
+    "vc_norm_fwd": [I, P, P, P, P, P, P, P, I, I, F, F, I, I, I, P],
+    "vc_norm_bwd": [I, P, P, P, P, P, P, P, I, P, P, I, I, F, I, I, I, P],
+    "vc_embed_fwd": [P, P, P, I, I, I, P],
+    "vc_embed_bwd": [P, P, P, I, I, I, P],
+    "vc_prepare_targets": [P, P, P, P, I, I, I64, P],
+    "vc_bias_expand": [P, P, P, I, I, P],
+    "vc_bias_fold": [P, P, P, I, I, P],
+    "vc_add_pos": [P, P, P, I, I, I, I, P],
+    "vc_add_pos_bwd": [P, P, I, I, I, I, P],
+    "vc_cross_entropy": [P, I64, P, P, F, P, P, I64, I, I, P],
+    "vc_colsum_bf16": [P, I64, P, I, I, P],
+    "vc_cast_f32_bf16": [P, I64, P, I64, I, I, F, P],
+    "vc_copy_rows_bf16": [P, P, I, I, I, I, I, P],
+    "vc_sumsq": [P, I64, P, P],
+    "vc_adam_step": [P, P, P, P, P, I64, F, F, F, F, I, P, F, F, P],
+    "vc_renorm_time_tokens": [P, P, I, I, I, P, P],
+    "vc_cast_flat_bf16": [P, P, I64, P],
+    "vc_version": [],
+    "vc_last_error": [],
+    "vc_device_check": [],
+}
 
 _lib = None
 
@@ -47,6 +103,11 @@ def load() -> C.CDLL:
     lib.vc_version.restype = C.c_int
     if lib.vc_version() != ABI_VERSION:
         raise RuntimeError(f"libvidchap ABI {lib.vc_version()} != expected {ABI_VERSION}; rebuild")
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == the .so does not export what include/vidchap.h declares
+        fn.argtypes = argtypes
+        if name != "vc_last_error":
+            fn.restype = C.c_int
     _lib = lib
     return lib
 

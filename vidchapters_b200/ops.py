@@ -41,7 +41,7 @@ class CudaOps:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, pre_out=None,
-             aux=None, alpha=1.0, splits=1, atomic=False, tile_n=0):
+             aux=None, alpha=1.0, alpha_dev=None, splits=1, atomic=False, tile_n=0):
         """out[M,N] = epi(alpha * op(A) @ op(B)^T).  A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn)."""
         _chk_cuda(A, B, out, bias, residual, pre_out, aux)
         assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -72,8 +72,177 @@ class CudaOps:
             assert aux.dtype == torch.bfloat16 and aux.stride(1) == 1
             a.aux, a.ld_aux = aux.data_ptr(), aux.stride(0)
         a.alpha = float(alpha)
+        a.alpha_dev = None if alpha_dev is None else alpha_dev.data_ptr()
         a.splits = int(splits)
         a.tile_n = int(tile_n)
         _lib.check(self.lib.vc_gemm_bf16(C.byref(a), self._stream()))
         self.launches += 1
         return out
+
+    # ------------------------------------------------------------------ attention
+    def _attn_args(self, q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale):
+        _chk_cuda(q, k, v, out, lse2, bias_rel, kmask)
+        for t in (q, k, v, out):
+            assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+        assert q.shape[0] == B * Lq and k.shape[0] == B * Lk and v.shape[0] == B * Lk and out.shape[0] == B * Lq
+        if kmask is not None:
+            assert kmask.dtype == torch.uint8 and kmask.shape == (B, Lk) and kmask.is_contiguous()
+        if bias_rel is not None:
+            assert bias_rel.dtype == torch.float32 and bias_rel.shape == (H, Lq + Lk - 1) and bias_rel.is_contiguous()
+        a = _lib.AttnArgs()
+        a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+        a.ldq, a.ldk, a.ldv = q.stride(0), k.stride(0), v.stride(0)
+        a.q_col, a.k_col, a.v_col = q_col, k_col, v_col
+        a.B, a.H, a.Lq, a.Lk, a.head_dim = B, H, Lq, Lk, 64
+        a.out, a.ldo = out.data_ptr(), out.stride(0)
+        a.lse2 = None if lse2 is None else lse2.data_ptr()
+        a.bias_rel = None if bias_rel is None else bias_rel.data_ptr()
+        a.kmask = None if kmask is None else kmask.data_ptr()
+        a.causal = int(causal)
+        a.scale = float(scale)
+        return a
+
+    def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
+                 causal=False, scale=1.0):
+        a = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale)
+        _lib.check(self.lib.vc_attn_fwd(C.byref(a), self._stream()))
+        self.launches += 1
+
+    def attn_bwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
+                 causal=False, scale=1.0, dout, do_col=0, delta, dq_acc, dk, dk_col, dv, dv_col, dbias_rel=None,
+                 bucket_lut=None):
+        """dq_acc must be zeroed by the caller (fp32 atomics); dk/dv are fully written; dbias_rel accumulates."""
+        _chk_cuda(dout, delta, dq_acc, dk, dv, dbias_rel, bucket_lut)
+        b = _lib.AttnBwdArgs()
+        b.fwd = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale)
+        assert dout.dtype == torch.bfloat16 and dq_acc.dtype == torch.float32 and delta.dtype == torch.float32
+        assert dk.dtype == torch.bfloat16 and dv.dtype == torch.bfloat16
+        b.dout, b.ld_do, b.do_col = dout.data_ptr(), dout.stride(0), do_col
+        b.delta = delta.data_ptr()
+        b.dq_acc, b.ld_dq = dq_acc.data_ptr(), dq_acc.stride(0)
+        b.dk, b.ld_dk, b.dk_col = dk.data_ptr(), dk.stride(0), dk_col
+        b.dv, b.ld_dv, b.dv_col = dv.data_ptr(), dv.stride(0), dv_col
+        b.dbias_rel = None if dbias_rel is None else dbias_rel.data_ptr()
+        if bucket_lut is not None:
+            assert bucket_lut.dtype == torch.int32
+        b.bucket_lut = None if bucket_lut is None else bucket_lut.data_ptr()
+        _lib.check(self.lib.vc_attn_bwd(C.byref(b), self._stream()))
+        self.launches += 2
+
+    # ------------------------------------------------------------------ norms
+    def norm_fwd(self, kind, x, w, bias, *, out_bf16=None, out_f32=None, rstd=None, mean=None, eps, out_scale=1.0,
+                 rows_per_batch=0, out_batch_stride=0, out_row_offset=0):
+        _chk_cuda(x, w, bias, out_bf16, out_f32, rstd, mean)
+        M, D = x.shape
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        _lib.check(self.lib.vc_norm_fwd(kind, _ptr(x), _ptr(w), _ptr(bias), _ptr(out_bf16), _ptr(out_f32), _ptr(rstd),
+                                        _ptr(mean), M, D, eps, out_scale, rows_per_batch, out_batch_stride,
+                                        out_row_offset, self._stream()))
+        self.launches += 1
+
+    def norm_bwd(self, kind, g, x, w, rstd, mean, *, dx, dx_bf16=None, accumulate_dx, dw, db=None, scale=1.0,
+                 rows_per_batch=0, g_batch_stride=0, g_row_offset=0):
+        _chk_cuda(g, x, w, rstd, mean, dx, dx_bf16, dw, db)
+        M, D = x.shape
+        assert g.dtype == torch.float32 and dx.dtype == torch.float32 and x.is_contiguous() and dx.is_contiguous()
+        _lib.check(self.lib.vc_norm_bwd(kind, _ptr(g), _ptr(x), _ptr(w), _ptr(rstd), _ptr(mean), _ptr(dx), _ptr(dx_bf16),
+                                        int(accumulate_dx), _ptr(dw), _ptr(db), M, D, scale, rows_per_batch,
+                                        g_batch_stride, g_row_offset, self._stream()))
+        self.launches += 1
+
+    # ------------------------------------------------------------------ small ops
+    def embed_fwd(self, ids, table, out):
+        _chk_cuda(ids, table, out)
+        assert ids.dtype == torch.int64 and ids.is_contiguous() and out.is_contiguous()
+        _lib.check(self.lib.vc_embed_fwd(_ptr(ids), _ptr(table), _ptr(out), ids.numel(), table.shape[1], table.shape[0],
+                                         self._stream()))
+        self.launches += 1
+
+    def embed_bwd(self, ids, dout, dtable):
+        _chk_cuda(ids, dout, dtable)
+        _lib.check(self.lib.vc_embed_bwd(_ptr(ids), _ptr(dout), _ptr(dtable), ids.numel(), dtable.shape[1],
+                                         dtable.shape[0], self._stream()))
+        self.launches += 1
+
+    def prepare_targets(self, out_ids, dec_in, labels, n_valid, pad_id=0):
+        _chk_cuda(out_ids, dec_in, labels, n_valid)
+        B, S = out_ids.shape
+        assert out_ids.dtype == torch.int64 and out_ids.is_contiguous()
+        _lib.check(self.lib.vc_prepare_targets(_ptr(out_ids), _ptr(dec_in), _ptr(labels), _ptr(n_valid), B, S, pad_id,
+                                               self._stream()))
+        self.launches += 1
+
+    def bias_expand(self, table, lut, out):
+        _chk_cuda(table, lut, out)
+        H, R = out.shape
+        _lib.check(self.lib.vc_bias_expand(_ptr(table), _ptr(lut), _ptr(out), H, R, self._stream()))
+        self.launches += 1
+
+    def bias_fold(self, drel, lut, dtable):
+        _chk_cuda(drel, lut, dtable)
+        H, R = drel.shape
+        _lib.check(self.lib.vc_bias_fold(_ptr(drel), _ptr(lut), _ptr(dtable), H, R, self._stream()))
+        self.launches += 1
+
+    def add_pos(self, x, pos, out, P):
+        _chk_cuda(x, pos, out)
+        B, T, Cc = x.shape
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        _lib.check(self.lib.vc_add_pos(_ptr(x), _ptr(pos), _ptr(out), B, T, Cc, P, self._stream()))
+        self.launches += 1
+
+    def add_pos_bwd(self, dx, dpos, B, T, Cc, P):
+        _chk_cuda(dx, dpos)
+        _lib.check(self.lib.vc_add_pos_bwd(_ptr(dx), _ptr(dpos), B, T, Cc, P, self._stream()))
+        self.launches += 1
+
+    def cross_entropy(self, logits, labels, n_valid, smoothing, loss_out, dlogits):
+        _chk_cuda(logits, labels, n_valid, loss_out, dlogits)
+        n, V = logits.shape
+        assert logits.dtype == torch.float32 and logits.stride(1) == 1
+        _lib.check(self.lib.vc_cross_entropy(_ptr(logits), logits.stride(0), _ptr(labels), _ptr(n_valid), smoothing,
+                                             _ptr(loss_out), _ptr(dlogits), 0 if dlogits is None else dlogits.stride(0),
+                                             n, V, self._stream()))
+        self.launches += 1
+
+    def colsum_bf16(self, x, out):
+        _chk_cuda(x, out)
+        M, N = x.shape
+        _lib.check(self.lib.vc_colsum_bf16(_ptr(x), x.stride(0), _ptr(out), M, N, self._stream()))
+        self.launches += 1
+
+    def cast_f32_bf16(self, src, dst, scale=1.0):
+        _chk_cuda(src, dst)
+        M, N = src.shape
+        _lib.check(self.lib.vc_cast_f32_bf16(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0), M, N, scale,
+                                             self._stream()))
+        self.launches += 1
+
+    def copy_rows_bf16(self, src, dst, B, T, Cc, E, row_off):
+        _chk_cuda(src, dst)
+        _lib.check(self.lib.vc_copy_rows_bf16(_ptr(src), _ptr(dst), B, T, Cc, E, row_off, self._stream()))
+        self.launches += 1
+
+    # ------------------------------------------------------------------ optimiser tail
+    def sumsq(self, g, out_accum):
+        _chk_cuda(g, out_accum)
+        _lib.check(self.lib.vc_sumsq(_ptr(g), g.numel(), _ptr(out_accum), self._stream()))
+        self.launches += 1
+
+    def adam_step(self, p, g, m, v, p_bf16, *, lr, beta1, beta2, eps, step, norm_sq=None, clip_max_norm=0.0,
+                  grad_scale=1.0):
+        _chk_cuda(p, g, m, v, p_bf16, norm_sq)
+        _lib.check(self.lib.vc_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), p.numel(), lr, beta1, beta2, eps,
+                                         step, _ptr(norm_sq), clip_max_norm, grad_scale, self._stream()))
+        self.launches += 1
+
+    def renorm_time_tokens(self, w, w_bf16, num_bins, scratch2):
+        _chk_cuda(w, w_bf16, scratch2)
+        V, d = w.shape
+        _lib.check(self.lib.vc_renorm_time_tokens(_ptr(w), _ptr(w_bf16), V, d, num_bins, _ptr(scratch2), self._stream()))
+        self.launches += 2
+
+    def cast_flat_bf16(self, src, dst):
+        _chk_cuda(src, dst)
+        _lib.check(self.lib.vc_cast_flat_bf16(_ptr(src), _ptr(dst), src.numel(), self._stream()))
+        self.launches += 1

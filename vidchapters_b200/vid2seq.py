@@ -1,0 +1,233 @@
+"""Drop-in `Vid2Seq` module: the reference's Python surface over the B200 engine.
+
+Mirrors model/vid2seq.py:20-167 and model/__init__.py:4-19 of the reference: same constructor arguments, same
+`forward(video, input_tokenized, output_tokenized) -> ({"loss": loss}, video_dict)`, same attribute names touched from
+dvc.py / vc.py (`t5_model.shared.weight`, `t5_model.lm_head.weight`, `t5_tokenizer`, `visual_encoder`, `proj_v2t`,
+`use_video`, `use_speech`) and the same state-dict key space (incl. the four aliased embedding keys),
+so `dvc.py`'s loop — forward, `loss.backward()`, `clip_grad_norm_`, `optimizer.step()`, time-token renorm — runs
+unchanged.  Underneath, forward and backward are single autograd nodes that call the hand-written sm_100a kernels
+(vidchapters_b200.engine); there is no CPU / PyTorch fallback: calling the module without a B200 raises.
+
+All parameters are views into ONE flat fp32 buffer (what the fused optimiser and the gradient all-reduce want); their
+`.grad`s are views into one flat fp32 gradient buffer.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .config import CONFIGS, param_shapes
+from .engine import Vid2SeqEngine
+from .init import init_state_dict
+
+
+def _get_tokenizer(tokenizer_path, num_bins=0):
+    """Same contract as the reference's model/vid2seq.py:10-18 (T5Tokenizer + <time=i> tokens)."""
+    if "t5" in tokenizer_path:
+        from transformers import T5Tokenizer
+        tokenizer = T5Tokenizer.from_pretrained(tokenizer_path, local_files_only=True)
+        if num_bins:
+            tokenizer.add_tokens(["<time=" + str(i) + ">" for i in range(num_bins)])
+    else:
+        raise NotImplementedError(tokenizer_path)
+    return tokenizer
+
+
+class _Node(nn.Module):
+    """Bare container used to reproduce the reference's module tree (and hence its state-dict keys)."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("sub-modules of vidchapters_b200.Vid2Seq are parameter containers; call the model itself")
+
+
+class _Embedding(_Node):
+    def forward(self, ids):  # API compatibility only (vid2seq.py:71 calls encoder.embed_tokens); not on the hot path
+        return torch.nn.functional.embedding(ids, self.weight)
+
+
+class _Vid2SeqFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, anchor, video, input_ids, input_mask, output_ids, output_mask, cached):
+        eng = module.engine
+        loss, ectx = eng.forward(video, input_ids, input_mask, output_ids, output_mask, video_cached=cached)
+        ctx.module, ctx.ectx = module, ectx
+        ctx.set_materialize_grads(False)
+        B, T = ectx["B"], ectx["T"]
+        vid = ectx["vid_f32"]
+        vid = vid.view(B, T, -1) if vid is not None else loss.new_zeros(0)
+        return loss.view(()), vid
+
+    @staticmethod
+    def backward(ctx, grad_loss, grad_vid):
+        module = ctx.module
+        module._begin_backward()
+        if grad_loss is None:
+            grad_loss = torch.zeros(1, device=module._flat.device)
+        dvideo = module.engine.backward(ctx.ectx, grad_loss, grad_vid)
+        ctx.ectx = None
+        module._end_backward()
+        return None, None, dvideo, None, None, None, None, None
+
+
+class Vid2Seq(nn.Module):
+    def __init__(self, t5_path, num_features=100, embed_dim=768, depth=12, heads=12, mlp_dim=2048, vis_drop=0.0,
+                 tokenizer=None, enc_drop=0.0, dec_drop=0.1, use_speech=True, use_video=True, num_bins=100,
+                 label_smoothing=0.1, *, t5_config: Optional[dict] = None, seed: int = 0, ops=None):
+        """`t5_path` selects the T5 shape ("t5-base" / "t5-large" in the path, like the reference's from_pretrained
+        directory name).  Weights are seeded-random in the reference's init scheme unless a checkpoint is loaded with
+        `load_state_dict` (offline image: no pretrained files).  `t5_config`, `seed`, `ops` are extensions: an explicit
+        shape dict, the init seed, and an injected op table (tests inject the torch oracle table on CPU)."""
+        super().__init__()
+        if t5_config is None:
+            key = "t5-large" if "large" in str(t5_path) else "t5-base"
+            t5_config = dict(CONFIGS[key])
+        cfg = dict(t5_config)
+        if tokenizer is not None:
+            cfg["base_vocab"] = len(tokenizer) - num_bins
+        cfg.update(num_bins=num_bins, num_features=num_features, embed_dim=embed_dim, depth=depth, heads=heads,
+                   mlp_dim=mlp_dim)
+        self.cfg = cfg
+        self.t5_tokenizer = tokenizer
+        self.use_speech, self.use_video = use_speech, use_video
+        self.vis_drop, self.enc_drop, self.dec_drop = vis_drop, enc_drop, dec_drop
+        self.label_smoothing = label_smoothing
+        self._ops = ops
+        self._engine: Optional[Vid2SeqEngine] = None
+        self._shadow_valid = False
+
+        # flat fp32 parameter buffer + the reference's module tree of Parameter views
+        probe = Vid2SeqEngine.layout_of(cfg)
+        self._layout, total = probe
+        self._flat = torch.zeros(total, dtype=torch.float32)
+        sd = init_state_dict(cfg, seed)
+        self._params = {}
+        for name, shape in param_shapes(cfg):
+            o, shp, n = self._layout[name]
+            self._flat[o:o + n].copy_(sd[name].reshape(-1))
+            par = nn.Parameter(self._flat[o:o + n].view(shp))
+            self._params[name] = par
+            self._attach(name, par)
+        del sd
+        t5 = self.t5_model
+        t5.encoder.add_module("embed_tokens", t5.shared)   # aliases, as in the reference (modeling_t5.py:1507-1532)
+        t5.decoder.add_module("embed_tokens", t5.shared)
+        lm = _Node()
+        lm.weight = t5.shared.weight                        # tied lm_head
+        t5.add_module("lm_head", lm)
+        t5.model_dim = cfg["d_model"]
+        if cfg["d_model"] == 768:
+            self.proj_v2t = None
+
+    # ------------------------------------------------------------------ module tree
+    def _attach(self, name, par):
+        parts = name.split(".")
+        node = self
+        for i, part in enumerate(parts[:-1]):
+            nxt = node._modules.get(part)
+            if nxt is None:
+                nxt = _Embedding() if (part == "shared") else _Node()
+                node.add_module(part, nxt)
+            node = nxt
+        node.register_parameter(parts[-1], par)
+
+    def _apply(self, fn, recurse=True):
+        """.to()/.cuda(): move the flat buffer and re-point every Parameter view (keeps them aliased)."""
+        new_flat = fn(self._flat)
+        if new_flat.dtype != torch.float32:
+            raise RuntimeError("vidchapters_b200.Vid2Seq keeps fp32 master weights (bf16 compute copies are internal)")
+        if new_flat is not self._flat:
+            self._flat = new_flat
+            for name, par in self._params.items():
+                o, shp, n = self._layout[name]
+                par.data = self._flat[o:o + n].view(shp)
+                par.grad = None
+            self._engine = None
+            self._shadow_valid = False
+        return self
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        r = super().load_state_dict(state_dict, strict=strict, assign=False)
+        self._shadow_valid = False
+        return r
+
+    # ------------------------------------------------------------------ engine
+    @property
+    def engine(self) -> Vid2SeqEngine:
+        if self._engine is None:
+            dev = self._flat.device
+            ops = self._ops
+            if ops is None:
+                if dev.type != "cuda":
+                    raise RuntimeError("vidchapters_b200.Vid2Seq runs on a B200 only: move it with .to('cuda') first "
+                                       "(there is no CPU fallback path)")
+                from .ops import CudaOps
+                with torch.cuda.device(dev):
+                    ops = CudaOps()
+            self._engine = Vid2SeqEngine(self.cfg, ops, dev, label_smoothing=self.label_smoothing,
+                                         use_video=self.use_video, use_speech=self.use_speech, flat_p=self._flat)
+            self._shadow_valid = False
+        return self._engine
+
+    def _refresh_shadow(self):
+        eng = self.engine
+        if not self._shadow_valid:
+            eng.sync_bf16()   # parameters may have been changed by load_state_dict / a stock optimiser / dvc.py's renorm
+        self._shadow_valid = False  # only the fused optimiser (which maintains the shadow itself) re-validates it
+
+    def _begin_backward(self):
+        if self._params["t5_model.shared.weight"].grad is None:
+            self.engine.zero_grad()
+
+    def _end_backward(self):
+        eng = self.engine
+        for name, par in self._params.items():
+            if par.grad is None:
+                par.grad = eng.g(name)
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, video, input_tokenized, output_tokenized):
+        if self.training and (self.vis_drop > 0 or self.enc_drop > 0 or self.dec_drop > 0):
+            raise NotImplementedError("dropout > 0 is not implemented yet in the B200 path; build with *_drop=0")
+        self._refresh_shadow()
+        cached = isinstance(video, dict)
+        if self.use_video:
+            vid_in = video["video"] if cached else video
+        else:
+            vid_in = None
+        input_ids = input_tokenized["input_ids"] if self.use_speech else None
+        input_mask = input_tokenized["attention_mask"] if self.use_speech else None
+        out_ids = output_tokenized["input_ids"]
+        out_mask = output_tokenized["attention_mask"]
+        anchor = self._params["t5_model.shared.weight"]
+        loss, vid = _Vid2SeqFn.apply(self, anchor, vid_in, input_ids, input_mask, out_ids, out_mask, cached)
+        video_dict = None
+        if self.use_video:
+            atts = video["atts_vis"] if cached else torch.ones(vid.shape[:2], dtype=torch.long, device=vid.device)
+            video_dict = {"video": vid, "atts_vis": atts}
+        return {"loss": loss}, video_dict
+
+    @torch.no_grad()
+    def forward_logits(self, video, input_tokenized, output_tokenized):
+        """Debug path: materialises (B,S,V) logits like `model.t5_model(...).logits` in the reference."""
+        self._refresh_shadow()
+        eng = self.engine
+        loss, ectx = eng.forward(video, input_tokenized["input_ids"], input_tokenized["attention_mask"],
+                                 output_tokenized["input_ids"], output_tokenized["attention_mask"], want_logits=True)
+        B, S = ectx["B"], ectx["S"]
+        return loss.view(()), ectx["logits"].view(B, S, -1)
+
+    @torch.no_grad()
+    def generate(self, video, input_tokenized, use_nucleus_sampling=False, num_beams=4, max_length=256, min_length=1,
+                 top_p=0.9, repetition_penalty=1.0, length_penalty=1.0, num_captions=1, temperature=1):
+        raise NotImplementedError("generate(): decoding is SURVEY §8(f) N1 (next after the train step); not built yet")
+
+
+def build_vid2seq_model(args, tokenizer):
+    """Same factory as the reference's model/__init__.py:4-19."""
+    return Vid2Seq(t5_path=args.model_name, num_features=args.max_feats, embed_dim=args.embedding_dim, depth=args.depth,
+                   heads=args.heads, mlp_dim=args.mlp_dim, vis_drop=args.visual_encoder_dropout,
+                   enc_drop=args.text_encoder_dropout, dec_drop=args.text_decoder_dropout, tokenizer=tokenizer,
+                   num_bins=args.num_bins, label_smoothing=args.label_smoothing, use_speech=args.use_speech,
+                   use_video=args.use_video)
