@@ -110,7 +110,9 @@ def measured_peaks():
 def cpu_oracle_step_time(cfg, B, T, L, S, steps, warmup, budget_s):
     from oracle import vid2seq_oracle as O
     from vidchapters_b200.init import init_state_dict
-    torch.set_num_threads(os.cpu_count() or 1)
+    # many-core hosts: the step is hundreds of small fp32 ops, so OpenMP barriers over 100+ threads dominate; 32 threads
+    # measured fastest (cores actually used are reported)
+    torch.set_num_threads(int(os.environ.get("VIDCHAP_CPU_THREADS", min(os.cpu_count() or 1, 32))))
     sd = init_state_dict(cfg, 0)
     params = {k: v.requires_grad_(True) for k, v in sd.items()}
     state = {}

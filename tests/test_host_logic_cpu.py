@@ -54,12 +54,12 @@ def test_engine_matches_oracle(cfg):
     o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True)
     o["loss"].backward()
     assert abs(loss.item() - o["loss"].item()) < 1e-4 * abs(o["loss"].item())
-    assert rel(ctx["logits"].view_as(o["logits"]), o["logits"]) < 1e-3          # tier A
-    assert torch.equal(ctx["logits"].view_as(o["logits"]).argmax(-1), o["logits"].argmax(-1))
+    assert rel(ctx["logits"].reshape(o["logits"].shape), o["logits"]) < 1e-3          # tier A
+    assert torch.equal(ctx["logits"].reshape(o["logits"].shape).argmax(-1), o["logits"].argmax(-1))
     for n in sd:
         assert rel(eng.g(n), sdg[n].grad) < 2e-2, n
     o32 = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=False)
-    assert rel(ctx["logits"].view_as(o32["logits"]), o32["logits"]) < 1.2e-2   # tier B: below the reference's own bf16 error
+    assert rel(ctx["logits"].reshape(o32["logits"].shape), o32["logits"]) < 1.2e-2   # tier B: below the reference's own bf16 error
 
 
 def test_bucket_lut_known_answers():

@@ -23,6 +23,7 @@ BF16_TOL, F32_TOL = 4e-3, 2e-5
 
 @pytest.mark.parametrize("M,N,K,a_mn,b_mn,tile_n", [
     (128, 64, 64, 0, 0, 64), (256, 256, 256, 0, 0, 256), (1600, 776, 768, 0, 0, 0), (1000, 2304, 768, 0, 0, 0),
+    (300, 1100, 768, 0, 0, 0), (130, 2004, 128, 0, 0, 0),  # ragged N: not a multiple of 8 (vocab 32100-style)
     (256, 256, 256, 0, 1, 256), (1001, 768, 3072, 0, 1, 0), (128, 128, 128, 1, 0, 128), (384, 512, 1000, 1, 1, 0),
 ])
 def test_gemm_layouts(cuda_ops, torch_ops, M, N, K, a_mn, b_mn, tile_n):
@@ -32,8 +33,9 @@ def test_gemm_layouts(cuda_ops, torch_ops, M, N, K, a_mn, b_mn, tile_n):
     A_st = A.t().contiguous() if a_mn else A
     B_st = B.t().contiguous() if b_mn else B
     for dt, tol in ((torch.float32, F32_TOL), (torch.bfloat16, BF16_TOL)):
-        out = torch.empty(M, N, device=DEV, dtype=dt)
-        ref = torch.empty(M, N, device=DEV, dtype=dt)
+        Np = (N + 7) // 8 * 8
+        out = torch.zeros(M, Np, device=DEV, dtype=dt)[:, :N]
+        ref = torch.zeros(M, Np, device=DEV, dtype=dt)[:, :N]
         cuda_ops.gemm(A_st, B_st, out, a_mn=bool(a_mn), b_mn=bool(b_mn), tile_n=tile_n)
         torch_ops.gemm(A_st, B_st, ref, a_mn=bool(a_mn), b_mn=bool(b_mn))
         assert rel(out, ref) < tol
@@ -226,17 +228,20 @@ def test_small_ops(cuda_ops, torch_ops):
             assert rel(a, r) < 1e-5 or (a - r).abs().max() < 1e-6, (i, rel(a, r))
 
 
-def test_cross_entropy(cuda_ops, torch_ops):
+@pytest.mark.parametrize("V", [32200, 32100, 1100])
+def test_cross_entropy(cuda_ops, torch_ops, V):
     g = gen(9)
-    n, V = 64, 32200
-    logits = (torch.randn(n, V, generator=g) * 3).to(DEV)
+    n = 64
+    Vp = (V + 7) // 8 * 8
+    logits = torch.zeros(n, Vp, device=DEV)[:, :V]
+    logits.copy_((torch.randn(n, V, generator=g) * 3).to(DEV))
     labels = torch.randint(0, V, (n,), generator=g).to(DEV)
     labels[::5] = -100
     nv = torch.tensor([float((labels != -100).sum())], device=DEV)
     out = []
     for ops in (cuda_ops, torch_ops):
         loss = torch.zeros(1, device=DEV)
-        dl = torch.zeros(n, V, device=DEV, dtype=torch.bfloat16)
+        dl = torch.zeros(n, Vp, device=DEV, dtype=torch.bfloat16)[:, :V]
         ops.cross_entropy(logits, labels, nv, 0.1, loss, dl)
         out.append((loss, dl))
     ref = torch.nn.functional.cross_entropy(logits, labels, ignore_index=-100, label_smoothing=0.1)

@@ -189,7 +189,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
         if (row_ok && col0 < p.N) {
-          const int ncols = min(32, p.N - col0);  // N is a multiple of 8 (checked on host)
+          const int ncols = min(32, p.N - col0);
+          const bool vec = (ncols & 7) == 0;  // ragged N (e.g. vocab 32100): the last chunk takes the scalar path
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= alpha;
           if (p.bias) {
@@ -197,12 +198,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
           }
           if (p.act == 2 && p.pre_out) {
-            uint4* dst = reinterpret_cast<uint4*>(p.pre_out + (long long)row * p.ldo + col0);
+            __nv_bfloat16* dstp = p.pre_out + (long long)row * p.ldo + col0;
+            if (vec) {
+              uint4* dst = reinterpret_cast<uint4*>(dstp);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j * 8 < ncols)
-                dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
-                                    pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+              for (int j = 0; j < 4; ++j)
+                if (j * 8 < ncols)
+                  dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                      pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) dstp[j] = __float2bfloat16(v[j]);
+            }
           }
           if (p.act == 1) {
 #pragma unroll
@@ -211,12 +218,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
           } else if (p.act == 3 || p.act == 4) {
-            const uint4* ax = reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ld_aux + col0);
+            const __nv_bfloat16* axp = p.aux + (long long)row * p.ld_aux + col0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (j * 8 < ncols) {
-                const uint4 a = __ldg(ax + j);
-                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+                uint32_t w[4];
+                if (vec) {
+                  const uint4 a = __ldg(reinterpret_cast<const uint4*>(axp) + j);
+                  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int c0 = j * 8 + e * 2;
+                    const float lo = c0 < ncols ? __bfloat162float(axp[c0]) : 0.f;
+                    const float hi = c0 + 1 < ncols ? __bfloat162float(axp[c0 + 1]) : 0.f;
+                    w[e] = pack_bf16x2(lo, hi);
+                  }
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
@@ -232,33 +250,55 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (p.residual) {
-            const float4* rs = reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + col0);
+            const float* rsp = p.residual + (long long)row * p.ldr + col0;
+            if (vec) {
+              const float4* rs = reinterpret_cast<const float4*>(rsp);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (j * 4 < ncols) {
-                const float4 r = rs[j];
-                v[j * 4 + 0] += r.x; v[j * 4 + 1] += r.y; v[j * 4 + 2] += r.z; v[j * 4 + 3] += r.w;
+              for (int j = 0; j < 8; ++j) {
+                if (j * 4 < ncols) {
+                  const float4 r = rs[j];
+                  v[j * 4 + 0] += r.x; v[j * 4 + 1] += r.y; v[j * 4 + 2] += r.z; v[j * 4 + 3] += r.w;
+                }
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += rsp[j];
             }
           }
           if (p.out_fp32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0);
-            if (p.atomic) {
+            float* dstf = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
+            if (vec) {
+              float4* dst = reinterpret_cast<float4*>(dstf);
+              if (p.atomic) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (j * 4 < ncols) atomicAdd(dst + j, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
+                for (int j = 0; j < 8; ++j)
+                  if (j * 4 < ncols) atomicAdd(dst + j, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (j * 4 < ncols) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+              }
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (j * 4 < ncols) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+              for (int j = 0; j < 32; ++j) {
+                if (j < ncols) {
+                  if (p.atomic) atomicAdd(dstf + j, v[j]); else dstf[j] = v[j];
+                }
+              }
             }
           } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0);
+            __nv_bfloat16* dstb = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
+            if (vec) {
+              uint4* dst = reinterpret_cast<uint4*>(dstb);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j * 8 < ncols)
-                dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
-                                    pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+              for (int j = 0; j < 4; ++j)
+                if (j * 8 < ncols)
+                  dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                      pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) dstb[j] = __float2bfloat16(v[j]);
+            }
           }
         }
       }
@@ -297,7 +337,6 @@ using namespace vc;
 extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   VC_CHECK(a != nullptr, "vc_gemm_bf16: null args");
   VC_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "vc_gemm_bf16: bad dims M=%d N=%d K=%d", a->M, a->N, a->K);
-  VC_CHECK(a->N % 8 == 0, "vc_gemm_bf16: N=%d must be a multiple of 8", a->N);
   VC_CHECK(a->lda % 8 == 0 && a->ldb % 8 == 0, "vc_gemm_bf16: lda/ldb must be multiples of 8 elements (16 B)");
   VC_CHECK(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->B & 15) == 0 && ((uintptr_t)a->out & 15) == 0,
            "vc_gemm_bf16: A/B/out must be 16-byte aligned");

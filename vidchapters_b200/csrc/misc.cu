@@ -128,15 +128,20 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
   const float* z = logits + (long long)row * ld;
   __nv_bfloat16* dz = dlogits ? dlogits + (long long)row * ldd : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V4 = V & ~3, V8 = V & ~7;
   if (y < 0) {  // ignore_index: zero gradient row
-    if (dz) for (int c = tid * 8; c < V; c += 256 * 8) *reinterpret_cast<uint4*>(dz + c) = make_uint4(0, 0, 0, 0);
+    if (dz) {
+      for (int c = tid * 8; c < V8; c += 256 * 8) *reinterpret_cast<uint4*>(dz + c) = make_uint4(0, 0, 0, 0);
+      for (int c = V8 + tid; c < V; c += 256) dz[c] = __float2bfloat16(0.f);
+    }
     return;
   }
   float mx = -INFINITY;
-  for (int c = tid * 4; c < V; c += 256 * 4) {
+  for (int c = tid * 4; c < V4; c += 256 * 4) {
     const float4 v = *reinterpret_cast<const float4*>(z + c);
     mx = fmaxf(fmaxf(fmaxf(mx, v.x), fmaxf(v.y, v.z)), v.w);
   }
+  for (int c = V4 + tid; c < V; c += 256) mx = fmaxf(mx, z[c]);
   mx = warp_max_f(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
@@ -144,11 +149,12 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
   __syncthreads();
   mx = bcast[0];
   float se = 0.f, sz = 0.f;
-  for (int c = tid * 4; c < V; c += 256 * 4) {
+  for (int c = tid * 4; c < V4; c += 256 * 4) {
     const float4 v = *reinterpret_cast<const float4*>(z + c);
     se += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
     sz += v.x + v.y + v.z + v.w;
   }
+  for (int c = V4 + tid; c < V; c += 256) { se += __expf(z[c] - mx); sz += z[c]; }
   se = warp_sum_f(se); sz = warp_sum_f(sz);
   __syncthreads();
   if (lane == 0) red[warp] = se;
@@ -171,7 +177,7 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
   }
   if (dz) {
     const float inv_nv = 1.0f / nv, inv_se = 1.0f / se, sm = eps / (float)V;
-    for (int c = tid * 8; c < V; c += 256 * 8) {
+    for (int c = tid * 8; c < V8; c += 256 * 8) {
       const float4 a = *reinterpret_cast<const float4*>(z + c);
       const float4 b = *reinterpret_cast<const float4*>(z + c + 4);
       float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -182,6 +188,8 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
       *reinterpret_cast<uint4*>(dz + c) = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
                                                      pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
     }
+    for (int c = V8 + tid; c < V; c += 256)
+      dz[c] = __float2bfloat16((__expf(z[c] - mx) * inv_se - sm - (c == y ? (1.0f - eps) : 0.0f)) * inv_nv);
   }
 }
 
@@ -279,7 +287,7 @@ extern "C" int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C,
 }
 extern "C" int vc_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, const float* n_valid, float smoothing,
                                 float* loss_out, void* dlogits_bf16, int64_t ldd, int n, int V, void* stream) {
-  VC_CHECK(n > 0 && V % 8 == 0 && ld % 4 == 0 && ldd % 8 == 0, "vc_cross_entropy: V/ld alignment");
+  VC_CHECK(n > 0 && ld % 4 == 0 && (dlogits_bf16 == nullptr || ldd % 8 == 0), "vc_cross_entropy: ld alignment");
   VC_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ST(stream)));
   cross_entropy_kernel<<<n, 256, 0, ST(stream)>>>(logits, ld, (const long long*)labels, n_valid, smoothing, loss_out,
                                                   (__nv_bfloat16*)dlogits_bf16, ldd, V);

@@ -437,10 +437,11 @@ class Vid2SeqEngine:
         rstd_d = self._e(B * S)
         ops.norm_fwd(0, y, self.pv("t5_model.decoder.final_layer_norm.weight"), None, out_bf16=seq, rstd=rstd_d, eps=1e-6,
                      out_scale=d ** -0.5)
-        logits = self._e(B * S, self.V)
+        Vp = (self.V + 7) // 8 * 8   # leading dimension padded to 16 B (vc.py's vocab 32100 is not a multiple of 8)
+        logits = self._e(B * S, Vp)[:, :self.V]
         ops.gemm(seq, self.pb("t5_model.shared.weight"), logits)
         loss = self._e(1)
-        dlogits = self._e(B * S, self.V, dtype=bf)
+        dlogits = self._e(B * S, Vp, dtype=bf)[:, :self.V]
         ops.cross_entropy(logits, labels.view(-1), n_valid, self.label_smoothing, loss, dlogits)
         ctx.update(memory=memory, mem_mask=mem_mask, dec_in=dec_in, dec_x=y, dec_rstd=rstd_d, seq=seq, dlogits=dlogits,
                    lut_d=lut_d, vid_f32=vid_f32)

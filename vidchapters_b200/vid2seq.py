@@ -216,7 +216,7 @@ class Vid2Seq(nn.Module):
         loss, ectx = eng.forward(video, input_tokenized["input_ids"], input_tokenized["attention_mask"],
                                  output_tokenized["input_ids"], output_tokenized["attention_mask"], want_logits=True)
         B, S = ectx["B"], ectx["S"]
-        return loss.view(()), ectx["logits"].view(B, S, -1)
+        return loss.view(()), ectx["logits"].reshape(B, S, -1)
 
     @torch.no_grad()
     def generate(self, video, input_tokenized, use_nucleus_sampling=False, num_beams=4, max_length=256, min_length=1,
