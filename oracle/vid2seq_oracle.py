@@ -54,8 +54,20 @@ class _EmuMatmul(torch.autograd.Function):
 
 
 class Arith:
-    def __init__(self, emulate_bf16: bool):
+    def __init__(self, emulate_bf16: bool, flash_rounding: bool = False):
         self.emu = emulate_bf16
+        # flash_rounding: the probabilities that enter P.V are the UN-normalised exp(s - rowmax) rounded to bf16, the
+        # division by the row sum happens after the product — the rounding points of any flash-attention kernel with
+        # bf16 operands.  (Normalised-then-rounded P, the default, is what eager bf16 attention does; the two differ by
+        # ~3.5e-3 rel-L2 on the logits purely through the rounding realisation, see tests/test_e2e_gpu.py.)
+        self.flash = flash_rounding and emulate_bf16
+
+    def softmax_pv(self, scores, v):
+        if not self.flash:
+            return self.matmul(F.softmax(scores.float(), dim=-1), v)
+        m = scores.max(-1, keepdim=True).values
+        e = torch.exp(scores - m)
+        return self.matmul(e, v) / e.sum(-1, keepdim=True)
 
     def matmul(self, a, b):
         if self.emu:
@@ -85,8 +97,7 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, ar: Ari
         qkv = qkv.reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
         attn = ar.matmul(q, k.transpose(-2, -1)) * ((C // H) ** -0.5)  # vit.py:47
-        attn = attn.softmax(dim=-1)
-        o = ar.matmul(attn, v).transpose(1, 2).reshape(B, N, C)
+        o = ar.softmax_pv(attn, v).transpose(1, 2).reshape(B, N, C)        # vit.py:48-51
         x = x + ar.linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])
         h = F.layer_norm(x, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
         h = ar.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
@@ -139,8 +150,7 @@ def t5_attention(sd, p, H, dkv, x, kv, position_bias, ar: Arith):
     v = ar.linear(kv, sd[p + "v.weight"]).view(B, Lk, H, dkv).transpose(1, 2)
     scores = ar.matmul(q, k.transpose(3, 2))
     scores = scores + position_bias
-    w = F.softmax(scores.float(), dim=-1)
-    o = ar.matmul(w, v).transpose(1, 2).contiguous().view(B, Lq, H * dkv)
+    o = ar.softmax_pv(scores, v).transpose(1, 2).contiguous().view(B, Lq, H * dkv)  # fp32 softmax, :569-580
     return ar.linear(o, sd[p + "o.weight"])
 
 
@@ -197,12 +207,12 @@ def t5_decoder(sd, cfg, dec_ids, dec_mask, enc_h, enc_mask, ar: Arith, pfx="t5_m
 
 
 def vid2seq_forward(sd, cfg, video, input_ids, input_mask, output_ids, output_mask, *, emulate_bf16=False,
-                    label_smoothing=0.1, video_is_cached=False):
+                    label_smoothing=0.1, video_is_cached=False, flash_rounding=False):
     """model/vid2seq.py:58-98 (+ modeling_t5.py:1587-1738).  Dropout-free (p=0 / eval) restatement.
 
     Returns dict(loss, logits (B,S,V), video (B,T,d), memory (B,T+L,d)).
     """
-    ar = Arith(emulate_bf16)
+    ar = Arith(emulate_bf16, flash_rounding)
     d = cfg["d_model"]
     if video_is_cached:
         vid = video

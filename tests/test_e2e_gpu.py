@@ -1,7 +1,8 @@
 """End-to-end parity of the CUDA path (through the drop-in module and the C ABI) on the GPU.
 
-Tier A: vs the bf16-operand emulation oracle on the same device: logits rel-L2 <= 1e-3... the flash
-        softmax rounds un-normalised probabilities, so the gate used is 3e-3 (measured value is printed);
+Tier A: vs the bf16-operand emulation oracle on the same device evaluated at the kernels' rounding points
+        (flash_rounding=True: un-normalised probabilities rounded to bf16): logits rel-L2 <= 1e-3, time-token argmax
+        bit-exact.  The same oracle with normalised-then-rounded P differs from it by ~3.5e-3 on its own (printed);
 Tier B: vs the golden vectors minted from the real fp32 reference: logits rel-L2 must stay below the reference's own
         bf16 error (1.2e-2), loss within 1e-3 rel, time-token argmax bit-exact.
 """
@@ -61,10 +62,13 @@ def test_cuda_vs_golden_and_emulation_oracle(name):
     assert agree >= 0.99
     # ---- tier A: emulation oracle on the same device
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in m._params.items()}
-    o = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True)
+    o = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True)
     ea = rel(logits, o["logits"])
-    print(f"[{name}] tier-A logits rel-L2 vs bf16-operand emulation oracle: {ea:.3e}")
-    assert ea < 3e-3
+    with torch.no_grad():
+        o_n = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True)
+    print(f"[{name}] tier-A logits rel-L2 vs bf16-operand emulation oracle (kernel rounding points): {ea:.3e}; "
+          f"vs the normalised-P emulation: {rel(logits, o_n['logits']):.3e}")
+    assert ea < 1e-3
     assert torch.equal(logits[..., V0:].argmax(-1), o["logits"][..., V0:].argmax(-1))   # time tokens: bit-exact
     assert abs(loss.item() - o["loss"].item()) < 5e-4 * abs(o["loss"].item())
     # ---- backward through the module surface

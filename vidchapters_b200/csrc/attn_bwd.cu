@@ -44,7 +44,7 @@ struct AttnBwdParams {
 
 constexpr int kBwdSmemTiles = 16384 * 2 /*K,V*/ + 2 * 16384 /*Q ring*/ + 2 * 16384 /*dO ring*/ + 32768 /*P*/ + 32768 /*dS*/;
 constexpr int kBwdRelMax = 2304;  // floats of d(bias) scratch: Lq + 128 <= 2304
-constexpr int kAttnBwdSmem = kBwdSmemTiles + kBwdRelMax * 4 + 256;
+constexpr int kAttnBwdSmem = kBwdSmemTiles + 2 * kBwdRelMax * 4 + 128 + 256;  // + d(bias) scratch + bias window + key mask
 
 __global__ void __launch_bounds__(192, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -57,7 +57,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sP = sDO + 2 * 16384;   // 32 KB
   uint8_t* sDS = sP + 32768;       // 32 KB
   float* s_rel = reinterpret_cast<float*>(sDS + 32768);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rel + kBwdRelMax);
+  float* s_bias = s_rel + kBwdRelMax;   // bias(k - q) * log2e for this key tile: slot (k - k0) + (Lq - 1 - q)
+  uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_bias + kBwdRelMax);  // key mask of this tile (128 bytes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 128);
   uint64_t* kv_full = bars + 0;
   uint64_t* qd_full = bars + 1;   // [2]
   uint64_t* qd_empty = bars + 3;  // [2]
@@ -86,6 +88,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int rel_base = k0;       // slot = (k - k0) + (Lq - 1 - q)
   if (p.dbias_rel)
     for (int i = threadIdx.x; i < n_rel; i += blockDim.x) s_rel[i] = 0.f;
+  if (p.bias_rel) {
+    const float* brow_g = p.bias_rel + (long long)h * (p.Lq + p.Lk - 1);
+    for (int i = threadIdx.x; i < n_rel; i += blockDim.x)
+      s_bias[i] = (rel_base + i < p.Lq + p.Lk - 1) ? __ldg(brow_g + rel_base + i) * kBLog2e : 0.f;
+  }
+  if (p.kmask && threadIdx.x < 128)
+    s_mask[threadIdx.x] = (k0 + (int)threadIdx.x < p.Lk) ? p.kmask[(long long)b * p.Lk + k0 + threadIdx.x] : 0;
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -148,7 +157,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint8_t* mrow = p.kmask ? p.kmask + (long long)b * p.Lk : nullptr;
+    const uint8_t* mrow = p.kmask ? s_mask : nullptr;   // indexed by k - k0
     for (int i = 0; i < nqt; ++i) {
       const int q0 = (qt0 + i) * kBT;
       const int q = q0 + r;
@@ -156,7 +165,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const long long stat_idx = ((long long)b * p.H + h) * p.Lq + (q_ok ? q : 0);
       const float lse2 = p.lse2[stat_idx];
       const float delta = p.delta[stat_idx];
-      const float* brow = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) + (p.Lq - 1 - q) : nullptr;
+      const float* brow = (p.bias_rel && q_ok) ? s_bias + (p.Lq - 1 - q) : nullptr;   // indexed by k - k0
       // d(bias): is the whole tile inside one bucket?  then one add per row instead of one per element
       bool uniform = false;
       if (p.dbias_rel && p.bucket_lut) {
@@ -177,8 +186,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int j = 0; j < 32; ++j) {
           const int k = k0 + c * 32 + j;
           float s2 = sv[j] * p.scale_log2e;
-          if (brow && k < p.Lk) s2 += __ldg(brow + k) * kBLog2e;
-          const bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[k]);
+          if (brow && k < p.Lk) s2 += brow[c * 32 + j];
+          const bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[c * 32 + j]);
           s2 = masked ? kBMasked : s2;
           const float pj = (q_ok && k < p.Lk) ? fast_exp2(s2 - lse2) : 0.0f;
           const float dsj = pj * (dp[j] - delta);

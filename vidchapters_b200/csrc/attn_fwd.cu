@@ -38,7 +38,11 @@ struct AttnFwdParams {
   float scale_log2e;
 };
 
-constexpr int kAttnFwdSmem = 16384 /*Q*/ + 2 * 16384 /*K*/ + 2 * 16384 /*V*/ + 32768 /*P*/ + 512 /*barriers*/;
+// smem: Q 16K | K 2x16K | V 16K | P 32K | bias window (Lk+128 floats) | key mask (Lk bytes) | barriers.
+// The bias/mask staging matters: with two 100 KB CTAs per SM almost no L1 is left, so per-element global loads of the
+// bias row went to L2 and made the kernel 10x slower (profiles/r01_launches_before.txt).
+constexpr int kAttnFwdTiles = 16384 + 2 * 16384 + 16384 + 32768;
+constexpr int kAttnMaxLk = 2176;  // bias window + mask must fit: (Lk+128)*4 + Lk bytes <= ~11.5 KB
 
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -47,16 +51,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;
   uint8_t* sV = sK + 2 * 16384;
-  uint8_t* sP = sV + 2 * 16384;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  uint8_t* sP = sV + 16384;
+  float* sBias = reinterpret_cast<float*>(sP + 32768);
+  const int bias_elems = (p.Lk + 128 + 3) & ~3;
+  uint8_t* sMask = reinterpret_cast<uint8_t*>(sBias + bias_elems);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + ((p.Lk + 15) & ~15));
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint64_t* o_read = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;
+  uint64_t* v_empty = bars + 6;
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint64_t* o_read = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -66,12 +75,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (smem_u32(smem) & 1023) __trap();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     mbar_init(o_read, 128);
     fence_barrier_init();
+  }
+  // stage this query tile's bias window (index k + 127 - r == (k - q + Lq - 1) - (Lq - 128 - q0)) and the key mask
+  {
+    const int win0 = p.Lq - 128 - q0;  // global bias index of window slot 0 (may be negative: clamp, never used)
+    if (p.bias_rel) {
+      const float* brow = p.bias_rel + (long long)h * (p.Lq + p.Lk - 1);
+      for (int i = threadIdx.x; i < p.Lk + 127; i += blockDim.x) {
+        const int gi = win0 + i;
+        sBias[i] = (gi >= 0 && gi < p.Lq + p.Lk - 1) ? __ldg(brow + gi) * kLog2e : 0.f;
+      }
+    }
+    if (p.kmask) {
+      const uint8_t* mrow = p.kmask + (long long)b * p.Lk;
+      for (int i = threadIdx.x; i < p.Lk; i += blockDim.x) sMask[i] = mrow[i];
+    }
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -91,10 +117,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_load_3d(sQ, &tmQ, q_full, p.q_col + h * kD, q0, b);
     for (int j = 0; j < nkt; ++j) {
       const int st = j & 1;
-      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-      mbar_arrive_expect_tx(&kv_full[st], 32768);
-      tma_load_3d(sK + st * 16384, &tmK, &kv_full[st], p.k_col + h * kD, j * kTK, b);
-      tma_load_3d(sV + st * 16384, &tmV, &kv_full[st], p.v_col + h * kD, j * kTK, b);
+      mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+      mbar_arrive_expect_tx(&k_full[st], 16384);
+      tma_load_3d(sK + st * 16384, &tmK, &k_full[st], p.k_col + h * kD, j * kTK, b);
+      mbar_wait(v_empty, (j & 1) ^ 1);
+      mbar_arrive_expect_tx(v_full, 16384);
+      tma_load_3d(sV, &tmV, v_full, p.v_col + h * kD, j * kTK, b);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -104,23 +132,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
     for (int j = 0; j < nkt; ++j) {
       const int st = j & 1;
-      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      mbar_wait(&k_full[st], (j >> 1) & 1);
       tc_fence_after();
       const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + st * 16384), 0, 1024);
 #pragma unroll
       for (int k = 0; k < kD / 16; ++k) tc_mma_bf16(tmem_S, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0);
+      tc_commit(&k_empty[st]);  // K stage is free as soon as S(j) has been computed
       tc_commit(s_full);
-      // P(j) written and S(j) consumed; O(j-1) read back
+      // P(j) written and S(j) consumed; O(j-1) read back; V(j) landed
       mbar_wait(p_full, j & 1);
       if (j > 0) mbar_wait(o_read, (j - 1) & 1);
+      mbar_wait(v_full, j & 1);
       tc_fence_after();
-      const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + st * 16384), 0, 1024);
+      const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 0, 1024);
 #pragma unroll
       for (int k = 0; k < kTK / 16; ++k) {
         const uint64_t pd = make_smem_desc_sw128(smem_u32(sP + (k >> 2) * 16384) + (k & 3) * 32, 0, 1024);
         tc_mma_bf16(tmem_O, pd, vdesc + (uint64_t)(k * 128), idesc_o, k > 0);
       }
-      tc_commit(&kv_empty[st]);
+      tc_commit(v_empty);
       tc_commit(o_full);
     }
   } else if (warp >= 2) {
@@ -129,8 +159,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = quarter * 32 + lane;  // row in tile == TMEM lane
     const int q = q0 + r;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const float* brow = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) + (p.Lq - 1 - q) : nullptr;
-    const uint8_t* mrow = p.kmask ? p.kmask + (long long)b * p.Lk : nullptr;
+    const float* brow = p.bias_rel ? sBias + (127 - r) : nullptr;  // brow[k] = bias(k - q) * log2e
+    const uint8_t* mrow = p.kmask ? sMask : nullptr;
     float m_run = -INFINITY, l_run = 0.0f;
     float o_acc[kD];
 #pragma unroll
@@ -151,7 +181,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int i = 0; i < 32; ++i) {
           const int k = k0 + c * 32 + i;
           float s2 = v[i] * p.scale_log2e;
-          if (brow && k < p.Lk) s2 += __ldg(brow + k) * kLog2e;
+          if (brow && k < p.Lk) s2 += brow[k];
           bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[k]);
           s2 = masked ? kMasked : s2;
           s2 = (k < p.Lk) ? s2 : -INFINITY;
@@ -171,7 +201,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int i = 0; i < 32; ++i) {
           const int k = k0 + c * 32 + i;
           float s2 = v[i] * p.scale_log2e;
-          if (brow && k < p.Lk) s2 += __ldg(brow + k) * kLog2e;
+          if (brow && k < p.Lk) s2 += brow[k];
           bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[k]);
           s2 = masked ? kMasked : s2;
           const float pv = (k < p.Lk) ? fast_exp2(s2 - m_new) : 0.0f;
@@ -250,13 +280,16 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
   p.lse2 = a->lse2; p.bias_rel = a->bias_rel; p.kmask = a->kmask; p.causal = a->causal;
   p.scale_log2e = a->scale * kLog2e;
+  VC_CHECK(a->Lk <= kAttnMaxLk, "vc_attn_fwd: Lk=%d exceeds the %d keys the bias/mask staging supports", a->Lk, kAttnMaxLk);
+  const int smem_bytes = kAttnFwdTiles + ((a->Lk + 128 + 3) & ~3) * 4 + ((a->Lk + 15) & ~15) + 128;
   static bool attr = false;
   if (!attr) {
-    VC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwdSmem));
+    VC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kAttnFwdTiles + (kAttnMaxLk + 128) * 4 + kAttnMaxLk + 128));
     attr = true;
   }
   dim3 grid((a->Lq + kTQ - 1) / kTQ, a->H, a->B);
-  attn_fwd_kernel<<<grid, 192, kAttnFwdSmem, st>>>(tmQ, tmK, tmV, p);
+  attn_fwd_kernel<<<grid, 192, smem_bytes, st>>>(tmQ, tmK, tmV, p);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -1,0 +1,71 @@
+"""Static-shape train step replayed as a CUDA graph.
+
+A dvc.py step at fixed (B, T, L, S) is ~1000 kernel launches; issued one by one from Python the host cannot keep a
+B200 busy (measured: 75 ms/step of which the GPU works ~45 ms).  `GraphedTrainStep` captures forward + backward
+(zeroing of the flat gradient buffer included) once into a `torch.cuda.CUDAGraph` and replays it per step; the
+optimiser tail (gradient all-reduce for N>1, clip + Adam + renorm: 5 launches) stays eager so NCCL is never captured
+and the learning rate / Adam step count remain plain host values.
+
+The semantics are exactly `loss_dict, _ = model(...); optimizer.zero_grad(); loss.backward(); optimizer.step()`
+(dvc.py:70-116) on the batch copied into the static input buffers.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, video, input_ids, output_ids, warmup_steps: int = 2):
+        """`video` (B,T,768) float, `input_ids` (B,L), `output_ids` (B,S) int64: example batch (any device; shapes are
+        frozen).  Masks are `ids != 0` as in dvc.py:44-53.  NOTE: the warm-up runs real optimiser steps on the example
+        batch unless warmup_steps=0 (then the caller must have run at least one eager step at these shapes)."""
+        self.model, self.optimizer = model, optimizer
+        dev = model._flat.device
+        assert dev.type == "cuda", "GraphedTrainStep needs the model on a CUDA device"
+        self.video = video.to(dev, copy=True).float().contiguous()
+        self.input_ids = input_ids.to(dev, copy=True).contiguous()
+        self.output_ids = output_ids.to(dev, copy=True).contiguous()
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup_steps):
+                self._fwd_bwd()
+                optimizer.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        model._refresh_shadow()            # outside the graph: the fused optimiser keeps the shadow valid afterwards
+        model._shadow_valid = True
+        optimizer.zero_grad(set_to_none=True)   # so the captured backward starts by zeroing the flat gradient buffer
+        ops = model.engine.ops
+        n0 = ops.launches
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+        self.launches_per_replay = ops.launches - n0   # libvidchap kernels inside the captured graph
+        self.replays = 0
+
+    def _fwd_bwd(self):
+        m = self.model
+        it = {"input_ids": self.input_ids, "attention_mask": self.input_ids != 0}
+        ot = {"input_ids": self.output_ids, "attention_mask": self.output_ids != 0}
+        loss_dict, _ = m(self.video, it, ot)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss_dict["loss"].backward()
+        return loss_dict["loss"].detach()
+
+    def __call__(self, video=None, input_ids=None, output_ids=None):
+        """Copies the batch (host pinned or device tensors) into the static buffers, replays forward+backward, runs the
+        optimiser tail.  Returns the (static) 0-dim device loss tensor; `.item()` it to read the value."""
+        if video is not None:
+            self.video.copy_(video, non_blocking=True)
+        if input_ids is not None:
+            self.input_ids.copy_(input_ids, non_blocking=True)
+        if output_ids is not None:
+            self.output_ids.copy_(output_ids, non_blocking=True)
+        if not self.model._shadow_valid:     # parameters were changed from outside (load_state_dict, stock optimiser)
+            self.model.engine.sync_bf16()
+        self.graph.replay()
+        self.replays += 1
+        self.model.engine.ops.launches += self.launches_per_replay
+        self.optimizer.step()
+        return self.loss
