@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-gemms", default="")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -258,15 +259,26 @@ def main():
         s.record()
         r = orig_gemm(A, Bm, out, **kw)
         e.record()
-        rec.append((s, e, 2.0 * M * N * K))
+        rec.append((s, e, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), str(out.dtype).replace("torch.", ""),
+                                            int(kw.get("act", 0)), int(kw.get("atomic", False)), int(kw.get("splits", 1)))))
         return r
 
     ops.gemm = timed_gemm
     step(False, False)
     torch.cuda.synchronize()
     ops.gemm = orig_gemm
-    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in rec)
-    gemm_flops = sum(f for _, _, f in rec)
+    gemm_ms = sum(r[0].elapsed_time(r[1]) for r in rec)
+    gemm_flops = sum(r[2] for r in rec)
+    if args.dump_gemms and rank == 0:
+        agg = {}
+        for s_, e_, f_, key in rec:
+            a = agg.setdefault(key, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += s_.elapsed_time(e_); a[2] += f_
+        os.makedirs(os.path.dirname(args.dump_gemms) or ".", exist_ok=True)
+        with open(args.dump_gemms, "w") as fo:
+            fo.write("# M N K a_mn b_mn out act atomic splits | launches total_ms TFLOP/s  (one instrumented step)\n")
+            for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                fo.write(" ".join(str(x) for x in key) + f" | {a[0]} {a[1]:.3f} {a[2] / (a[1] * 1e-3) / 1e12:.1f}\n")
     sustained, burst, peak_src = measured_peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
 

@@ -30,7 +30,9 @@ int vc_device_check(void);          /* VC_OK iff the current device is sm_100 (B
  * dgrad/wgrad.  a_mn_major: A is stored [K][M] (lda = row stride) instead of [M][K]; b_mn_major: B is stored
  * [K][N] instead of [N][K].  Epilogue order: *alpha, +bias[N], (pre_out=copy), act, +residual, store.
  *   act: 0 none | 1 relu | 2 gelu(erf) | 3 multiply by relu'(aux) | 4 multiply by gelu'(aux)
- *   atomic=1 (fp32 out only): atomicAdd into out; required when splits>1 (split-K over `splits` CTAs). */
+ *   atomic=1 (fp32 out only): atomicAdd into out; required when splits>1 (split-K over `splits` CTAs).
+ * Dropout everywhere in this ABI is counter-based: p16 = round(p*65536), element kept iff a 16-bit hash of
+ * (seed, element index) >= p16, kept values scaled by 65536/(65536-p16); p16 = 0 disables it. */
 typedef struct vc_gemm_args {
   const void* A; const void* B;
   int64_t lda, ldb;
@@ -46,6 +48,7 @@ typedef struct vc_gemm_args {
   const float* alpha_dev;   /* optional device scalar multiplied into alpha (upstream loss gradient) */
   int32_t splits;
   int32_t tile_n;   /* 0 = auto, else 64/128/256 */
+  uint32_t drop_seed, drop_p16;  /* dropout after act, before +residual; keep iff rnd16(seed, row*N+col) >= p16 */
 } vc_gemm_args;
 int vc_gemm_bf16(const vc_gemm_args* args, void* stream);
 
@@ -67,6 +70,7 @@ typedef struct vc_attn_args {
   const uint8_t* kmask;
   int32_t causal;
   float scale;
+  uint32_t drop_seed, drop_p16;  /* dropout on the probabilities (modeling_t5.py:572-574, vit.py:49); index ((b*H+h)*Lq+q)*Lk+k */
 } vc_attn_args;
 int vc_attn_fwd(const vc_attn_args* args, void* stream);
 
@@ -93,16 +97,20 @@ int vc_attn_bwd(const vc_attn_bwd_args* args, void* stream);
  * rstd (and mean for kind 1) [M] are saved for the backward. */
 int vc_norm_fwd(int kind, const float* x, const float* w, const float* bias, void* out_bf16, float* out_f32, float* rstd,
                 float* mean, int M, int D, float eps, float out_scale, int rows_per_batch, int out_batch_stride,
-                int out_row_offset, void* stream);
-/* g = dL/dy fp32, read through the same row map.  dx (+)= d/dx; dx_bf16 (optional) = bf16 copy of the final dx;
- * dw/db accumulated with atomics (db only for kind 1; either may be NULL). */
+                int out_row_offset, uint32_t drop_seed, uint32_t drop_p16, void* stream);
+/* g = dL/dy fp32, read through the same row map (and through the forward's output-dropout mask g_drop_*).
+ * dx (+)= d/dx; dx_bf16 (optional) = bf16 copy of the final dx, masked by dxb_drop_* (the output dropout of the
+ * sub-layer below, whose dY it is); dw/db accumulated with atomics (db only for kind 1; either may be NULL). */
 int vc_norm_bwd(int kind, const float* g, const float* x, const float* w, const float* rstd, const float* mean, float* dx,
                 void* dx_bf16, int accumulate_dx, float* dw, float* db, int M, int D, float scale, int rows_per_batch,
-                int g_batch_stride, int g_row_offset, void* stream);
+                int g_batch_stride, int g_row_offset, uint32_t g_drop_seed, uint32_t g_drop_p16, uint32_t dxb_drop_seed,
+                uint32_t dxb_drop_p16, void* stream);
 
 /* ---- Embedding (vid2seq.py:71, modeling_t5.py:972) and its scatter-add backward into the tied table. */
-int vc_embed_fwd(const int64_t* ids, const float* table, float* out, int n, int d, int V, void* stream);
-int vc_embed_bwd(const int64_t* ids, const float* dout, float* dtable, int n, int d, int V, void* stream);
+int vc_embed_fwd(const int64_t* ids, const float* table, float* out, int n, int d, int V, uint32_t drop_seed,
+                 uint32_t drop_p16, void* stream);   /* + T5Stack input dropout (modeling_t5.py:1019), index i*d+c */
+int vc_embed_bwd(const int64_t* ids, const float* dout, float* dtable, int n, int d, int V, uint32_t drop_seed,
+                 uint32_t drop_p16, void* stream);
 /* ---- labels = ids with pad->-100 (vid2seq.py:86-88); dec_in = shift_right(labels) (modeling_t5.py:845-868);
  * n_valid[0] = number of non-pad targets. */
 int vc_prepare_targets(const int64_t* out_ids, int64_t* dec_in, int64_t* labels, float* n_valid, int B, int S,
@@ -112,8 +120,10 @@ int vc_prepare_targets(const int64_t* out_ids, int64_t* dec_in, int64_t* labels,
 int vc_bias_expand(const float* table, const int32_t* lut, float* out, int H, int R, void* stream);
 int vc_bias_fold(const float* drel, const int32_t* lut, float* dtable, int H, int R, void* stream);
 /* ---- x + pos_embed with nearest interpolation when T != P (vit.py:119-127), and d(pos_embed). */
-int vc_add_pos(const float* x, const float* pos, float* out, int B, int T, int C, int P, void* stream);
-int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C, int P, void* stream);
+int vc_add_pos(const float* x, const float* pos, float* out, int B, int T, int C, int P, uint32_t drop_seed,
+               uint32_t drop_p16, void* stream);     /* + pos_drop (vit.py:126) */
+int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C, int P, uint32_t drop_seed, uint32_t drop_p16,
+                   void* stream);
 /* ---- F.cross_entropy(ignore_index=-100, label_smoothing) (modeling_t5.py:1721): loss_out[0] = mean over valid rows;
  * dlogits (bf16, optional) = d loss / d logits for upstream gradient 1. */
 int vc_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, const float* n_valid, float smoothing,

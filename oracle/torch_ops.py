@@ -19,6 +19,33 @@ ACT_NONE, ACT_RELU, ACT_GELU, ACT_RELU_BWD, ACT_GELU_BWD = 0, 1, 2, 3, 4
 _MASKED = -3.0e38
 
 
+NO_DROP = (0, 0)
+_M32 = 0xFFFFFFFF
+
+
+def drop_mask(spec, idx: torch.Tensor) -> torch.Tensor:
+    """Float multiplier (0 or 65536/(65536-p16)) for int64 element indices — the same counter-based hash as
+    vidchapters_b200/csrc/ptx.cuh::drop_keep (murmur3 finaliser of the pair index, 16 bits per element)."""
+    seed, p16 = spec
+    if p16 == 0:
+        return torch.ones(idx.shape, dtype=torch.float32, device=idx.device)
+    x = (((idx >> 1) & _M32) * 0x9E3779B1 + ((idx >> 33) & _M32) * 0x85EBCA77 + seed) & _M32
+    x = x ^ (x >> 16)
+    x = (x * 0x85EBCA6B) & _M32
+    x = x ^ (x >> 13)
+    x = (x * 0xC2B2AE35) & _M32
+    x = x ^ (x >> 16)
+    r = torch.where((idx & 1) == 1, x >> 16, x & 0xFFFF)
+    return (r >= p16).float() * (65536.0 / (65536.0 - p16))
+
+
+def _idx(shape, device):
+    n = 1
+    for s_ in shape:
+        n *= s_
+    return torch.arange(n, dtype=torch.int64, device=device).view(shape)
+
+
 def _gelu_grad(x):
     cdf = 0.5 * (1.0 + torch.erf(x * 0.7071067811865476))
     pdf = 0.3989422804014327 * torch.exp(-0.5 * x * x)
@@ -33,7 +60,7 @@ class TorchOps:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, pre_out=None,
-             aux=None, alpha=1.0, alpha_dev=None, splits=1, atomic=False, tile_n=0):
+             aux=None, alpha=1.0, alpha_dev=None, splits=1, atomic=False, tile_n=0, drop=NO_DROP):
         a = A.float().t() if a_mn else A.float()
         b = B.float() if b_mn else B.float().t()
         acc = (a @ b) * alpha
@@ -51,6 +78,8 @@ class TorchOps:
             acc = acc * (aux.float() > 0)
         elif act == ACT_GELU_BWD:
             acc = acc * _gelu_grad(aux.float())
+        if drop[1]:
+            acc = acc * drop_mask(drop, _idx(acc.shape, acc.device))
         if residual is not None:
             acc = acc + residual
         if atomic:
@@ -78,9 +107,11 @@ class TorchOps:
         return torch.where(masked, torch.full_like(s, _MASKED), s)
 
     def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
-                 causal=False, scale=1.0):
+                 causal=False, scale=1.0, drop=NO_DROP):
         s = self._scores(q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale)
         p = torch.softmax(s, dim=-1)
+        if drop[1]:
+            p = p * drop_mask(drop, _idx(p.shape, p.device))
         vh = self._heads(v, v_col, B, Lk, H)
         o = p.to(torch.bfloat16).float() @ vh
         out[:, :H * 64].copy_(o.permute(0, 2, 1, 3).reshape(B * Lq, H * 64).to(out.dtype))
@@ -89,17 +120,20 @@ class TorchOps:
 
     def attn_bwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, dout, do_col=0, delta, dq_acc, dk, dk_col, dv, dv_col, dbias_rel=None,
-                 bucket_lut=None):
+                 bucket_lut=None, drop=NO_DROP):
         s = self._scores(q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale)
         p = torch.softmax(s, dim=-1)
+        dm = drop_mask(drop, _idx(p.shape, p.device)) if drop[1] else None
         qh, kh, vh = (self._heads(q, q_col, B, Lq, H), self._heads(k, k_col, B, Lk, H), self._heads(v, v_col, B, Lk, H))
         do = self._heads(dout, do_col, B, Lq, H)
         oh = self._heads(out, 0, B, Lq, H)
         dlt = (do * oh).sum(-1, keepdim=True)
         delta.copy_(dlt.squeeze(-1))
         dp = do @ vh.transpose(-1, -2)
+        if dm is not None:
+            dp = dp * dm
         ds = p * (dp - dlt)
-        pb = p.to(torch.bfloat16).float()
+        pb = (p if dm is None else p * dm).to(torch.bfloat16).float()
         dsb = (ds * scale).to(torch.bfloat16).float()
         dvh = pb.transpose(-1, -2) @ do
         dkh = dsb.transpose(-1, -2) @ qh
@@ -122,7 +156,7 @@ class TorchOps:
         return r
 
     def norm_fwd(self, kind, x, w, bias, *, out_bf16=None, out_f32=None, rstd=None, mean=None, eps, out_scale=1.0,
-                 rows_per_batch=0, out_batch_stride=0, out_row_offset=0):
+                 rows_per_batch=0, out_batch_stride=0, out_row_offset=0, drop=NO_DROP):
         M, D = x.shape
         if kind == 1:
             mu = x.mean(-1, keepdim=True)
@@ -135,6 +169,8 @@ class TorchOps:
         if kind == 1:
             y = y + bias
         y = y * out_scale
+        if drop[1]:
+            y = y * drop_mask(drop, _idx(y.shape, y.device))
         rows = self._rows(M, rows_per_batch, out_batch_stride, out_row_offset, x.device)
         if out_bf16 is not None:
             out_bf16.view(-1, D)[rows] = y.to(out_bf16.dtype)
@@ -146,10 +182,12 @@ class TorchOps:
             mean.copy_(mu.squeeze(-1))
 
     def norm_bwd(self, kind, g, x, w, rstd, mean, *, dx, dx_bf16=None, accumulate_dx, dw, db=None, scale=1.0,
-                 rows_per_batch=0, g_batch_stride=0, g_row_offset=0):
+                 rows_per_batch=0, g_batch_stride=0, g_row_offset=0, g_drop=NO_DROP, dxb_drop=NO_DROP):
         M, D = x.shape
         rows = self._rows(M, rows_per_batch, g_batch_stride, g_row_offset, x.device)
         gg = g.view(-1, D)[rows] * scale
+        if g_drop[1]:
+            gg = gg * drop_mask(g_drop, _idx(gg.shape, gg.device))
         mu = mean[:, None] if kind == 1 else 0.0
         xh = (x - mu) * rstd[:, None]
         dh = gg * w
@@ -161,18 +199,23 @@ class TorchOps:
         else:
             dx.copy_(d)
         if dx_bf16 is not None:
-            dx_bf16.copy_(dx.to(dx_bf16.dtype))
+            dd = dx * drop_mask(dxb_drop, _idx(dx.shape, dx.device)) if dxb_drop[1] else dx
+            dx_bf16.copy_(dd.to(dx_bf16.dtype))
         if dw is not None:
             dw.add_((gg * xh).sum(0))
         if db is not None and kind == 1:
             db.add_(gg.sum(0))
 
     # ------------------------------------------------------------------ small ops
-    def embed_fwd(self, ids, table, out):
-        out.copy_(table[ids.reshape(-1)].view_as(out))
+    def embed_fwd(self, ids, table, out, drop=NO_DROP):
+        e = table[ids.reshape(-1)].view_as(out)
+        out.copy_(e * drop_mask(drop, _idx(e.shape, e.device)) if drop[1] else e)
 
-    def embed_bwd(self, ids, dout, dtable):
-        dtable.index_add_(0, ids.reshape(-1), dout.reshape(-1, dtable.shape[1]))
+    def embed_bwd(self, ids, dout, dtable, drop=NO_DROP):
+        g = dout.reshape(-1, dtable.shape[1])
+        if drop[1]:
+            g = g * drop_mask(drop, _idx(g.shape, g.device))
+        dtable.index_add_(0, ids.reshape(-1), g)
 
     def prepare_targets(self, out_ids, dec_in, labels, n_valid, pad_id=0):
         lab = out_ids.masked_fill(out_ids == pad_id, -100)
@@ -194,12 +237,16 @@ class TorchOps:
             return torch.arange(T, device=device)
         return torch.floor(torch.arange(T, device=device, dtype=torch.float32) * (float(P) / float(T))).long()
 
-    def add_pos(self, x, pos, out, P):
+    def add_pos(self, x, pos, out, P, drop=NO_DROP):
         B, T, C = x.shape
-        out.copy_(x + pos.view(P, C)[self._pos_idx(T, P, x.device)][None])
+        y = x + pos.view(P, C)[self._pos_idx(T, P, x.device)][None]
+        out.copy_(y * drop_mask(drop, _idx(y.shape, y.device)) if drop[1] else y)
 
-    def add_pos_bwd(self, dx, dpos, B, T, C, P):
-        dpos.view(P, C).index_add_(0, self._pos_idx(T, P, dx.device), dx.view(B, T, C).sum(0))
+    def add_pos_bwd(self, dx, dpos, B, T, C, P, drop=NO_DROP):
+        g = dx.view(B, T, C)
+        if drop[1]:
+            g = g * drop_mask(drop, _idx(g.shape, g.device))
+        dpos.view(P, C).index_add_(0, self._pos_idx(T, P, dx.device), g.sum(0))
 
     def cross_entropy(self, logits, labels, n_valid, smoothing, loss_out, dlogits):
         n, V = logits.shape

@@ -53,21 +53,49 @@ class _EmuMatmul(torch.autograd.Function):
         return gr @ br.transpose(-1, -2), ar.transpose(-1, -2) @ gr
 
 
+class DropPlan:
+    """Replays the engine's counter-based dropout (vidchapters_b200/engine.py::_site, csrc/ptx.cuh::drop_keep): the
+    k-th dropout site with a positive rate gets seed base + k*0x632BE5AB; element index = flat index of the tensor."""
+
+    def __init__(self, rates: dict, base: int):
+        self.rates, self.base, self.k = rates, base, 0
+
+    def mask(self, which: str, x: torch.Tensor):
+        from oracle.torch_ops import _idx, drop_mask
+        p = self.rates.get(which, 0.0)
+        if p <= 0:
+            return None
+        self.k += 1
+        p16 = int(round(p * 65536.0))
+        return drop_mask(((self.base + self.k * 0x632BE5AB) & 0xFFFFFFFF, p16), _idx(x.shape, x.device))
+
+
 class Arith:
-    def __init__(self, emulate_bf16: bool, flash_rounding: bool = False):
+    def __init__(self, emulate_bf16: bool, flash_rounding: bool = False, drop_plan: "DropPlan" = None):
         self.emu = emulate_bf16
+        self.dp = drop_plan
         # flash_rounding: the probabilities that enter P.V are the UN-normalised exp(s - rowmax) rounded to bf16, the
         # division by the row sum happens after the product — the rounding points of any flash-attention kernel with
         # bf16 operands.  (Normalised-then-rounded P, the default, is what eager bf16 attention does; the two differ by
         # ~3.5e-3 rel-L2 on the logits purely through the rounding realisation, see tests/test_e2e_gpu.py.)
         self.flash = flash_rounding and emulate_bf16
 
-    def softmax_pv(self, scores, v):
+    def dropout(self, which, x):
+        """nn.Dropout / F.dropout site (training mode) with the replayed mask; identity without a plan."""
+        if self.dp is None:
+            return x
+        m = self.dp.mask(which, x)
+        return x if m is None else x * m
+
+    def softmax_pv(self, scores, v, which=None):
+        """softmax -> dropout on the probabilities (modeling_t5.py:569-574, vit.py:48-49) -> . V"""
         if not self.flash:
-            return self.matmul(F.softmax(scores.float(), dim=-1), v)
-        m = scores.max(-1, keepdim=True).values
-        e = torch.exp(scores - m)
-        return self.matmul(e, v) / e.sum(-1, keepdim=True)
+            return self.matmul(self.dropout(which, F.softmax(scores.float(), dim=-1)), v)
+        # kernel rounding points: P~ = 2^(s*log2e - ceil(rowmax*log2e)) is rounded to bf16 (the integer exponent offset
+        # makes the rounding independent of the kernel's tiling), dropped, multiplied by V, then divided by sum(P~).
+        s2 = scores * 1.4426950408889634
+        e = torch.exp2(s2 - torch.ceil(s2.max(-1, keepdim=True).values))
+        return self.matmul(self.dropout(which, e), v) / e.sum(-1, keepdim=True)
 
     def matmul(self, a, b):
         if self.emu:
@@ -89,7 +117,7 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, ar: Ari
     pos = sd[pfx + "pos_embed"]
     if N != pos.shape[1]:  # vit.py:119-123 nearest interpolation of the time embedding
         pos = F.interpolate(pos.transpose(1, 2), size=N, mode="nearest").transpose(1, 2)
-    x = x + pos
+    x = ar.dropout("vis", x + pos)  # pos_drop, vit.py:126
     for i in range(cfg["depth"]):
         p = f"{pfx}blocks.{i}."
         h = F.layer_norm(x, (C,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
@@ -97,12 +125,12 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, ar: Ari
         qkv = qkv.reshape(B, N, 3, H, C // H).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
         attn = ar.matmul(q, k.transpose(-2, -1)) * ((C // H) ** -0.5)  # vit.py:47
-        o = ar.softmax_pv(attn, v).transpose(1, 2).reshape(B, N, C)        # vit.py:48-51
-        x = x + ar.linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])
+        o = ar.softmax_pv(attn, v, "vis").transpose(1, 2).reshape(B, N, C)        # vit.py:48-51
+        x = x + ar.dropout("vis", ar.linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]))  # proj_drop
         h = F.layer_norm(x, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
         h = ar.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
-        h = F.gelu(h)  # nn.GELU() exact erf, vit.py:9,19
-        x = x + ar.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+        h = ar.dropout("vis", F.gelu(h))  # nn.GELU() exact erf + drop, vit.py:9,19-20
+        x = x + ar.dropout("vis", ar.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"]))  # vit.py:21-22
     return F.layer_norm(x, (C,), sd[pfx + "norm.weight"], sd[pfx + "norm.bias"], 1e-5)
 
 
@@ -141,7 +169,7 @@ def compute_bias(table: torch.Tensor, qlen: int, klen: int, bidirectional: bool)
     return table[bucket].permute(2, 0, 1).unsqueeze(0)
 
 
-def t5_attention(sd, p, H, dkv, x, kv, position_bias, ar: Arith):
+def t5_attention(sd, p, H, dkv, x, kv, position_bias, ar: Arith, which=None):
     """modeling_t5.py:462-588 (no cache, no head mask, no dropout): UNSCALED q.k^T + bias, fp32 softmax."""
     B, Lq, _ = x.shape
     Lk = kv.shape[1]
@@ -150,16 +178,16 @@ def t5_attention(sd, p, H, dkv, x, kv, position_bias, ar: Arith):
     v = ar.linear(kv, sd[p + "v.weight"]).view(B, Lk, H, dkv).transpose(1, 2)
     scores = ar.matmul(q, k.transpose(3, 2))
     scores = scores + position_bias
-    o = ar.softmax_pv(scores, v).transpose(1, 2).contiguous().view(B, Lq, H * dkv)  # fp32 softmax, :569-580
+    o = ar.softmax_pv(scores, v, which).transpose(1, 2).contiguous().view(B, Lq, H * dkv)  # fp32 softmax, :569-580
     return ar.linear(o, sd[p + "o.weight"])
 
 
-def t5_ff(sd, p, x, ar: Arith):
+def t5_ff(sd, p, x, ar: Arith, which=None):
     """modeling_t5.py:339-354 + :296-311 (T5LayerFF / T5DenseActDense, ReLU)."""
     h = t5_layer_norm(x, sd[p + "layer_norm.weight"])
     h = ar.linear(h, sd[p + "DenseReluDense.wi.weight"])
-    h = torch.relu(h)
-    return x + ar.linear(h, sd[p + "DenseReluDense.wo.weight"])
+    h = ar.dropout(which, torch.relu(h))  # :306-307
+    return x + ar.dropout(which, ar.linear(h, sd[p + "DenseReluDense.wo.weight"]))  # :353
 
 
 def t5_encoder(sd, cfg, embeds, mask, ar: Arith, pfx="t5_model.encoder."):
@@ -169,13 +197,13 @@ def t5_encoder(sd, cfg, embeds, mask, ar: Arith, pfx="t5_model.encoder."):
     ext = (1.0 - mask[:, None, None, :].to(torch.float32)) * NEG_MIN  # get_extended_attention_mask (HF)
     table = sd[pfx + "block.0.layer.0.SelfAttention.relative_attention_bias.weight"]
     bias = compute_bias(table, L, L, True) + ext  # modeling_t5.py:543-559 (layer 0 builds, others reuse :1092-1097)
-    x = embeds
+    x = ar.dropout("enc", embeds)  # :1019
     for i in range(cfg["num_layers"]):
         p = f"{pfx}block.{i}."
         h = t5_layer_norm(x, sd[p + "layer.0.layer_norm.weight"])
-        x = x + t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, bias, ar)
-        x = t5_ff(sd, p + "layer.1.", x, ar)
-    return t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"])
+        x = x + ar.dropout("enc", t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, bias, ar, "enc"))  # :618
+        x = t5_ff(sd, p + "layer.1.", x, ar, "enc")
+    return ar.dropout("enc", t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"]))  # :1113-1114
 
 
 def shift_right(labels):
@@ -190,7 +218,7 @@ def t5_decoder(sd, cfg, dec_ids, dec_mask, enc_h, enc_mask, ar: Arith, pfx="t5_m
     """modeling_t5.py:930-1138 (decoder stack): causal self-attn (+rel bias), cross-attn (zero bias), FF."""
     H, dkv = cfg["num_heads"], cfg["d_kv"]
     B, S = dec_ids.shape
-    x = sd["t5_model.shared.weight"][dec_ids]  # modeling_t5.py:972
+    x = ar.dropout("dec", sd["t5_model.shared.weight"][dec_ids])  # modeling_t5.py:972,1019
     causal = torch.tril(torch.ones(S, S, device=x.device))[None, :, :] * dec_mask[:, None, :].to(torch.float32)
     ext = (1.0 - causal[:, None, :, :]) * NEG_MIN  # create_extended_attention_mask_for_decoder (HF)
     table = sd[pfx + "block.0.layer.0.SelfAttention.relative_attention_bias.weight"]
@@ -199,20 +227,20 @@ def t5_decoder(sd, cfg, dec_ids, dec_mask, enc_h, enc_mask, ar: Arith, pfx="t5_m
     for i in range(cfg["num_layers"]):
         p = f"{pfx}block.{i}."
         h = t5_layer_norm(x, sd[p + "layer.0.layer_norm.weight"])
-        x = x + t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, self_bias, ar)
+        x = x + ar.dropout("dec", t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, self_bias, ar, "dec"))
         h = t5_layer_norm(x, sd[p + "layer.1.layer_norm.weight"])
-        x = x + t5_attention(sd, p + "layer.1.EncDecAttention.", H, dkv, h, enc_h, cross_bias, ar)
-        x = t5_ff(sd, p + "layer.2.", x, ar)
-    return t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"])
+        x = x + ar.dropout("dec", t5_attention(sd, p + "layer.1.EncDecAttention.", H, dkv, h, enc_h, cross_bias, ar, "dec"))
+        x = t5_ff(sd, p + "layer.2.", x, ar, "dec")
+    return ar.dropout("dec", t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"]))
 
 
 def vid2seq_forward(sd, cfg, video, input_ids, input_mask, output_ids, output_mask, *, emulate_bf16=False,
-                    label_smoothing=0.1, video_is_cached=False, flash_rounding=False):
+                    label_smoothing=0.1, video_is_cached=False, flash_rounding=False, drop_plan=None):
     """model/vid2seq.py:58-98 (+ modeling_t5.py:1587-1738).  Dropout-free (p=0 / eval) restatement.
 
     Returns dict(loss, logits (B,S,V), video (B,T,d), memory (B,T+L,d)).
     """
-    ar = Arith(emulate_bf16, flash_rounding)
+    ar = Arith(emulate_bf16, flash_rounding, drop_plan)
     d = cfg["d_model"]
     if video_is_cached:
         vid = video

@@ -137,3 +137,42 @@ def test_two_pass_and_stock_optimizer():
     opt.step()
     l3, _ = m(video, {"input_ids": i1, "attention_mask": i1 != 0}, {"input_ids": o1, "attention_mask": o1 != 0})
     assert l3["loss"].item() < l1["loss"].item()
+
+
+def test_dropout_training_step_cuda_vs_torch_ops():
+    """Reference default dropout 0.1 in training mode: the CUDA engine and the torch op table regenerate the same
+    counter-based masks, so loss and gradients must agree to bf16 noise."""
+    from oracle.torch_ops import TorchOps
+    from vidchapters_b200.engine import Vid2SeqEngine
+    from vidchapters_b200.ops import CudaOps
+    fx = torch.load(os.path.join(GOLD, "tiny.pt"), weights_only=False)
+    cfg = fx["cfg"]
+    m = build(cfg)
+    eng_c = m.engine
+    eng_t = Vid2SeqEngine(cfg, TorchOps(), "cuda")
+    eng_t.flat_p.copy_(eng_c.flat_p)
+    eng_c.sync_bf16(); eng_t.sync_bf16()
+    video, inp, out = fx["video"].cuda(), fx["input_ids"].cuda(), fx["output_ids"].cuda()
+    res = []
+    for eng in (eng_c, eng_t):
+        eng.drop_rates = dict(vis=0.1, enc=0.1, dec=0.1)
+        eng.drop_seed, eng._drop_calls = 5, 0
+        loss, ctx = eng.forward(video, inp, inp != 0, out, out != 0, training=True)
+        eng.zero_grad()
+        eng.backward(ctx)
+        res.append((loss.item(), eng.flat_g.clone()))
+    assert abs(res[0][0] - res[1][0]) < 2e-3 * abs(res[1][0]), (res[0][0], res[1][0])
+    worst = 0.0
+    for n in eng_c.layout:
+        o, shp, k = eng_c.layout[n]
+        e = rel(res[0][1][o:o + k], res[1][1][o:o + k])
+        worst = max(worst, e)
+        assert e < 8e-2, (n, e)
+    print(f"[dropout] loss cuda {res[0][0]:.5f} torch-ops {res[1][0]:.5f}; worst gradient rel-L2 {worst:.3e}")
+    # module surface: dropout active in train(), off in eval()
+    m.vis_drop = m.enc_drop = m.dec_drop = 0.1
+    it = {"input_ids": inp, "attention_mask": inp != 0}
+    ot = {"input_ids": out, "attention_mask": out != 0}
+    m.train(); l_tr = m(video, it, ot)[0]["loss"].item()
+    m.eval(); l_ev = m(video, it, ot)[0]["loss"].item()
+    assert abs(l_tr - l_ev) > 1e-3 and abs(l_ev - fx["loss"].item()) < 2e-3 * abs(l_ev)

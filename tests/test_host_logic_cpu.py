@@ -167,3 +167,39 @@ def test_two_pass_cached_video_gradients():
     for n in ("visual_encoder.blocks.0.attn.qkv.weight", "visual_encoder.pos_embed", "t5_model.shared.weight",
               "t5_model.decoder.block.1.layer.1.EncDecAttention.k.weight"):
         assert rel(g_two[n], sd[n].grad) < 2e-2, n
+
+
+@pytest.mark.parametrize("cfg", [dict(TINY, num_features=10), dict(TINY_PROJ)], ids=["tiny", "tiny-proj"])
+def test_dropout_forward_backward_match_replayed_masks(cfg):
+    """Training-mode dropout (reference defaults 0.1): the engine's counter-based masks replayed inside the oracle
+    (oracle.DropPlan) must give the same loss and — through torch autograd — the same gradients."""
+    sd = init_state_dict(cfg, 0)
+    eng = Vid2SeqEngine(cfg, TorchOps(), "cpu")
+    for n, t in sd.items():
+        eng.p(n).copy_(t)
+    eng.sync_bf16()
+    eng.drop_rates = dict(vis=0.1, enc=0.1, dec=0.1)
+    eng.drop_seed = 77
+    video, inp, out = batch(cfg)
+    loss, ctx = eng.forward(video, inp, inp != 0, out, out != 0, training=True)
+    base, n_sites = eng._drop_base, eng._drop_site
+    eng.zero_grad()
+    eng.backward(ctx)
+    loss_eval, _ = eng.forward(video, inp, inp != 0, out, out != 0, training=False)
+    assert abs(loss.item() - loss_eval.item()) > 1e-3          # dropout really changes the forward
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    plan = O.DropPlan(dict(vis=0.1, enc=0.1, dec=0.1), base)
+    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, drop_plan=plan)
+    o["loss"].backward()
+    assert plan.k == n_sites                              # same number of dropout sites visited
+    assert abs(loss.item() - o["loss"].item()) < 2e-4 * abs(o["loss"].item())
+    # (fp32-noise-level differences in the ViT output flip individual bf16 roundings / ReLUs downstream: ~4e-2 on the
+    #  most affected decoder FF gradients; a wrong mask anywhere would show up as O(1))
+    for n in sd:
+        assert rel(eng.g(n), sdg[n].grad) < 8e-2, n
+    # a new forward call draws new masks; the same seed + call index reproduces them
+    loss2, _ = eng.forward(video, inp, inp != 0, out, out != 0, training=True)
+    assert abs(loss2.item() - loss.item()) > 1e-4
+    eng._drop_calls -= 1
+    loss3, _ = eng.forward(video, inp, inp != 0, out, out != 0, training=True)
+    assert loss3.item() == loss2.item()

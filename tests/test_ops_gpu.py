@@ -269,3 +269,83 @@ def test_optimizer_tail(cuda_ops, torch_ops):
         res.append((p, m, v, pb, ns))
     for a, r in zip(*res):
         assert rel(a, r) < 2e-5 if a.dtype == torch.float32 else rel(a, r) < BF16_TOL
+
+
+# ----------------------------------------------------------------------------- dropout (counter-based masks)
+DROP = (0xC0FFEE, 6554)   # p ~ 0.1
+
+
+def test_dropout_gemm_epilogue(cuda_ops, torch_ops):
+    M, N, K = 300, 2048, 768
+    g = gen(21)
+    A = (torch.randn(M, K, generator=g) * 0.3).to(DEV).bfloat16()
+    B = (torch.randn(N, K, generator=g) * 0.3).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    resid = torch.randn(M, N, generator=g).to(DEV)
+    aux = torch.randn(M, N, generator=g).to(DEV).bfloat16()
+    for act in (0, 1, 2, 4):
+        out = torch.empty(M, N, device=DEV)
+        ref = torch.empty(M, N, device=DEV)
+        kw = dict(bias=bias, residual=resid, act=act, aux=aux if act == 4 else None, drop=DROP)
+        cuda_ops.gemm(A, B, out, **kw)
+        torch_ops.gemm(A, B, ref, **kw)
+        assert rel(out, ref) < 1e-4, act
+        zeros = ((out - resid).abs() < 1e-12).float().mean().item()
+        assert 0.05 < zeros < 0.6   # ~10% dropped (more with relu)
+
+
+@pytest.mark.parametrize("case", [ATTN_CASES[1], ATTN_CASES[2], ATTN_CASES[4]])
+def test_dropout_attention(cuda_ops, torch_ops, case):
+    B, H, Lq, Lk, causal, wb, wm, scale, sa = case
+    q, k, v, cols, bias, kmask = _attn_case(B, H, Lq, Lk, causal, wb, wm, scale, sa, seed=8)
+    inner = H * 64
+    kw = dict(B=B, H=H, Lq=Lq, Lk=Lk, bias_rel=bias, kmask=kmask, causal=causal, scale=scale, drop=DROP, **cols)
+    outs = []
+    dout = (torch.randn(B * Lq, inner, generator=gen(12)) * 0.5).to(DEV).bfloat16()
+    for ops in (cuda_ops, torch_ops):
+        out = torch.zeros(B * Lq, inner, device=DEV, dtype=torch.bfloat16)
+        lse = torch.zeros(B, H, Lq, device=DEV)
+        ops.attn_fwd(q, k, v, out=out, lse2=lse, **kw)
+        outs.append((out, lse))
+    assert rel(outs[0][0], outs[1][0]) < 8e-3
+    out, lse = outs[0]
+    res = []
+    for ops in (cuda_ops, torch_ops):
+        delta = torch.zeros(B, H, Lq, device=DEV)
+        dq = torch.zeros(B * Lq, inner, device=DEV)
+        dk = torch.zeros(B * Lk, 2 * inner, device=DEV, dtype=torch.bfloat16)
+        ops.attn_bwd(q, k, v, out=out, lse2=lse, dout=dout, do_col=0, delta=delta, dq_acc=dq, dk=dk, dk_col=0, dv=dk,
+                     dv_col=inner, dbias_rel=None, bucket_lut=None, **kw)
+        res.append((dq, dk.clone()))
+    assert rel(res[0][0], res[1][0]) < 1.5e-2 and rel(res[0][1], res[1][1]) < 1.5e-2
+
+
+def test_dropout_norm_embed_pos(cuda_ops, torch_ops):
+    g = gen(31)
+    M, D = 200, 768
+    x = torch.randn(M, D, generator=g).to(DEV)
+    w = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV)
+    gy = torch.randn(M, D, generator=g).to(DEV)
+    table = torch.randn(500, D, generator=g).to(DEV)
+    ids = torch.randint(0, 500, (M,), generator=g).to(DEV)
+    vid = torch.randn(2, 100, D, generator=g).to(DEV)
+    pos = torch.randn(1, 100, D, generator=g).to(DEV)
+    res = []
+    for ops in (cuda_ops, torch_ops):
+        ob = torch.zeros(M, D, device=DEV, dtype=torch.bfloat16)
+        rstd = torch.zeros(M, device=DEV)
+        ops.norm_fwd(0, x, w, None, out_bf16=ob, rstd=rstd, eps=1e-6, drop=DROP)
+        dx = torch.zeros(M, D, device=DEV)
+        dxb = torch.zeros(M, D, device=DEV, dtype=torch.bfloat16)
+        dw = torch.zeros(D, device=DEV)
+        ops.norm_bwd(0, gy, x, w, rstd, None, dx=dx, dx_bf16=dxb, accumulate_dx=False, dw=dw, g_drop=DROP,
+                     dxb_drop=(77, 13107))
+        e = torch.zeros(M, D, device=DEV); ops.embed_fwd(ids, table, e, drop=DROP)
+        dt = torch.zeros(500, D, device=DEV); ops.embed_bwd(ids, gy, dt, drop=DROP)
+        ap = torch.zeros_like(vid); ops.add_pos(vid, pos, ap, 100, drop=DROP)
+        dp = torch.zeros(1, 100, D, device=DEV); ops.add_pos_bwd(ap.view(200, D), dp, 2, 100, D, 100, drop=DROP)
+        res.append((ob, dx, dxb, dw, e, dt, ap, dp))
+    for i, (a, r) in enumerate(zip(*res)):
+        assert rel(a, r) < (BF16_TOL if a.dtype == torch.bfloat16 else 1e-4), i
+    assert 0.08 < (res[0][4] == 0).float().mean().item() < 0.12
+    assert 0.17 < (res[0][2] == 0).float().mean().item() < 0.23   # dxb_drop p = 0.2

@@ -1,0 +1,43 @@
+"""Launches the hot kernels at config-2 shapes a few times (driver for `ncu --set full -k regex:<name>`)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vidchapters_b200.ops import CudaOps
+from vidchapters_b200.engine import relative_position_bucket
+
+ops = CudaOps()
+dev = "cuda"
+g = torch.Generator().manual_seed(0)
+B, H, L = 16, 12, 1000
+inner = H * 64
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "attn"):
+    qkv = (torch.randn(B * L, 3 * inner, generator=g) * 0.5).to(dev).bfloat16()
+    bias = torch.randn(H, 2 * L - 1, generator=g).to(dev)
+    lens = torch.randint(L // 2, L + 1, (B,), generator=g)
+    kmask = (torch.arange(L)[None] < lens[:, None]).to(torch.uint8).to(dev)
+    out = torch.zeros(B * L, inner, device=dev, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, L, device=dev)
+    kw = dict(q_col=0, k_col=inner, v_col=2 * inner, B=B, H=H, Lq=L, Lk=L, bias_rel=bias, kmask=kmask, causal=False, scale=1.0)
+    dout = (torch.randn(B * L, inner, generator=g) * 0.5).to(dev).bfloat16()
+    delta = torch.zeros(B, H, L, device=dev); dq = torch.zeros(B * L, inner, device=dev)
+    dqkv = torch.zeros(B * L, 3 * inner, device=dev, dtype=torch.bfloat16)
+    db = torch.zeros(H, 2 * L - 1, device=dev)
+    lut = relative_position_bucket(torch.arange(2 * L - 1) - (L - 1), True).to(torch.int32).to(dev)
+    for _ in range(3):
+        ops.attn_fwd(qkv, qkv, qkv, out=out, lse2=lse, **kw)
+        ops.attn_bwd(qkv, qkv, qkv, out=out, lse2=lse, dout=dout, do_col=0, delta=delta, dq_acc=dq, dk=dqkv, dk_col=inner,
+                     dv=dqkv, dv_col=2 * inner, dbias_rel=db, bucket_lut=lut, **kw)
+if which in ("all", "gemm"):
+    M, N, K = 16000, 3072, 768
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.5).to(dev).bfloat16()
+    C = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    dW = torch.zeros(N, K, device=dev)
+    dA = torch.zeros(M, K, device=dev)
+    for _ in range(3):
+        ops.gemm(A, W, C, act=1)                                    # forward wi + relu
+        ops.gemm(C, W, dA, b_mn=True)                               # dgrad
+        ops.gemm(C, A, dW, a_mn=True, b_mn=True, atomic=True, splits=5)  # wgrad
+torch.cuda.synchronize()
+print("done")

@@ -40,11 +40,13 @@ struct AttnBwdParams {
   __nv_bfloat16* dk; long long ld_dk; int dk_col;  // bf16 [B*Lk][ld], head h at cols dk_col + 64h
   __nv_bfloat16* dv; long long ld_dv; int dv_col;
   float* dbias_rel;       // fp32 [H][Lq+Lk-1] (atomicAdd) or null
+  uint32_t drop_seed, drop_p16;
 };
 
 constexpr int kBwdSmemTiles = 16384 * 2 /*K,V*/ + 2 * 16384 /*Q ring*/ + 2 * 16384 /*dO ring*/ + 32768 /*P*/ + 32768 /*dS*/;
-constexpr int kBwdRelMax = 2304;  // floats of d(bias) scratch: Lq + 128 <= 2304
-constexpr int kAttnBwdSmem = kBwdSmemTiles + 2 * kBwdRelMax * 4 + 128 + 256;  // + d(bias) scratch + bias window + key mask
+constexpr int kBwdRelMax = 1536;  // floats per relative-position window: ceil(Lq/128)*128 + 128 <= 1536 (Lq <= 1408)
+// + 4 per-warp d(bias) windows + bias window + key ceilings + 4 per-warp 32x33 transposition scratches + barriers
+constexpr int kAttnBwdSmem = kBwdSmemTiles + 5 * kBwdRelMax * 4 + 512 + 4 * 32 * 33 * 4 + 256;
 
 __global__ void __launch_bounds__(192, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -56,10 +58,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sDO = sQ + 2 * 16384;   // [2]
   uint8_t* sP = sDO + 2 * 16384;   // 32 KB
   uint8_t* sDS = sP + 32768;       // 32 KB
-  float* s_rel = reinterpret_cast<float*>(sDS + 32768);
-  float* s_bias = s_rel + kBwdRelMax;   // bias(k - q) * log2e for this key tile: slot (k - k0) + (Lq - 1 - q)
-  uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_bias + kBwdRelMax);  // key mask of this tile (128 bytes)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 128);
+  float* s_rel = reinterpret_cast<float*>(sDS + 32768);   // [4 warps][kBwdRelMax]: private d(bias) windows, no atomics
+  float* s_bias = s_rel + 4 * kBwdRelMax;   // bias(k - q) * log2e for this key tile: slot (k - k0) + (Lq - 1 - q)
+  float* s_pen = s_bias + kBwdRelMax;   // per-key ceiling of this tile: +inf attend | kBMasked | -inf out of range
+  float* s_tr = s_pen + 128;            // [4 warps][32][33] skewed scratch for the diagonal sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tr + 4 * 32 * 33);
   uint64_t* kv_full = bars + 0;
   uint64_t* qd_full = bars + 1;   // [2]
   uint64_t* qd_empty = bars + 3;  // [2]
@@ -87,14 +90,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_rel = p.Lq + kBT;  // relative positions touched by this CTA: (k - q + Lq - 1) - rel_base in [0, Lq+127)
   const int rel_base = k0;       // slot = (k - k0) + (Lq - 1 - q)
   if (p.dbias_rel)
-    for (int i = threadIdx.x; i < n_rel; i += blockDim.x) s_rel[i] = 0.f;
-  if (p.bias_rel) {
-    const float* brow_g = p.bias_rel + (long long)h * (p.Lq + p.Lk - 1);
-    for (int i = threadIdx.x; i < n_rel; i += blockDim.x)
-      s_bias[i] = (rel_base + i < p.Lq + p.Lk - 1) ? __ldg(brow_g + rel_base + i) * kBLog2e : 0.f;
+    for (int i = threadIdx.x; i < 4 * kBwdRelMax; i += blockDim.x) s_rel[i] = 0.f;
+  {  // always filled + padded so the per-element loop below is branch-free (see attn_fwd.cu)
+    const float* brow_g = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) : nullptr;
+    const int n_pad = ((p.Lq + kBT - 1) / kBT) * kBT + kBT;  // covers slot (k-k0) + (Lq-1-q) for every q of every tile
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
+      s_bias[i] = (brow_g && rel_base + i < p.Lq + p.Lk - 1) ? __ldg(brow_g + rel_base + i) * kBLog2e : 0.f;
+    if (threadIdx.x < 128) {
+      const int k = k0 + (int)threadIdx.x;
+      s_pen[threadIdx.x] = (k >= p.Lk) ? -INFINITY : ((p.kmask && p.kmask[(long long)b * p.Lk + k] == 0) ? kBMasked : INFINITY);
+    }
   }
-  if (p.kmask && threadIdx.x < 128)
-    s_mask[threadIdx.x] = (k0 + (int)threadIdx.x < p.Lk) ? p.kmask[(long long)b * p.Lk + k0 + threadIdx.x] : 0;
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -157,15 +163,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint8_t* mrow = p.kmask ? s_mask : nullptr;   // indexed by k - k0
+    float* rel_w = s_rel + quarter * kBwdRelMax;   // this warp's private window
+    float* tr_w = s_tr + quarter * (32 * 33);
     for (int i = 0; i < nqt; ++i) {
       const int q0 = (qt0 + i) * kBT;
       const int q = q0 + r;
       const bool q_ok = q < p.Lq;
       const long long stat_idx = ((long long)b * p.H + h) * p.Lq + (q_ok ? q : 0);
-      const float lse2 = p.lse2[stat_idx];
+      const float lse2 = q_ok ? p.lse2[stat_idx] : INFINITY;   // rows past Lq: p = exp2(-inf) = 0
       const float delta = p.delta[stat_idx];
-      const float* brow = (p.bias_rel && q_ok) ? s_bias + (p.Lq - 1 - q) : nullptr;   // indexed by k - k0
+      // indexed by k - k0; rows past Lq (zero-filled Q/dO, p forced to 0) clamp to slot 0 to stay inside the window
+      const float* brow = s_bias + (q_ok ? (p.Lq - 1 - q) : 0);
+      const bool causal_tile = p.causal && (k0 + kBT - 1 > q0);
       // d(bias): is the whole tile inside one bucket?  then one add per row instead of one per element
       bool uniform = false;
       if (p.dbias_rel && p.bucket_lut) {
@@ -181,27 +190,67 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float sv[32], dp[32];
         tmem_ld32(tS + lane_off + c * 32, sv);
         tmem_ld32(tDP + lane_off + c * 32, dp);
+        const float4* pen4 = reinterpret_cast<const float4*>(s_pen + c * 32);
+        const float* bk = brow + c * 32;
+        const int tq = q - k0 - c * 32;  // column j is causally masked iff j > tq
         tmem_ld_wait();
+        if (causal_tile) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int k = k0 + c * 32 + j;
-          float s2 = sv[j] * p.scale_log2e;
-          if (brow && k < p.Lk) s2 += brow[c * 32 + j];
-          const bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[c * 32 + j]);
-          s2 = masked ? kBMasked : s2;
-          const float pj = (q_ok && k < p.Lk) ? fast_exp2(s2 - lse2) : 0.0f;
-          const float dsj = pj * (dp[j] - delta);
-          sv[j] = pj;
-          dp[j] = dsj;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 pe = pen4[j >> 2];
+            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float s2 = fminf(fmaf(sv[j + e], p.scale_log2e, bk[j + e]), pen[e]);
+              s2 = (j + e > tq) ? fminf(s2, kBMasked) : s2;
+              sv[j + e] = fast_exp2(s2 - lse2);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 pe = pen4[j >> 2];
+            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              sv[j + e] = fast_exp2(fminf(fmaf(sv[j + e], p.scale_log2e, bk[j + e]), pen[e]) - lse2);
+          }
+        }
+        if (p.drop_p16) {  // O = drop(P).V: dV uses the dropped P, dP flows back through the same mask
+          const float sc = drop_scale(p.drop_p16);
+          const unsigned long long base = (((unsigned long long)b * p.H + h) * p.Lq + q) * p.Lk + k0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool keep = drop_keep(p.drop_seed, p.drop_p16, base + j);
+            const float dpm = keep ? dp[j] * sc : 0.0f;
+            dp[j] = sv[j] * (dpm - delta);
+            sv[j] = keep ? sv[j] * sc : 0.0f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dp[j] = sv[j] * (dp[j] - delta);
         }
         if (p.dbias_rel) {
           if (uniform) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) ds_rowsum += dp[j];
-          } else if (q_ok) {
-            float* slot = s_rel + (c * 32) + (p.Lq - 1 - q);
+          } else {
+            // d(bias)[k - q] over this warp's 32x32 block: transpose through a skewed scratch, lane d sums diagonal
+            // k - q = d (and its wrapped partner d - 32), then adds them to its own two slots of the warp-private
+            // window.  No shared-memory float atomics (they compile to CAS spin loops).
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(slot + j, dp[j]);
+            for (int j = 0; j < 32; ++j) tr_w[lane * 33 + j] = dp[j];
+            __syncwarp();
+            float sa = 0.f, sb = 0.f;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+              const float tv = tr_w[l * 33 + ((lane + l) & 31)];
+              if (lane + l < 32) sa += tv; else sb += tv;
+            }
+            const int base_c = c * 32 + (p.Lq - 1 - (q0 + quarter * 32));   // slot of (k - q) == 0 for this block
+            if (base_c + lane >= 0) rel_w[base_c + lane] += sa;
+            if (base_c + lane - 32 >= 0) rel_w[base_c + lane - 32] += sb;
+            __syncwarp();
           }
         }
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
@@ -219,7 +268,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                          pack_bf16x2(dp[g * 8 + 6] * p.scale, dp[g * 8 + 7] * p.scale));
         }
       }
-      if (p.dbias_rel && uniform && q_ok) atomicAdd(s_rel + (p.Lq - 1 - q), ds_rowsum);
+      if (p.dbias_rel && uniform) {
+        if (q_ok) rel_w[p.Lq - 1 - q] += ds_rowsum;   // own slot of the warp-private window
+        __syncwarp();
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
@@ -279,7 +331,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float* dst = p.dbias_rel + (long long)h * (p.Lq + p.Lk - 1) + rel_base;
     const int lim = p.Lq + p.Lk - 1 - rel_base;
     for (int i = threadIdx.x; i < n_rel && i < lim; i += blockDim.x) {
-      const float g = s_rel[i];
+      const float g = s_rel[i] + s_rel[kBwdRelMax + i] + s_rel[2 * kBwdRelMax + i] + s_rel[3 * kBwdRelMax + i];
       if (g != 0.f) atomicAdd(dst + i, g);
     }
   }
@@ -325,7 +377,7 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   VC_CHECK(a != nullptr, "vc_attn_bwd: null args");
   const vc_attn_args* f = &a->fwd;
   VC_CHECK(f->B > 0 && f->H > 0 && f->Lq > 0 && f->Lk > 0 && f->head_dim == 64, "vc_attn_bwd: bad dims");
-  VC_CHECK(f->Lq + kBT <= kBwdRelMax, "vc_attn_bwd: Lq=%d too long for the d(bias) scratch", f->Lq);
+  VC_CHECK(((f->Lq + kBT - 1) / kBT) * kBT + kBT <= kBwdRelMax, "vc_attn_bwd: Lq=%d too long for the d(bias) scratch", f->Lq);
   VC_CHECK(f->lse2 && a->delta && a->dq_acc && a->dk && a->dv && a->dout, "vc_attn_bwd: null buffers");
   VC_CHECK(a->ld_dq % 4 == 0 && a->ld_dk % 8 == 0 && a->ld_dv % 8 == 0 && a->ld_do % 8 == 0, "vc_attn_bwd: strides");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -352,6 +404,7 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   p.dk = (__nv_bfloat16*)a->dk; p.ld_dk = a->ld_dk; p.dk_col = a->dk_col;
   p.dv = (__nv_bfloat16*)a->dv; p.ld_dv = a->ld_dv; p.dv_col = a->dv_col;
   p.dbias_rel = a->dbias_rel;
+  p.drop_seed = f->drop_seed; p.drop_p16 = f->drop_p16;
   static bool attr = false;
   if (!attr) {
     VC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));

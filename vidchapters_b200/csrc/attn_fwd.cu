@@ -36,13 +36,14 @@ struct AttnFwdParams {
   const uint8_t* kmask;   // [B][Lk] or null
   int causal;
   float scale_log2e;
+  uint32_t drop_seed, drop_p16;
 };
 
 // smem: Q 16K | K 2x16K | V 16K | P 32K | bias window (Lk+128 floats) | key mask (Lk bytes) | barriers.
 // The bias/mask staging matters: with two 100 KB CTAs per SM almost no L1 is left, so per-element global loads of the
 // bias row went to L2 and made the kernel 10x slower (profiles/r01_launches_before.txt).
 constexpr int kAttnFwdTiles = 16384 + 2 * 16384 + 16384 + 32768;
-constexpr int kAttnMaxLk = 2176;  // bias window + mask must fit: (Lk+128)*4 + Lk bytes <= ~11.5 KB
+constexpr int kAttnMaxLk = 1792;  // bias window + key ceilings must fit next to 96 KB of tiles, twice per SM: 8*Lk B <= 14 KB
 
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -53,9 +54,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sV = sK + 2 * 16384;
   uint8_t* sP = sV + 16384;
   float* sBias = reinterpret_cast<float*>(sP + 32768);
-  const int bias_elems = (p.Lk + 128 + 3) & ~3;
-  uint8_t* sMask = reinterpret_cast<uint8_t*>(sBias + bias_elems);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + ((p.Lk + 15) & ~15));
+  const int lk_pad = ((p.Lk + kTK - 1) / kTK) * kTK;   // key count rounded up to whole tiles
+  // per-key ceiling applied with one FMNMX: +inf attend | kMasked (reference's additive finfo.min) | -inf out of range
+  float* sPen = sBias + lk_pad + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPen + lk_pad);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;   // [2]
   uint64_t* k_empty = bars + 3;  // [2]
@@ -87,17 +89,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // stage this query tile's bias window (index k + 127 - r == (k - q + Lq - 1) - (Lq - 128 - q0)) and the key mask
   {
     const int win0 = p.Lq - 128 - q0;  // global bias index of window slot 0 (may be negative: clamp, never used)
-    if (p.bias_rel) {
-      const float* brow = p.bias_rel + (long long)h * (p.Lq + p.Lk - 1);
-      for (int i = threadIdx.x; i < p.Lk + 127; i += blockDim.x) {
-        const int gi = win0 + i;
-        sBias[i] = (gi >= 0 && gi < p.Lq + p.Lk - 1) ? __ldg(brow + gi) * kLog2e : 0.f;
-      }
+    // Both arrays are always filled (zeros / ones without bias / mask) and padded to whole tiles so that the
+    // softmax loops below are branch-free: conditional loads compiled to one divergence region per element and
+    // serialised the whole tile (profiles/r01_attn_notes.md).
+    const float* brow = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) : nullptr;
+    for (int i = threadIdx.x; i < lk_pad + 128; i += blockDim.x) {
+      const int gi = win0 + i;
+      sBias[i] = (brow && gi >= 0 && gi < p.Lq + p.Lk - 1) ? __ldg(brow + gi) * kLog2e : 0.f;
     }
-    if (p.kmask) {
-      const uint8_t* mrow = p.kmask + (long long)b * p.Lk;
-      for (int i = threadIdx.x; i < p.Lk; i += blockDim.x) sMask[i] = mrow[i];
-    }
+    const uint8_t* mrow = p.kmask ? p.kmask + (long long)b * p.Lk : nullptr;
+    for (int i = threadIdx.x; i < lk_pad; i += blockDim.x)
+      sPen[i] = (i >= p.Lk) ? -INFINITY : ((mrow && mrow[i] == 0) ? kMasked : INFINITY);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -159,8 +161,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = quarter * 32 + lane;  // row in tile == TMEM lane
     const int q = q0 + r;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const float* brow = p.bias_rel ? sBias + (127 - r) : nullptr;  // brow[k] = bias(k - q) * log2e
-    const uint8_t* mrow = p.kmask ? sMask : nullptr;
+    const float* brow = sBias + (127 - r);  // brow[k] = bias(k - q) * log2e
     float m_run = -INFINITY, l_run = 0.0f;
     float o_acc[kD];
 #pragma unroll
@@ -170,24 +171,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int k0 = j * kTK;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // ---- pass 1: row max of s2 over the tile
+      // ---- pass 1: row max of s2 over the tile.  s2 = min(acc*scale*log2e + bias*log2e, pen[k]); causal tiles add k<=q.
+      const bool causal_tile = p.causal && (k0 + kTK - 1 > q0);   // uniform: only tiles touching the diagonal
       float m_tile = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float v[32];
         tmem_ld32(tmem_S + lane_off + c * 32, v);
+        const float4* pen4 = reinterpret_cast<const float4*>(sPen + k0 + c * 32);
+        const float* bk = brow + k0 + c * 32;
+        const int tq = q - k0 - c * 32;  // column i is causally masked iff i > tq
         tmem_ld_wait();
+        if (causal_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = k0 + c * 32 + i;
-          float s2 = v[i] * p.scale_log2e;
-          if (brow && k < p.Lk) s2 += brow[k];
-          bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[k]);
-          s2 = masked ? kMasked : s2;
-          s2 = (k < p.Lk) ? s2 : -INFINITY;
-          m_tile = fmaxf(m_tile, s2);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 pe = pen4[i >> 2];
+            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float s2 = fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]);
+              s2 = (i + e > tq) ? fminf(s2, kMasked) : s2;
+              m_tile = fmaxf(m_tile, s2);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 pe = pen4[i >> 2];
+            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m_tile = fmaxf(m_tile, fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]));
+          }
         }
       }
+      // Integer running max (log2 domain): every rescale factor is an exact power of two, so the bf16 rounding of
+      // P = 2^(s2 - m) does not depend on the tiling / on when the maximum was discovered.
+      m_tile = ceilf(m_tile);
       const float m_new = fmaxf(m_run, m_tile);
       const float corr = fast_exp2(m_run - m_new);  // m_run=-inf on first tile -> 0
       // ---- pass 2: p = exp2(s2 - m_new), write bf16 P (swizzled, K-major A operand), row sum
@@ -196,17 +215,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int c = 0; c < 4; ++c) {
         float v[32];
         tmem_ld32(tmem_S + lane_off + c * 32, v);
+        const float4* pen4 = reinterpret_cast<const float4*>(sPen + k0 + c * 32);
+        const float* bk = brow + k0 + c * 32;
+        const int tq = q - k0 - c * 32;
         tmem_ld_wait();
+        // the normaliser l uses the un-dropped probabilities (dropout acts on softmax's output)
+        if (causal_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = k0 + c * 32 + i;
-          float s2 = v[i] * p.scale_log2e;
-          if (brow && k < p.Lk) s2 += brow[k];
-          bool masked = (p.causal && k > q) || (mrow && k < p.Lk && !mrow[k]);
-          s2 = masked ? kMasked : s2;
-          const float pv = (k < p.Lk) ? fast_exp2(s2 - m_new) : 0.0f;
-          l_tile += pv;
-          v[i] = pv;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 pe = pen4[i >> 2];
+            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float s2 = fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]);
+              s2 = (i + e > tq) ? fminf(s2, kMasked) : s2;
+              const float pv = fast_exp2(s2 - m_new);
+              l_tile += pv;
+              v[i + e] = pv;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 pe = pen4[i >> 2];
+            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float pv = fast_exp2(fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]) - m_new);
+              l_tile += pv;
+              v[i + e] = pv;
+            }
+          }
+        }
+        if (p.drop_p16) {
+          const float sc = drop_scale(p.drop_p16);
+          const unsigned long long base = (((unsigned long long)b * p.H + h) * p.Lq + q) * p.Lk + k0 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = drop_keep(p.drop_seed, p.drop_p16, base + i) ? v[i] * sc : 0.0f;
         }
         // 32 columns = 4 x 16-byte chunks of this row; chunk index within the 64-wide atom: (c&1)*4 + g
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
@@ -280,12 +325,14 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
   p.lse2 = a->lse2; p.bias_rel = a->bias_rel; p.kmask = a->kmask; p.causal = a->causal;
   p.scale_log2e = a->scale * kLog2e;
+  p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16;
   VC_CHECK(a->Lk <= kAttnMaxLk, "vc_attn_fwd: Lk=%d exceeds the %d keys the bias/mask staging supports", a->Lk, kAttnMaxLk);
-  const int smem_bytes = kAttnFwdTiles + ((a->Lk + 128 + 3) & ~3) * 4 + ((a->Lk + 15) & ~15) + 128;
+  const int lk_pad = ((a->Lk + kTK - 1) / kTK) * kTK;
+  const int smem_bytes = kAttnFwdTiles + (lk_pad + 128) * 4 + lk_pad * 4 + 128;
   static bool attr = false;
   if (!attr) {
     VC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kAttnFwdTiles + (kAttnMaxLk + 128) * 4 + kAttnMaxLk + 128));
+                                 kAttnFwdTiles + (kAttnMaxLk + 128) * 4 + kAttnMaxLk * 4 + 128));
     attr = true;
   }
   dim3 grid((a->Lq + kTQ - 1) / kTQ, a->H, a->B);

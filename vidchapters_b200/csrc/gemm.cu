@@ -43,6 +43,7 @@ struct GemmParams {
   long long ld_aux;
   float alpha;
   const float* alpha_dev;  // optional device scalar multiplied into alpha
+  uint32_t drop_seed, drop_p16;  // dropout applied after the activation, before the residual add (p16 = 0: off)
 };
 
 template <int BN>
@@ -249,6 +250,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+          if (p.drop_p16) {
+            const float sc = drop_scale(p.drop_p16);
+            const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = drop_keep(p.drop_seed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
+          }
           if (p.residual) {
             const float* rsp = p.residual + (long long)row * p.ldr + col0;
             if (vec) {
@@ -372,6 +379,7 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   p.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux); p.ld_aux = a->ld_aux;
   p.alpha = a->alpha;
   p.alpha_dev = a->alpha_dev;
+  p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16;
 
   CUtensorMap tmA, tmB;
   int s;

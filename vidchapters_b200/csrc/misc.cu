@@ -21,28 +21,52 @@ __device__ __forceinline__ float warp_max_f(float v) {
 
 // ---- embedding gather: out[i,:] = table[ids[i],:]   (model/vid2seq.py:71, modeling_t5.py:972)
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
-                                                       float* __restrict__ out, int n, int d, int V) {
+                                                       float* __restrict__ out, int n, int d, int V, uint32_t drop_seed,
+                                                       uint32_t drop_p16) {
   const int lane = threadIdx.x & 31;
   const int wt = gridDim.x * (blockDim.x >> 5);
+  const float sc = drop_p16 ? drop_scale(drop_p16) : 1.f;
   for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += wt) {
     long long id = ids[i];
     if (id < 0 || id >= V) id = 0;
     const float4* src = reinterpret_cast<const float4*>(table + id * d);
     float4* dst = reinterpret_cast<float4*>(out + (long long)i * d);
-    for (int c = lane; c < d / 4; c += 32) dst[c] = __ldg(src + c);
+    for (int c = lane; c < d / 4; c += 32) {
+      float4 v = __ldg(src + c);
+      if (drop_p16) {
+        const unsigned long long base = (unsigned long long)i * d + c * 4;
+        v.x = drop_keep(drop_seed, drop_p16, base + 0) ? v.x * sc : 0.f;
+        v.y = drop_keep(drop_seed, drop_p16, base + 1) ? v.y * sc : 0.f;
+        v.z = drop_keep(drop_seed, drop_p16, base + 2) ? v.z * sc : 0.f;
+        v.w = drop_keep(drop_seed, drop_p16, base + 3) ? v.w * sc : 0.f;
+      }
+      dst[c] = v;
+    }
   }
 }
 // ---- embedding backward: dtable[ids[i],:] += dout[i,:]   (autograd of nn.Embedding; tied table)
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dout,
-                                                       float* __restrict__ dtable, int n, int d, int V) {
+                                                       float* __restrict__ dtable, int n, int d, int V, uint32_t drop_seed,
+                                                       uint32_t drop_p16) {
   const int lane = threadIdx.x & 31;
   const int wt = gridDim.x * (blockDim.x >> 5);
+  const float sc = drop_p16 ? drop_scale(drop_p16) : 1.f;
   for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += wt) {
     long long id = ids[i];
     if (id < 0 || id >= V) continue;
     const float4* src = reinterpret_cast<const float4*>(dout + (long long)i * d);
     float4* dst = reinterpret_cast<float4*>(dtable + id * d);
-    for (int c = lane; c < d / 4; c += 32) atomicAdd(dst + c, src[c]);
+    for (int c = lane; c < d / 4; c += 32) {
+      float4 v = src[c];
+      if (drop_p16) {
+        const unsigned long long base = (unsigned long long)i * d + c * 4;
+        v.x = drop_keep(drop_seed, drop_p16, base + 0) ? v.x * sc : 0.f;
+        v.y = drop_keep(drop_seed, drop_p16, base + 1) ? v.y * sc : 0.f;
+        v.z = drop_keep(drop_seed, drop_p16, base + 2) ? v.z * sc : 0.f;
+        v.w = drop_keep(drop_seed, drop_p16, base + 3) ? v.w * sc : 0.f;
+      }
+      atomicAdd(dst + c, v);
+    }
   }
 }
 
@@ -91,7 +115,7 @@ __global__ void bias_fold_kernel(const float* __restrict__ drel, const int* __re
 
 // ---- x + pos_embed (model/vit.py:119-127; nearest interpolation when T != num_features)
 __global__ void add_pos_kernel(const float* __restrict__ x, const float* __restrict__ pos, float* __restrict__ out, int B,
-                               int T, int C, int P) {
+                               int T, int C, int P, uint32_t drop_seed, uint32_t drop_p16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
   const long long total = (long long)B * T * C / 4;
   if (i < total) {
@@ -100,16 +124,31 @@ __global__ void add_pos_kernel(const float* __restrict__ x, const float* __restr
     const int src_t = (T == P) ? t : (int)floorf((float)t * ((float)P / (float)T));
     const float4 a = reinterpret_cast<const float4*>(x)[i];
     const float4 b = __ldg(reinterpret_cast<const float4*>(pos) + (long long)src_t * (C / 4) + c4);
-    reinterpret_cast<float4*>(out)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    if (drop_p16) {
+      const float sc = drop_scale(drop_p16);
+      const unsigned long long base = (unsigned long long)i * 4;
+      v.x = drop_keep(drop_seed, drop_p16, base + 0) ? v.x * sc : 0.f;
+      v.y = drop_keep(drop_seed, drop_p16, base + 1) ? v.y * sc : 0.f;
+      v.z = drop_keep(drop_seed, drop_p16, base + 2) ? v.z * sc : 0.f;
+      v.w = drop_keep(drop_seed, drop_p16, base + 3) ? v.w * sc : 0.f;
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
   }
 }
-__global__ void add_pos_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B, int T, int C, int P) {
+__global__ void add_pos_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B, int T, int C, int P,
+                                   uint32_t drop_seed, uint32_t drop_p16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over T*C
   if (i < T * C) {
     const int t = i / C, c = i % C;
     const int src_t = (T == P) ? t : (int)floorf((float)t * ((float)P / (float)T));
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dx[((long long)b * T + t) * C + c];
+    const float sc = drop_p16 ? drop_scale(drop_p16) : 1.f;
+    for (int b = 0; b < B; ++b) {
+      const unsigned long long idx = ((unsigned long long)b * T + t) * C + c;
+      const float g = dx[idx];
+      s += (!drop_p16 || drop_keep(drop_seed, drop_p16, idx)) ? g * sc : 0.f;
+    }
     atomicAdd(dpos + src_t * C + c, s);
   }
 }
@@ -242,15 +281,19 @@ static inline int cap_grid(long long blocks) {
 using namespace vc;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
-extern "C" int vc_embed_fwd(const int64_t* ids, const float* table, float* out, int n, int d, int V, void* stream) {
+extern "C" int vc_embed_fwd(const int64_t* ids, const float* table, float* out, int n, int d, int V, uint32_t drop_seed,
+                            uint32_t drop_p16, void* stream) {
   VC_CHECK(n > 0 && d % 4 == 0, "vc_embed_fwd: bad dims");
-  embed_fwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, table, out, n, d, V);
+  embed_fwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, table, out, n, d, V, drop_seed,
+                                                                  drop_p16);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
-extern "C" int vc_embed_bwd(const int64_t* ids, const float* dout, float* dtable, int n, int d, int V, void* stream) {
+extern "C" int vc_embed_bwd(const int64_t* ids, const float* dout, float* dtable, int n, int d, int V, uint32_t drop_seed,
+                            uint32_t drop_p16, void* stream) {
   VC_CHECK(n > 0 && d % 4 == 0, "vc_embed_bwd: bad dims");
-  embed_bwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, dout, dtable, n, d, V);
+  embed_bwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, dout, dtable, n, d, V, drop_seed,
+                                                                  drop_p16);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -273,15 +316,17 @@ extern "C" int vc_bias_fold(const float* drel, const int32_t* lut, float* dtable
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
-extern "C" int vc_add_pos(const float* x, const float* pos, float* out, int B, int T, int C, int P, void* stream) {
+extern "C" int vc_add_pos(const float* x, const float* pos, float* out, int B, int T, int C, int P, uint32_t drop_seed,
+                          uint32_t drop_p16, void* stream) {
   VC_CHECK(C % 4 == 0, "vc_add_pos: C must be x4");
   const long long total = (long long)B * T * C / 4;
-  add_pos_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(x, pos, out, B, T, C, P);
+  add_pos_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(x, pos, out, B, T, C, P, drop_seed, drop_p16);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
-extern "C" int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C, int P, void* stream) {
-  add_pos_bwd_kernel<<<(T * C + 255) / 256, 256, 0, ST(stream)>>>(dx, dpos, B, T, C, P);
+extern "C" int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C, int P, uint32_t drop_seed,
+                              uint32_t drop_p16, void* stream) {
+  add_pos_bwd_kernel<<<(T * C + 255) / 256, 256, 0, ST(stream)>>>(dx, dpos, B, T, C, P, drop_seed, drop_p16);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -35,7 +35,8 @@ template <bool LAYERNORM>
 __global__ void __launch_bounds__(256)
 norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, float* __restrict__ rstd_out,
-                float* __restrict__ mean_out, int M, int D, float eps, float out_scale, RowMap map) {
+                float* __restrict__ mean_out, int M, int D, float eps, float out_scale, RowMap map, uint32_t drop_seed,
+                uint32_t drop_p16) {
   const int lane = threadIdx.x & 31;
   const int nv = D / 128;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -84,6 +85,14 @@ norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
           y.x += bv.x; y.y += bv.y; y.z += bv.z; y.w += bv.w;
         }
         y.x *= out_scale; y.y *= out_scale; y.z *= out_scale; y.w *= out_scale;
+        if (drop_p16) {  // dropout on the normalised output (T5Stack final dropout, modeling_t5.py:1114)
+          const float sc = drop_scale(drop_p16);
+          const unsigned long long base = (unsigned long long)row * D + c;
+          y.x = drop_keep(drop_seed, drop_p16, base + 0) ? y.x * sc : 0.f;
+          y.y = drop_keep(drop_seed, drop_p16, base + 1) ? y.y * sc : 0.f;
+          y.z = drop_keep(drop_seed, drop_p16, base + 2) ? y.z * sc : 0.f;
+          y.w = drop_keep(drop_seed, drop_p16, base + 3) ? y.w * sc : 0.f;
+        }
         if (out)
           *reinterpret_cast<uint2*>(out + orow * D + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
         if (out_f32) *reinterpret_cast<float4*>(out_f32 + orow * D + c) = y;
@@ -100,7 +109,8 @@ __global__ void __launch_bounds__(256)
 norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ rstd_in, const float* __restrict__ mean_in, float* __restrict__ dx,
                 __nv_bfloat16* __restrict__ dx_bf16, int accumulate_dx, float* __restrict__ dw, float* __restrict__ db,
-                int M, int D, float scale, RowMap map) {
+                int M, int D, float scale, RowMap map, uint32_t g_drop_seed, uint32_t g_drop_p16, uint32_t dxb_drop_seed,
+                uint32_t dxb_drop_p16) {
   __shared__ float red[8][kMaxV4 * 128 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = D / 128;
@@ -119,7 +129,15 @@ norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const 
     for (int i = 0; i < kMaxV4; ++i) {
       if (i < nv) {
         const float4 xv = xr[lane + 32 * i];
-        const float4 gv = gr[lane + 32 * i];
+        float4 gv = gr[lane + 32 * i];
+        if (g_drop_p16) {  // the forward dropped the normalised output: the incoming gradient passes the same mask
+          const float sc = drop_scale(g_drop_p16);
+          const unsigned long long base = (unsigned long long)row * D + (lane + 32 * i) * 4;
+          gv.x = drop_keep(g_drop_seed, g_drop_p16, base + 0) ? gv.x * sc : 0.f;
+          gv.y = drop_keep(g_drop_seed, g_drop_p16, base + 1) ? gv.y * sc : 0.f;
+          gv.z = drop_keep(g_drop_seed, g_drop_p16, base + 2) ? gv.z * sc : 0.f;
+          gv.w = drop_keep(g_drop_seed, g_drop_p16, base + 3) ? gv.w * sc : 0.f;
+        }
         const float4 wv = *reinterpret_cast<const float4*>(w + (lane + 32 * i) * 4);
         xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd; xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
         const float gx = gv.x * scale, gy = gv.y * scale, gz = gv.z * scale, gw = gv.w * scale;
@@ -144,9 +162,19 @@ norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const 
           o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
         }
         dxr[lane + 32 * i] = o;
-        if (dx_bf16)
+        if (dx_bf16) {
+          // bf16 copy = the dY of the sub-layer below, whose output went through dropout before the residual add
+          if (dxb_drop_p16) {
+            const float sc = drop_scale(dxb_drop_p16);
+            const unsigned long long base = (unsigned long long)row * D + (lane + 32 * i) * 4;
+            o.x = drop_keep(dxb_drop_seed, dxb_drop_p16, base + 0) ? o.x * sc : 0.f;
+            o.y = drop_keep(dxb_drop_seed, dxb_drop_p16, base + 1) ? o.y * sc : 0.f;
+            o.z = drop_keep(dxb_drop_seed, dxb_drop_p16, base + 2) ? o.z * sc : 0.f;
+            o.w = drop_keep(dxb_drop_seed, dxb_drop_p16, base + 3) ? o.w * sc : 0.f;
+          }
           *reinterpret_cast<uint2*>(dx_bf16 + (long long)row * D + (lane + 32 * i) * 4) =
               make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
       }
     }
   }
@@ -186,7 +214,7 @@ using namespace vc;
 
 extern "C" int vc_norm_fwd(int kind, const float* x, const float* w, const float* bias, void* out_bf16, float* out_f32,
                            float* rstd, float* mean, int M, int D, float eps, float out_scale, int rows_per_batch,
-                           int out_batch_stride, int out_row_offset, void* stream) {
+                           int out_batch_stride, int out_row_offset, uint32_t drop_seed, uint32_t drop_p16, void* stream) {
   VC_CHECK(M > 0 && D > 0 && D % 128 == 0 && D <= 1024, "vc_norm_fwd: D=%d must be a multiple of 128 and <= 1024", D);
   VC_CHECK(kind == 0 || kind == 1, "vc_norm_fwd: kind 0=rms 1=layernorm");
   VC_CHECK(kind == 0 || bias != nullptr, "vc_norm_fwd: layernorm needs bias");
@@ -194,25 +222,28 @@ extern "C" int vc_norm_fwd(int kind, const float* x, const float* w, const float
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (kind == 0)
     norm_fwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
-                                                         eps, out_scale, map);
+                                                         eps, out_scale, map, drop_seed, drop_p16);
   else
     norm_fwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
-                                                        eps, out_scale, map);
+                                                        eps, out_scale, map, drop_seed, drop_p16);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 
 extern "C" int vc_norm_bwd(int kind, const float* g, const float* x, const float* w, const float* rstd, const float* mean,
                            float* dx, void* dx_bf16, int accumulate_dx, float* dw, float* db, int M, int D, float scale,
-                           int rows_per_batch, int g_batch_stride, int g_row_offset, void* stream) {
+                           int rows_per_batch, int g_batch_stride, int g_row_offset, uint32_t g_drop_seed, uint32_t g_drop_p16,
+                           uint32_t dxb_drop_seed, uint32_t dxb_drop_p16, void* stream) {
   VC_CHECK(M > 0 && D > 0 && D % 128 == 0 && D <= 1024, "vc_norm_bwd: D=%d must be a multiple of 128 and <= 1024", D);
   VC_CHECK(kind == 0 || kind == 1, "vc_norm_bwd: kind 0=rms 1=layernorm");
   RowMap map{rows_per_batch, g_batch_stride, g_row_offset};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (kind == 0)
-    norm_bwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map);
+    norm_bwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map,
+                                                         g_drop_seed, g_drop_p16, dxb_drop_seed, dxb_drop_p16);
   else
-    norm_bwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map);
+    norm_bwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map,
+                                                         g_drop_seed, g_drop_p16, dxb_drop_seed, dxb_drop_p16);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -138,6 +138,22 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 //           = +2048 B.
 constexpr uint32_t kSwizzleAtomBytes = 1024;
 
+// ---------------------------------------------------------------- dropout (counter-based, stateless)
+// keep(idx) = rnd16(seed, idx) >= p16 with p16 = round(p * 65536); kept values are scaled by 65536 / (65536 - p16).
+// Two consecutive elements share one 32-bit hash (murmur3 finaliser of the pair index), so forward and backward
+// regenerate the same mask from (seed, element index) and nothing is stored.  Reference semantics: nn.Dropout /
+// F.dropout (modeling_t5.py:307,353,572-574,618,1019,1114; vit.py:20,22,49,54,126) — same distribution, own stream.
+__device__ __forceinline__ uint32_t drop_hash(uint32_t seed, unsigned long long idx) {
+  uint32_t x = (uint32_t)(idx >> 1) * 0x9E3779B1u + (uint32_t)(idx >> 33) * 0x85EBCA77u + seed;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t p16, unsigned long long idx) {
+  const uint32_t h = drop_hash(seed, idx);
+  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= p16;
+}
+__device__ __forceinline__ float drop_scale(uint32_t p16) { return 65536.0f / (float)(65536u - p16); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;

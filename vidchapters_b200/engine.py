@@ -27,7 +27,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .config import param_shapes, vocab_size
-from .ops import ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD
+from .ops import ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD, NO_DROP, drop_spec
 
 _ALIGN = 64  # elements; keeps every parameter 256 B (fp32) / 128 B (bf16) aligned for TMA
 
@@ -114,6 +114,9 @@ class Vid2SeqEngine:
         self._scratch = torch.zeros(8, dtype=torch.float32, device=dev)
         self._luts: Dict[tuple, torch.Tensor] = {}
         self._one = torch.ones(1, dtype=torch.float32, device=dev)
+        self.drop_rates = dict(vis=0.0, enc=0.0, dec=0.0)   # vis_drop / enc_drop / dec_drop of the reference ctor
+        self.drop_seed = 0x5EED                             # user seed; every forward call derives its own stream
+        self._drop_calls = 0
         self._build_specs()
 
     # ------------------------------------------------------------------ parameter views
@@ -186,6 +189,21 @@ class Vid2SeqEngine:
             self._luts[key] = relative_position_bucket(rel, bidirectional).to(torch.int32).to(self.device)
         return self._luts[key]
 
+    # ------------------------------------------------------------------ dropout sites
+    def _begin_dropout(self, training: bool):
+        """Every forward call gets a fresh stream; every dropout site inside it a distinct seed.  Masks are regenerated
+        in the backward from (seed, element index) — nothing is stored."""
+        self._drop_on = bool(training) and any(v > 0 for v in self.drop_rates.values())
+        self._drop_calls += 1
+        self._drop_base = (self.drop_seed * 0x9E3779B1 + self._drop_calls * 0x7F4A7C15) & 0xFFFFFFFF
+        self._drop_site = 0
+
+    def _site(self, which: str):
+        if not self._drop_on or self.drop_rates[which] <= 0:
+            return NO_DROP
+        self._drop_site += 1
+        return drop_spec(self.drop_rates[which], (self._drop_base + self._drop_site * 0x632BE5AB) & 0xFFFFFFFF)
+
     # ------------------------------------------------------------------ allocation helpers
     def _e(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, device=self.device)
@@ -199,7 +217,7 @@ class Vid2SeqEngine:
         return s
 
     # ------------------------------------------------------------------ sub-layers: forward
-    def _sa_fwd(self, x0, sp: _Sub, B, L, bias_rel, kmask, causal, tape):
+    def _sa_fwd(self, x0, sp: _Sub, B, L, bias_rel, kmask, causal, tape, dk="enc"):
         ops, M, D = self.ops, x0.shape[0], x0.shape[1]
         inner = sp.H * 64
         bf = torch.bfloat16
@@ -211,12 +229,13 @@ class Vid2SeqEngine:
         ops.gemm(h, self.pb(sp.qkv_w, 3 * inner), qkv, bias=self.pv(sp.qkv_b))
         ctx = self._e(M, inner, dtype=bf)
         lse = self._e(B, sp.H, L)
+        d_attn, d_out = self._site(dk), self._site(dk)
         ops.attn_fwd(qkv, qkv, qkv, q_col=0, k_col=inner, v_col=2 * inner, B=B, H=sp.H, Lq=L, Lk=L, out=ctx, lse2=lse,
-                     bias_rel=bias_rel, kmask=kmask, causal=causal, scale=sp.scale)
+                     bias_rel=bias_rel, kmask=kmask, causal=causal, scale=sp.scale, drop=d_attn)
         x1 = self._e(M, D)
-        ops.gemm(ctx, self.pb(sp.o_w), x1, bias=self.pv(sp.o_b), residual=x0)
+        ops.gemm(ctx, self.pb(sp.o_w), x1, bias=self.pv(sp.o_b), residual=x0, drop=d_out)
         tape.append(dict(t="sa", sp=sp, x0=x0, h=h, rstd=rstd, mean=mean, qkv=qkv, ctx=ctx, lse=lse, B=B, L=L,
-                         bias_rel=bias_rel, kmask=kmask, causal=causal))
+                         bias_rel=bias_rel, kmask=kmask, causal=causal, d_attn=d_attn, d_out=d_out))
         return x1
 
     def _ca_fwd(self, y1, sp: _Sub, B, S, memory, E, mem_mask, tape):
@@ -232,15 +251,16 @@ class Vid2SeqEngine:
         ops.gemm(memory, self.pb(sp.kv_w, 2 * inner), kv)
         ctx = self._e(M, inner, dtype=bf)
         lse = self._e(B, sp.H, S)
+        d_attn, d_out = self._site("dec"), self._site("dec")
         ops.attn_fwd(qc, kv, kv, q_col=0, k_col=0, v_col=inner, B=B, H=sp.H, Lq=S, Lk=E, out=ctx, lse2=lse,
-                     bias_rel=None, kmask=mem_mask, causal=False, scale=1.0)
+                     bias_rel=None, kmask=mem_mask, causal=False, scale=1.0, drop=d_attn)
         y2 = self._e(M, D)
-        ops.gemm(ctx, self.pb(sp.o_w), y2, residual=y1)
+        ops.gemm(ctx, self.pb(sp.o_w), y2, residual=y1, drop=d_out)
         tape.append(dict(t="ca", sp=sp, x0=y1, h=h, rstd=rstd, qc=qc, kv=kv, ctx=ctx, lse=lse, B=B, S=S, E=E,
-                         mem_mask=mem_mask))
+                         mem_mask=mem_mask, d_attn=d_attn, d_out=d_out))
         return y2
 
-    def _ff_fwd(self, x1, sp: _Sub, tape):
+    def _ff_fwd(self, x1, sp: _Sub, tape, dk="enc"):
         ops, M, D = self.ops, x1.shape[0], x1.shape[1]
         bf = torch.bfloat16
         h = self._e(M, D, dtype=bf)
@@ -250,10 +270,11 @@ class Vid2SeqEngine:
         w1 = self.pb(sp.w1)
         act = self._e(M, w1.shape[0], dtype=bf)
         pre = self._e(M, w1.shape[0], dtype=bf) if sp.act == ACT_GELU else None
-        ops.gemm(h, w1, act, bias=self.pv(sp.b1), act=sp.act, pre_out=pre)
+        d_act, d_out = self._site(dk), self._site(dk)
+        ops.gemm(h, w1, act, bias=self.pv(sp.b1), act=sp.act, pre_out=pre, drop=d_act)
         x2 = self._e(M, D)
-        ops.gemm(act, self.pb(sp.w2), x2, bias=self.pv(sp.b2), residual=x1)
-        tape.append(dict(t="ff", sp=sp, x0=x1, h=h, rstd=rstd, mean=mean, act=act, pre=pre))
+        ops.gemm(act, self.pb(sp.w2), x2, bias=self.pv(sp.b2), residual=x1, drop=d_out)
+        tape.append(dict(t="ff", sp=sp, x0=x1, h=h, rstd=rstd, mean=mean, act=act, pre=pre, d_act=d_act, d_out=d_out))
         return x2
 
     # ------------------------------------------------------------------ sub-layers: backward
@@ -263,7 +284,9 @@ class Vid2SeqEngine:
         self.ops.gemm(dy, x, out, a_mn=True, b_mn=True, atomic=True,
                       splits=self._splits(out.shape[0], out.shape[1], dy.shape[0]))
 
-    def _ff_bwd(self, r, dx, dxb, ws):
+    def _ff_bwd(self, r, dx, dxb, ws, next_drop=NO_DROP):
+        """dxb arrives already masked by this sub-layer's output dropout (r["d_out"]); the norm backward at the end
+        emits the bf16 copy masked by `next_drop` = output dropout of the sub-layer processed next."""
         ops, sp = self.ops, r["sp"]
         M, D = dx.shape
         dff = r["act"].shape[1]
@@ -272,18 +295,18 @@ class Vid2SeqEngine:
         self._wgrad(dxb, r["act"], sp.w2)
         dact = ws["dact"][:M * dff].view(M, dff)
         if sp.act == ACT_GELU:
-            ops.gemm(dxb, self.pb(sp.w2), dact, b_mn=True, act=ACT_GELU_BWD, aux=r["pre"])
+            ops.gemm(dxb, self.pb(sp.w2), dact, b_mn=True, act=ACT_GELU_BWD, aux=r["pre"], drop=r["d_act"])
         else:
-            ops.gemm(dxb, self.pb(sp.w2), dact, b_mn=True, act=ACT_RELU_BWD, aux=r["act"])
+            ops.gemm(dxb, self.pb(sp.w2), dact, b_mn=True, act=ACT_RELU_BWD, aux=r["act"], drop=r["d_act"])
         if sp.b1:
             ops.colsum_bf16(dact, self.gv(sp.b1))
         self._wgrad(dact, r["h"], sp.w1)
         dh = ws["dh"][:M * D].view(M, D)
         ops.gemm(dact, self.pb(sp.w1), dh, b_mn=True)
         ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
-                     accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b))
+                     accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b), dxb_drop=next_drop)
 
-    def _sa_bwd(self, r, dx, dxb, ws, dbias_rel, lut):
+    def _sa_bwd(self, r, dx, dxb, ws, dbias_rel, lut, next_drop=NO_DROP):
         ops, sp = self.ops, r["sp"]
         M, D = dx.shape
         B, L, H = r["B"], r["L"], sp.H
@@ -301,7 +324,7 @@ class Vid2SeqEngine:
         ops.attn_bwd(qkv, qkv, qkv, q_col=0, k_col=inner, v_col=2 * inner, B=B, H=H, Lq=L, Lk=L, out=r["ctx"],
                      lse2=r["lse"], bias_rel=r["bias_rel"], kmask=r["kmask"], causal=r["causal"], scale=sp.scale,
                      dout=dctx, do_col=0, delta=delta, dq_acc=dq_acc, dk=dqkv, dk_col=inner, dv=dqkv, dv_col=2 * inner,
-                     dbias_rel=dbias_rel, bucket_lut=lut)
+                     dbias_rel=dbias_rel, bucket_lut=lut, drop=r["d_attn"])
         ops.cast_f32_bf16(dq_acc, dqkv[:, :inner])
         if sp.qkv_b:
             ops.colsum_bf16(dqkv, self.gv(sp.qkv_b))
@@ -309,9 +332,9 @@ class Vid2SeqEngine:
         dh = ws["dh"][:M * D].view(M, D)
         ops.gemm(dqkv, self.pb(sp.qkv_w, 3 * inner), dh, b_mn=True)
         ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
-                     accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b))
+                     accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b), dxb_drop=next_drop)
 
-    def _ca_bwd(self, r, dx, dxb, ws, memory, dmem):
+    def _ca_bwd(self, r, dx, dxb, ws, memory, dmem, next_drop=NO_DROP):
         ops, sp = self.ops, r["sp"]
         M, D = dx.shape
         B, S, E, H = r["B"], r["S"], r["E"], sp.H
@@ -326,13 +349,14 @@ class Vid2SeqEngine:
         delta = ws["delta"][:B * H * S].view(B, H, S)
         ops.attn_bwd(r["qc"], r["kv"], r["kv"], q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=S, Lk=E, out=r["ctx"],
                      lse2=r["lse"], bias_rel=None, kmask=r["mem_mask"], causal=False, scale=1.0, dout=dctx, do_col=0,
-                     delta=delta, dq_acc=dq_acc, dk=dkv, dk_col=0, dv=dkv, dv_col=inner, dbias_rel=None, bucket_lut=None)
+                     delta=delta, dq_acc=dq_acc, dk=dkv, dk_col=0, dv=dkv, dv_col=inner, dbias_rel=None, bucket_lut=None,
+                     drop=r["d_attn"])
         ops.cast_f32_bf16(dq_acc, dq)
         self._wgrad(dq, r["h"], sp.q_w)
         dh = ws["dh"][:M * D].view(M, D)
         ops.gemm(dq, self.pb(sp.q_w), dh, b_mn=True)
         ops.norm_bwd(0, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], None, dx=dx, dx_bf16=dxb, accumulate_dx=True,
-                     dw=self.gv(sp.norm_w))
+                     dw=self.gv(sp.norm_w), dxb_drop=next_drop)
         self._wgrad(dkv, memory, sp.kv_w, rows=2 * inner)
         ops.gemm(dkv, self.pb(sp.kv_w, 2 * inner), dmem, b_mn=True, residual=dmem)  # dmem += dkv @ Wkv
 
@@ -343,13 +367,14 @@ class Vid2SeqEngine:
         return m.contiguous().view(torch.uint8)
 
     def forward(self, video, input_ids, input_mask, output_ids, output_mask, video_cached: bool = False,
-                want_logits: bool = False):
+                want_logits: bool = False, training: bool = False):
         """One Vid2Seq forward (vid2seq.py:58-98).  Returns (loss[1] device tensor, ctx) — ctx feeds backward().
         `video` is (B,T,768) features, or the cached projected output (B,T,d) when video_cached."""
         ops, cfg, d = self.ops, self.cfg, self.d
         bf = torch.bfloat16
         tape: List[dict] = []
         ctx = {"tape": tape}
+        self._begin_dropout(training)
         B = output_ids.shape[0]
         T = video.shape[1] if self.use_video else 0
         L = input_ids.shape[1] if self.use_speech else 0
@@ -368,11 +393,13 @@ class Vid2SeqEngine:
             else:
                 C = self.C
                 xv = self._e(B * T, C)
+                d_pos = self._site("vis")
                 ops.add_pos(video.contiguous().float(), self.p("visual_encoder.pos_embed"), xv.view(B, T, C),
-                            cfg["num_features"])
+                            cfg["num_features"], drop=d_pos)
+                ctx["d_pos"] = d_pos
                 for sa, ff in self.vit_blocks:
-                    xv = self._sa_fwd(xv, sa, B, T, None, None, False, tape)
-                    xv = self._ff_fwd(xv, ff, tape)
+                    xv = self._sa_fwd(xv, sa, B, T, None, None, False, tape, dk="vis")
+                    xv = self._ff_fwd(xv, ff, tape, dk="vis")
                 rstd, mean = self._e(B * T), self._e(B * T)
                 if d == 768 and C == 768:
                     vid_f32 = self._e(B * T, C)
@@ -398,18 +425,20 @@ class Vid2SeqEngine:
         if self.use_speech:
             ids = input_ids.contiguous()
             x = self._e(B * L, d)
-            ops.embed_fwd(ids, self.p("t5_model.shared.weight"), x)
+            d_emb_e = self._site("enc")
+            ops.embed_fwd(ids, self.p("t5_model.shared.weight"), x, drop=d_emb_e)
             lut_e = self.lut(L, L, True)
             bias_e = self._e(self.H, 2 * L - 1)
             ops.bias_expand(self.p(self.enc_bias_name), lut_e, bias_e)
             kmask_e = self._mask_u8(input_mask)
             for sa, ff in self.enc_blocks:
-                x = self._sa_fwd(x, sa, B, L, bias_e, kmask_e, False, tape)
-                x = self._ff_fwd(x, ff, tape)
+                x = self._sa_fwd(x, sa, B, L, bias_e, kmask_e, False, tape, dk="enc")
+                x = self._ff_fwd(x, ff, tape, dk="enc")
             rstd_e = self._e(B * L)
+            d_fin_e = self._site("enc")
             ops.norm_fwd(0, x, self.pv("t5_model.encoder.final_layer_norm.weight"), None, out_bf16=memory, rstd=rstd_e,
-                         eps=1e-6, rows_per_batch=L, out_batch_stride=E, out_row_offset=T)
-            ctx.update(enc_x=x, enc_rstd=rstd_e, enc_ids=ids, lut_e=lut_e)
+                         eps=1e-6, rows_per_batch=L, out_batch_stride=E, out_row_offset=T, drop=d_fin_e)
+            ctx.update(enc_x=x, enc_rstd=rstd_e, enc_ids=ids, lut_e=lut_e, d_emb_e=d_emb_e, d_fin_e=d_fin_e)
         ctx["n_enc_tape"] = len(tape)
         parts = []
         if self.use_video:
@@ -423,20 +452,23 @@ class Vid2SeqEngine:
         n_valid = self._e(1)
         ops.prepare_targets(out_ids, dec_in, labels, n_valid, 0)
         y = self._e(B * S, d)
-        ops.embed_fwd(dec_in, self.p("t5_model.shared.weight"), y)
+        d_emb_d = self._site("dec")
+        ops.embed_fwd(dec_in, self.p("t5_model.shared.weight"), y, drop=d_emb_d)
         lut_d = self.lut(S, S, False)
         bias_d = self._e(self.H, 2 * S - 1)
         ops.bias_expand(self.p(self.dec_bias_name), lut_d, bias_d)
         kmask_d = self._mask_u8(output_mask)
         for sa, ca, ff in self.dec_blocks:
-            y = self._sa_fwd(y, sa, B, S, bias_d, kmask_d, True, tape)
+            y = self._sa_fwd(y, sa, B, S, bias_d, kmask_d, True, tape, dk="dec")
             y = self._ca_fwd(y, ca, B, S, memory, E, mem_mask, tape)
-            y = self._ff_fwd(y, ff, tape)
+            y = self._ff_fwd(y, ff, tape, dk="dec")
         # ---------------- head: final norm * d^-0.5 (tied), lm_head, label-smoothed CE (modeling_t5.py:1709-1721)
         seq = self._e(B * S, d, dtype=bf)
         rstd_d = self._e(B * S)
+        d_fin_d = self._site("dec")
         ops.norm_fwd(0, y, self.pv("t5_model.decoder.final_layer_norm.weight"), None, out_bf16=seq, rstd=rstd_d, eps=1e-6,
-                     out_scale=d ** -0.5)
+                     out_scale=d ** -0.5, drop=d_fin_d)
+        ctx.update(d_emb_d=d_emb_d, d_fin_d=d_fin_d)
         Vp = (self.V + 7) // 8 * 8   # leading dimension padded to 16 B (vc.py's vocab 32100 is not a multiple of 8)
         logits = self._e(B * S, Vp)[:, :self.V]
         ops.gemm(seq, self.pb("t5_model.shared.weight"), logits)
@@ -473,20 +505,24 @@ class Vid2SeqEngine:
         ops.gemm(dlogits, self.pb("t5_model.shared.weight"), dseq, b_mn=True, alpha_dev=gl)
         dy = self._e(B * S, d)
         dyb = self._e(B * S, d, dtype=bf)
+        def out_drop(j):   # output dropout of tape record j (the sub-layer whose backward consumes the next bf16 dx)
+            return tape[j]["d_out"] if j >= 0 else NO_DROP
+        i = len(tape)
         ops.norm_bwd(0, dseq, ctx["dec_x"], self.pv("t5_model.decoder.final_layer_norm.weight"), ctx["dec_rstd"], None,
                      dx=dy, dx_bf16=dyb, accumulate_dx=False, dw=self.gv("t5_model.decoder.final_layer_norm.weight"),
-                     scale=d ** -0.5)
+                     scale=d ** -0.5, g_drop=ctx["d_fin_d"], dxb_drop=out_drop(i - 1))
         # ---- decoder blocks (reverse)
         dmem = self._z(B * E, d)
         drel_d = self._z(self.H, 2 * S - 1)
-        i = len(tape)
+        n_dec_end = ctx["n_enc_tape"]
         for _ in range(len(self.dec_blocks)):
-            self._ff_bwd(tape[i - 1], dy, dyb, ws)
-            self._ca_bwd(tape[i - 2], dy, dyb, ws, ctx["memory"], dmem)
-            self._sa_bwd(tape[i - 3], dy, dyb, ws, drel_d, ctx["lut_d"])
+            self._ff_bwd(tape[i - 1], dy, dyb, ws, next_drop=out_drop(i - 2))
+            self._ca_bwd(tape[i - 2], dy, dyb, ws, ctx["memory"], dmem, next_drop=out_drop(i - 3))
+            self._sa_bwd(tape[i - 3], dy, dyb, ws, drel_d, ctx["lut_d"],
+                         next_drop=out_drop(i - 4) if i - 4 >= n_dec_end else NO_DROP)
             i -= 3
         ops.bias_fold(drel_d, ctx["lut_d"], self.g(self.dec_bias_name))
-        ops.embed_bwd(ctx["dec_in"].view(-1), dy, self.g("t5_model.shared.weight"))
+        ops.embed_bwd(ctx["dec_in"].view(-1), dy, self.g("t5_model.shared.weight"), drop=ctx["d_emb_d"])
         if grad_video is not None and self.use_video:
             dmem.view(B, E, d)[:, :T].add_(grad_video.reshape(B, T, d).to(dmem.dtype))
         # ---- text encoder
@@ -495,14 +531,17 @@ class Vid2SeqEngine:
             dxb = self._e(B * L, d, dtype=bf)
             ops.norm_bwd(0, dmem, ctx["enc_x"], self.pv("t5_model.encoder.final_layer_norm.weight"), ctx["enc_rstd"], None,
                          dx=dx, dx_bf16=dxb, accumulate_dx=False, dw=self.gv("t5_model.encoder.final_layer_norm.weight"),
-                         rows_per_batch=L, g_batch_stride=E, g_row_offset=T)
+                         rows_per_batch=L, g_batch_stride=E, g_row_offset=T, g_drop=ctx["d_fin_e"],
+                         dxb_drop=out_drop(i - 1))
             drel_e = self._z(self.H, 2 * L - 1)
+            n_enc_end = ctx["n_vit_tape"]
             for _ in range(len(self.enc_blocks)):
-                self._ff_bwd(tape[i - 1], dx, dxb, ws)
-                self._sa_bwd(tape[i - 2], dx, dxb, ws, drel_e, ctx["lut_e"])
+                self._ff_bwd(tape[i - 1], dx, dxb, ws, next_drop=out_drop(i - 2))
+                self._sa_bwd(tape[i - 2], dx, dxb, ws, drel_e, ctx["lut_e"],
+                             next_drop=out_drop(i - 3) if i - 3 >= n_enc_end else NO_DROP)
                 i -= 2
             ops.bias_fold(drel_e, ctx["lut_e"], self.g(self.enc_bias_name))
-            ops.embed_bwd(ctx["enc_ids"].view(-1), dx, self.g("t5_model.shared.weight"))
+            ops.embed_bwd(ctx["enc_ids"].view(-1), dx, self.g("t5_model.shared.weight"), drop=ctx["d_emb_e"])
         # ---- visual encoder
         dvideo_out = None
         if self.use_video:
@@ -516,7 +555,7 @@ class Vid2SeqEngine:
                     ops.norm_bwd(1, dmem, ctx["vit_x"], self.pv("visual_encoder.norm.weight"), ctx["vit_rstd"],
                                  ctx["vit_mean"], dx=dxv, dx_bf16=dxvb, accumulate_dx=False,
                                  dw=self.gv("visual_encoder.norm.weight"), db=self.gv("visual_encoder.norm.bias"),
-                                 rows_per_batch=T, g_batch_stride=E, g_row_offset=0)
+                                 rows_per_batch=T, g_batch_stride=E, g_row_offset=0, dxb_drop=out_drop(i - 1))
                 else:
                     dvid = dmem.view(B, E, d)[:, :T].reshape(B * T, d).contiguous()
                     dvb = self._e(B * T, d, dtype=bf)
@@ -527,12 +566,14 @@ class Vid2SeqEngine:
                     ops.gemm(dvb, self.pb("proj_v2t.weight"), dvn, b_mn=True)
                     ops.norm_bwd(1, dvn, ctx["vit_x"], self.pv("visual_encoder.norm.weight"), ctx["vit_rstd"],
                                  ctx["vit_mean"], dx=dxv, dx_bf16=dxvb, accumulate_dx=False,
-                                 dw=self.gv("visual_encoder.norm.weight"), db=self.gv("visual_encoder.norm.bias"))
+                                 dw=self.gv("visual_encoder.norm.weight"), db=self.gv("visual_encoder.norm.bias"),
+                                 dxb_drop=out_drop(i - 1))
                 for _ in range(len(self.vit_blocks)):
-                    self._ff_bwd(tape[i - 1], dxv, dxvb, ws)
-                    self._sa_bwd(tape[i - 2], dxv, dxvb, ws, None, None)
+                    self._ff_bwd(tape[i - 1], dxv, dxvb, ws, next_drop=out_drop(i - 2))
+                    self._sa_bwd(tape[i - 2], dxv, dxvb, ws, None, None, next_drop=out_drop(i - 3))
                     i -= 2
-                ops.add_pos_bwd(dxv, self.g("visual_encoder.pos_embed"), B, T, C, self.cfg["num_features"])
+                ops.add_pos_bwd(dxv, self.g("visual_encoder.pos_embed"), B, T, C, self.cfg["num_features"],
+                                drop=ctx["d_pos"])
         assert i == 0, i
         return dvideo_out
 

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvidchap.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class GemmArgs(C.Structure):
@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("alpha_dev", C.c_void_p),
         ("splits", C.c_int32),
         ("tile_n", C.c_int32),
+        ("drop_seed", C.c_uint32), ("drop_p16", C.c_uint32),
     ]
 
 
@@ -44,6 +45,7 @@ class AttnArgs(C.Structure):
         ("kmask", C.c_void_p),
         ("causal", C.c_int32),
         ("scale", C.c_float),
+        ("drop_seed", C.c_uint32), ("drop_p16", C.c_uint32),
     ]
 
 
@@ -60,20 +62,20 @@ class AttnBwdArgs(C.Structure):
     ]
 
 
-P, I, I64, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+P, I, I64, F, U = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32
 SIGNATURES = {
     "vc_gemm_bf16": [C.POINTER(GemmArgs), P],
     "vc_attn_fwd": [C.POINTER(AttnArgs), P],
     "vc_attn_bwd": [C.POINTER(AttnBwdArgs), P],
-    "vc_norm_fwd": [I, P, P, P, P, P, P, P, I, I, F, F, I, I, I, P],
-    "vc_norm_bwd": [I, P, P, P, P, P, P, P, I, P, P, I, I, F, I, I, I, P],
-    "vc_embed_fwd": [P, P, P, I, I, I, P],
-    "vc_embed_bwd": [P, P, P, I, I, I, P],
+    "vc_norm_fwd": [I, P, P, P, P, P, P, P, I, I, F, F, I, I, I, U, U, P],
+    "vc_norm_bwd": [I, P, P, P, P, P, P, P, I, P, P, I, I, F, I, I, I, U, U, U, U, P],
+    "vc_embed_fwd": [P, P, P, I, I, I, U, U, P],
+    "vc_embed_bwd": [P, P, P, I, I, I, U, U, P],
     "vc_prepare_targets": [P, P, P, P, I, I, I64, P],
     "vc_bias_expand": [P, P, P, I, I, P],
     "vc_bias_fold": [P, P, P, I, I, P],
-    "vc_add_pos": [P, P, P, I, I, I, I, P],
-    "vc_add_pos_bwd": [P, P, I, I, I, I, P],
+    "vc_add_pos": [P, P, P, I, I, I, I, U, U, P],
+    "vc_add_pos_bwd": [P, P, I, I, I, I, U, U, P],
     "vc_cross_entropy": [P, I64, P, P, F, P, P, I64, I, I, P],
     "vc_colsum_bf16": [P, I64, P, I, I, P],
     "vc_cast_f32_bf16": [P, I64, P, I64, I, I, F, P],

@@ -13,6 +13,13 @@ import torch
 from . import lib as _lib
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_RELU_BWD, ACT_GELU_BWD = 0, 1, 2, 3, 4
+NO_DROP = (0, 0)   # (seed, p16): dropout spec; p16 = round(p * 65536), 0 = off
+
+
+def drop_spec(p: float, seed: int):
+    """(seed, p16) for a dropout site; kept values are scaled by 65536 / (65536 - p16) inside the kernels."""
+    p16 = int(round(float(p) * 65536.0))
+    return (int(seed) & 0xFFFFFFFF, p16) if p16 > 0 else NO_DROP
 
 
 def _ptr(t):
@@ -41,7 +48,7 @@ class CudaOps:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, pre_out=None,
-             aux=None, alpha=1.0, alpha_dev=None, splits=1, atomic=False, tile_n=0):
+             aux=None, alpha=1.0, alpha_dev=None, splits=1, atomic=False, tile_n=0, drop=NO_DROP):
         """out[M,N] = epi(alpha * op(A) @ op(B)^T).  A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn)."""
         _chk_cuda(A, B, out, bias, residual, pre_out, aux)
         assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -75,12 +82,14 @@ class CudaOps:
         a.alpha_dev = None if alpha_dev is None else alpha_dev.data_ptr()
         a.splits = int(splits)
         a.tile_n = int(tile_n)
+        a.drop_seed, a.drop_p16 = drop
         _lib.check(self.lib.vc_gemm_bf16(C.byref(a), self._stream()))
         self.launches += 1
         return out
 
     # ------------------------------------------------------------------ attention
-    def _attn_args(self, q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale):
+    def _attn_args(self, q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale,
+                   drop=NO_DROP):
         _chk_cuda(q, k, v, out, lse2, bias_rel, kmask)
         for t in (q, k, v, out):
             assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
@@ -100,21 +109,23 @@ class CudaOps:
         a.kmask = None if kmask is None else kmask.data_ptr()
         a.causal = int(causal)
         a.scale = float(scale)
+        a.drop_seed, a.drop_p16 = drop
         return a
 
     def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
-                 causal=False, scale=1.0):
-        a = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale)
+                 causal=False, scale=1.0, drop=NO_DROP):
+        a = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale, drop)
         _lib.check(self.lib.vc_attn_fwd(C.byref(a), self._stream()))
         self.launches += 1
 
     def attn_bwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, dout, do_col=0, delta, dq_acc, dk, dk_col, dv, dv_col, dbias_rel=None,
-                 bucket_lut=None):
+                 bucket_lut=None, drop=NO_DROP):
         """dq_acc must be zeroed by the caller (fp32 atomics); dk/dv are fully written; dbias_rel accumulates."""
         _chk_cuda(dout, delta, dq_acc, dk, dv, dbias_rel, bucket_lut)
         b = _lib.AttnBwdArgs()
-        b.fwd = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale)
+        b.fwd = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale,
+                                drop)
         assert dout.dtype == torch.bfloat16 and dq_acc.dtype == torch.float32 and delta.dtype == torch.float32
         assert dk.dtype == torch.bfloat16 and dv.dtype == torch.bfloat16
         b.dout, b.ld_do, b.do_col = dout.data_ptr(), dout.stride(0), do_col
@@ -131,37 +142,38 @@ class CudaOps:
 
     # ------------------------------------------------------------------ norms
     def norm_fwd(self, kind, x, w, bias, *, out_bf16=None, out_f32=None, rstd=None, mean=None, eps, out_scale=1.0,
-                 rows_per_batch=0, out_batch_stride=0, out_row_offset=0):
+                 rows_per_batch=0, out_batch_stride=0, out_row_offset=0, drop=NO_DROP):
         _chk_cuda(x, w, bias, out_bf16, out_f32, rstd, mean)
         M, D = x.shape
         assert x.dtype == torch.float32 and x.is_contiguous()
         _lib.check(self.lib.vc_norm_fwd(kind, _ptr(x), _ptr(w), _ptr(bias), _ptr(out_bf16), _ptr(out_f32), _ptr(rstd),
                                         _ptr(mean), M, D, eps, out_scale, rows_per_batch, out_batch_stride,
-                                        out_row_offset, self._stream()))
+                                        out_row_offset, drop[0], drop[1], self._stream()))
         self.launches += 1
 
     def norm_bwd(self, kind, g, x, w, rstd, mean, *, dx, dx_bf16=None, accumulate_dx, dw, db=None, scale=1.0,
-                 rows_per_batch=0, g_batch_stride=0, g_row_offset=0):
+                 rows_per_batch=0, g_batch_stride=0, g_row_offset=0, g_drop=NO_DROP, dxb_drop=NO_DROP):
         _chk_cuda(g, x, w, rstd, mean, dx, dx_bf16, dw, db)
         M, D = x.shape
         assert g.dtype == torch.float32 and dx.dtype == torch.float32 and x.is_contiguous() and dx.is_contiguous()
         _lib.check(self.lib.vc_norm_bwd(kind, _ptr(g), _ptr(x), _ptr(w), _ptr(rstd), _ptr(mean), _ptr(dx), _ptr(dx_bf16),
                                         int(accumulate_dx), _ptr(dw), _ptr(db), M, D, scale, rows_per_batch,
-                                        g_batch_stride, g_row_offset, self._stream()))
+                                        g_batch_stride, g_row_offset, g_drop[0], g_drop[1], dxb_drop[0], dxb_drop[1],
+                                        self._stream()))
         self.launches += 1
 
     # ------------------------------------------------------------------ small ops
-    def embed_fwd(self, ids, table, out):
+    def embed_fwd(self, ids, table, out, drop=NO_DROP):
         _chk_cuda(ids, table, out)
         assert ids.dtype == torch.int64 and ids.is_contiguous() and out.is_contiguous()
         _lib.check(self.lib.vc_embed_fwd(_ptr(ids), _ptr(table), _ptr(out), ids.numel(), table.shape[1], table.shape[0],
-                                         self._stream()))
+                                         drop[0], drop[1], self._stream()))
         self.launches += 1
 
-    def embed_bwd(self, ids, dout, dtable):
+    def embed_bwd(self, ids, dout, dtable, drop=NO_DROP):
         _chk_cuda(ids, dout, dtable)
         _lib.check(self.lib.vc_embed_bwd(_ptr(ids), _ptr(dout), _ptr(dtable), ids.numel(), dtable.shape[1],
-                                         dtable.shape[0], self._stream()))
+                                         dtable.shape[0], drop[0], drop[1], self._stream()))
         self.launches += 1
 
     def prepare_targets(self, out_ids, dec_in, labels, n_valid, pad_id=0):
@@ -184,16 +196,16 @@ class CudaOps:
         _lib.check(self.lib.vc_bias_fold(_ptr(drel), _ptr(lut), _ptr(dtable), H, R, self._stream()))
         self.launches += 1
 
-    def add_pos(self, x, pos, out, P):
+    def add_pos(self, x, pos, out, P, drop=NO_DROP):
         _chk_cuda(x, pos, out)
         B, T, Cc = x.shape
         assert x.dtype == torch.float32 and x.is_contiguous()
-        _lib.check(self.lib.vc_add_pos(_ptr(x), _ptr(pos), _ptr(out), B, T, Cc, P, self._stream()))
+        _lib.check(self.lib.vc_add_pos(_ptr(x), _ptr(pos), _ptr(out), B, T, Cc, P, drop[0], drop[1], self._stream()))
         self.launches += 1
 
-    def add_pos_bwd(self, dx, dpos, B, T, Cc, P):
+    def add_pos_bwd(self, dx, dpos, B, T, Cc, P, drop=NO_DROP):
         _chk_cuda(dx, dpos)
-        _lib.check(self.lib.vc_add_pos_bwd(_ptr(dx), _ptr(dpos), B, T, Cc, P, self._stream()))
+        _lib.check(self.lib.vc_add_pos_bwd(_ptr(dx), _ptr(dpos), B, T, Cc, P, drop[0], drop[1], self._stream()))
         self.launches += 1
 
     def cross_entropy(self, logits, labels, n_valid, smoothing, loss_out, dlogits):

@@ -51,7 +51,9 @@ class _Vid2SeqFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, anchor, video, input_ids, input_mask, output_ids, output_mask, cached):
         eng = module.engine
-        loss, ectx = eng.forward(video, input_ids, input_mask, output_ids, output_mask, video_cached=cached)
+        eng.drop_rates = dict(vis=module.vis_drop, enc=module.enc_drop, dec=module.dec_drop)
+        loss, ectx = eng.forward(video, input_ids, input_mask, output_ids, output_mask, video_cached=cached,
+                                 training=module.training)
         ctx.module, ctx.ectx = module, ectx
         ctx.set_materialize_grads(False)
         B, T = ectx["B"], ectx["T"]
@@ -188,8 +190,6 @@ class Vid2Seq(nn.Module):
 
     # ------------------------------------------------------------------ reference surface
     def forward(self, video, input_tokenized, output_tokenized):
-        if self.training and (self.vis_drop > 0 or self.enc_drop > 0 or self.dec_drop > 0):
-            raise NotImplementedError("dropout > 0 is not implemented yet in the B200 path; build with *_drop=0")
         self._refresh_shadow()
         cached = isinstance(video, dict)
         if self.use_video:
