@@ -55,8 +55,11 @@ def _gelu_grad(x):
 class TorchOps:
     name = "torch-oracle"
 
-    def __init__(self):
+    def __init__(self, flash_rounding: bool = True):
         self.launches = 0
+        # flash_rounding: round the UN-normalised probabilities 2^(s2 - ceil(rowmax2)) to bf16 before P.V and divide by
+        # the row sum afterwards — the attention kernel's rounding points (see oracle/vid2seq_oracle.py::Arith).
+        self.flash = flash_rounding
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, pre_out=None,
@@ -109,11 +112,14 @@ class TorchOps:
     def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, drop=NO_DROP):
         s = self._scores(q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale)
-        p = torch.softmax(s, dim=-1)
-        if drop[1]:
-            p = p * drop_mask(drop, _idx(p.shape, p.device))
         vh = self._heads(v, v_col, B, Lk, H)
-        o = p.to(torch.bfloat16).float() @ vh
+        dm = drop_mask(drop, _idx(s.shape, s.device)) if drop[1] else 1.0
+        if self.flash:
+            s2 = s * math.log2(math.e)
+            e = torch.exp2(s2 - torch.ceil(s2.max(-1, keepdim=True).values))
+            o = ((e * dm).to(torch.bfloat16).float() @ vh) / e.sum(-1, keepdim=True)
+        else:
+            o = (torch.softmax(s, dim=-1) * dm).to(torch.bfloat16).float() @ vh
         out[:, :H * 64].copy_(o.permute(0, 2, 1, 3).reshape(B * Lq, H * 64).to(out.dtype))
         if lse2 is not None:
             lse2.copy_(torch.logsumexp(s, dim=-1) * math.log2(math.e))

@@ -51,7 +51,7 @@ def test_engine_matches_oracle(cfg):
     eng.zero_grad()
     eng.backward(ctx)
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True)
+    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True)
     o["loss"].backward()
     assert abs(loss.item() - o["loss"].item()) < 1e-4 * abs(o["loss"].item())
     assert rel(ctx["logits"].reshape(o["logits"].shape), o["logits"]) < 1e-3          # tier A
@@ -161,8 +161,8 @@ def test_two_pass_cached_video_gradients():
     (l1["loss"] + l2["loss"]).backward()
     g_two = {n: p.grad.clone() for n, p in m._params.items()}
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in m._params.items()}
-    o1 = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True)
-    o2 = O.vid2seq_forward(sd, cfg, o1["video"], inp2, inp2 != 0, out2, out2 != 0, emulate_bf16=True, video_is_cached=True)
+    o1 = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True)
+    o2 = O.vid2seq_forward(sd, cfg, o1["video"], inp2, inp2 != 0, out2, out2 != 0, emulate_bf16=True, flash_rounding=True, video_is_cached=True)
     (o1["loss"] + o2["loss"]).backward()
     for n in ("visual_encoder.blocks.0.attn.qkv.weight", "visual_encoder.pos_embed", "t5_model.shared.weight",
               "t5_model.decoder.block.1.layer.1.EncDecAttention.k.weight"):
@@ -189,7 +189,7 @@ def test_dropout_forward_backward_match_replayed_masks(cfg):
     assert abs(loss.item() - loss_eval.item()) > 1e-3          # dropout really changes the forward
     sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     plan = O.DropPlan(dict(vis=0.1, enc=0.1, dec=0.1), base)
-    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, drop_plan=plan)
+    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True, drop_plan=plan)
     o["loss"].backward()
     assert plan.k == n_sites                              # same number of dropout sites visited
     assert abs(loss.item() - o["loss"].item()) < 2e-4 * abs(o["loss"].item())

@@ -8,11 +8,11 @@
 //   A "MN-major" : stored [K][M]  (dY^T in wgrad: reduction over tokens, tokens are the rows)
 //   B "K-major"  : stored [N][K]  (nn.Linear weight in forward)
 //   B "MN-major" : stored [K][N]  (weight in dgrad, activations in wgrad)
-// Kernel: persistent, one CTA per SM, 256 threads:
+// Kernel: persistent, one CTA per SM, 384 threads:
 //   warp 0 lane 0 : TMA producer      (cp.async.bulk.tensor, 128B-swizzled 64-wide boxes -> 4..8 stage smem ring)
 //   warp 1 lane 0 : tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1), commits to mbarriers
 //   warp 2        : TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4..7    : epilogue: tcgen05.ld TMEM->registers, fused bias / activation / activation-backward / residual /
+//   warps 4..11   : epilogue (2 warps per TMEM lane quarter, one per column half): tcgen05.ld TMEM->registers, fused bias / activation / activation-backward / residual /
 //                   alpha, bf16 or fp32 store, or fp32 atomic accumulate (split-K for wgrad).
 // The accumulator is double-buffered in TMEM so tile i's epilogue overlaps tile i+1's MMAs.
 #include <cuda_bf16.h>
@@ -62,7 +62,7 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
@@ -93,7 +93,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 256);
     }
     fence_barrier_init();
   }
@@ -171,8 +171,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter accessible to this warp
+    // ===================== epilogue: 8 warps =====================
+    // Warp w reads TMEM lane quarter (w & 3) and the column half (w - 4) / 4 of the tile.  Side inputs (residual, aux)
+    // are requested BEFORE waiting for the TMEM load so their L2/HBM latency overlaps it; with the accumulator double
+    // buffered the whole epilogue of tile i overlaps the MMAs of tile i+1.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kChunks = BN / 64;  // 32-column chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -184,128 +189,140 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < p.M;
       const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < kChunks; ++c) {
+        const int cc = half * kChunks + c;  // chunk index inside the tile
+        const int col0 = n0 + cc * 32;
         float v[32];
-        tmem_ld32(tmem_base + acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < p.N) {
-          const int ncols = min(32, p.N - col0);
-          const bool vec = (ncols & 7) == 0;  // ragged N (e.g. vocab 32100): the last chunk takes the scalar path
+        tmem_ld32(tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16), v);
+        const int ncols = min(32, p.N - col0);
+        const bool full = row_ok && ncols == 32;  // fast path: whole 32-column chunk in range
+        float4 rs[8];
+        uint4 ax[4];
+        if (full) {
+          if (p.residual) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= alpha;
-          if (p.bias) {
+            for (int j = 0; j < 8; ++j) rs[j] = rp[j];
+          }
+          if (p.act >= 3) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ld_aux + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ax[j] = __ldg(ap + j);
+          }
+        }
+        tmem_ld_wait();
+        if (!row_ok || ncols <= 0) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= alpha;
+        if (p.bias) {
+          if (full) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              v[j * 4] += b4.x; v[j * 4 + 1] += b4.y; v[j * 4 + 2] += b4.z; v[j * 4 + 3] += b4.w;
+            }
+          } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
           }
-          if (p.act == 2 && p.pre_out) {
-            __nv_bfloat16* dstp = p.pre_out + (long long)row * p.ldo + col0;
-            if (vec) {
-              uint4* dst = reinterpret_cast<uint4*>(dstp);
+        }
+        if (p.act == 2 && p.pre_out) {
+          __nv_bfloat16* dstp = p.pre_out + (long long)row * p.ldo + col0;
+          if (full) {
+            uint4* dst = reinterpret_cast<uint4*>(dstp);
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j * 8 < ncols)
-                  dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
-                                      pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
-            } else {
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                  pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+          } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) dstp[j] = __float2bfloat16(v[j]);
-            }
+            for (int j = 0; j < 32; ++j) if (j < ncols) dstp[j] = __float2bfloat16(v[j]);
           }
-          if (p.act == 1) {
+        }
+        if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-          } else if (p.act == 2) {
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (p.act == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (p.act == 3 || p.act == 4) {
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act >= 3) {
+          if (!full) {  // ragged tail: gather the aux values element-wise
             const __nv_bfloat16* axp = p.aux + (long long)row * p.ld_aux + col0;
+            uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j * 8 < ncols) {
-                uint32_t w[4];
-                if (vec) {
-                  const uint4 a = __ldg(reinterpret_cast<const uint4*>(axp) + j);
-                  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int c0 = j * 8 + e * 2;
-                    const float lo = c0 < ncols ? __bfloat162float(axp[c0]) : 0.f;
-                    const float hi = c0 + 1 < ncols ? __bfloat162float(axp[c0 + 1]) : 0.f;
-                    w[e] = pack_bf16x2(lo, hi);
-                  }
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
-                  if (p.act == 3) {
-                    v[j * 8 + e * 2] = lo > 0.0f ? v[j * 8 + e * 2] : 0.0f;
-                    v[j * 8 + e * 2 + 1] = hi > 0.0f ? v[j * 8 + e * 2 + 1] : 0.0f;
-                  } else {
-                    v[j * 8 + e * 2] *= gelu_erf_grad(lo);
-                    v[j * 8 + e * 2 + 1] *= gelu_erf_grad(hi);
-                  }
-                }
-              }
+            for (int e = 0; e < 16; ++e) {
+              const float lo = e * 2 < ncols ? __bfloat162float(axp[e * 2]) : 0.f;
+              const float hi = e * 2 + 1 < ncols ? __bfloat162float(axp[e * 2 + 1]) : 0.f;
+              w[e] = pack_bf16x2(lo, hi);
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ax[j] = make_uint4(w[j * 4], w[j * 4 + 1], w[j * 4 + 2], w[j * 4 + 3]);
           }
-          if (p.drop_p16) {
-            const float sc = drop_scale(p.drop_p16);
-            const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + col0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = drop_keep(p.drop_seed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
-          }
-          if (p.residual) {
-            const float* rsp = p.residual + (long long)row * p.ldr + col0;
-            if (vec) {
-              const float4* rs = reinterpret_cast<const float4*>(rsp);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w[4] = {ax[j].x, ax[j].y, ax[j].z, ax[j].w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (j * 4 < ncols) {
-                  const float4 r = rs[j];
-                  v[j * 4 + 0] += r.x; v[j * 4 + 1] += r.y; v[j * 4 + 2] += r.z; v[j * 4 + 3] += r.w;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += rsp[j];
-            }
-          }
-          if (p.out_fp32) {
-            float* dstf = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
-            if (vec) {
-              float4* dst = reinterpret_cast<float4*>(dstf);
-              if (p.atomic) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (j * 4 < ncols) atomicAdd(dst + j, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
+            for (int e = 0; e < 4; ++e) {
+              const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+              if (p.act == 3) {
+                v[j * 8 + e * 2] = lo > 0.0f ? v[j * 8 + e * 2] : 0.0f;
+                v[j * 8 + e * 2 + 1] = hi > 0.0f ? v[j * 8 + e * 2 + 1] : 0.0f;
               } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (j * 4 < ncols) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                v[j * 8 + e * 2] *= gelu_erf_grad(lo);
+                v[j * 8 + e * 2 + 1] *= gelu_erf_grad(hi);
               }
-            } else {
+            }
+          }
+        }
+        if (p.drop_p16) {
+          const float sc = drop_scale(p.drop_p16);
+          const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + col0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j < ncols) {
-                  if (p.atomic) atomicAdd(dstf + j, v[j]); else dstf[j] = v[j];
-                }
-              }
+          for (int j = 0; j < 32; ++j) v[j] = drop_keep(p.drop_seed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
+        }
+        if (p.residual) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j * 4 + 0] += rs[j].x; v[j * 4 + 1] += rs[j].y; v[j * 4 + 2] += rs[j].z; v[j * 4 + 3] += rs[j].w;
             }
           } else {
-            __nv_bfloat16* dstb = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
-            if (vec) {
-              uint4* dst = reinterpret_cast<uint4*>(dstb);
+            const float* rsp = p.residual + (long long)row * p.ldr + col0;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j * 8 < ncols)
-                  dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
-                                      pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += rsp[j];
+          }
+        }
+        if (p.out_fp32) {
+          float* dstf = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
+          if (full) {
+            float4* dst = reinterpret_cast<float4*>(dstf);
+            if (p.atomic) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) atomicAdd(dst + j, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) dstb[j] = __float2bfloat16(v[j]);
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < ncols) {
+                if (p.atomic) atomicAdd(dstf + j, v[j]); else dstf[j] = v[j];
+              }
+            }
+          }
+        } else {
+          __nv_bfloat16* dstb = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
+          if (full) {
+            uint4* dst = reinterpret_cast<uint4*>(dstb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                  pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) dstb[j] = __float2bfloat16(v[j]);
           }
         }
       }
@@ -332,7 +349,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, 256, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  kern<<<grid, 384, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
