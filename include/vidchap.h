@@ -71,6 +71,10 @@ typedef struct vc_attn_args {
   int32_t causal;
   float scale;
   uint32_t drop_seed, drop_p16;  /* dropout on the probabilities (modeling_t5.py:572-574, vit.py:49); index ((b*H+h)*Lq+q)*Lk+k */
+  /* incremental decoding (forward only; leave 0 for training): queries sit at positions q + q_offset (+ *q_offset_dev),
+   * K/V batches are kv_batch_rows rows apart (a KV cache of that capacity), bias row = bias_len entries with relative
+   * position 0 at bias_zero (bias_len = 0: the training layout Lq+Lk-1 / Lq-1).  modeling_t5.py:484-488,500-525,551-556. */
+  int32_t q_offset; const int32_t* q_offset_dev; int32_t kv_batch_rows; int32_t bias_zero, bias_len;
 } vc_attn_args;
 int vc_attn_fwd(const vc_attn_args* args, void* stream);
 
@@ -132,6 +136,13 @@ int vc_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, con
 int vc_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream);
 int vc_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int M, int N, float scale, void* stream);
 int vc_copy_rows_bf16(const void* src, void* dst, int B, int T, int C, int E, int row_off, void* stream);
+
+/* ---- Incremental greedy decoding (model/vid2seq.py:150-162 with num_beams=1; HF-4.28 greedy semantics).
+ * The step position lives in device memory (pos_dev) so one decode step is a fixed CUDA graph. */
+int vc_kv_append(const void* src, int64_t lds, void* cache, int B, int cap, int C, const int32_t* pos_dev, void* stream);
+int vc_greedy_next(const float* logits, int64_t ld, int V, uint8_t* done, int64_t* ids_out, int64_t* seq, int seq_ld,
+                   const int32_t* pos_dev, int64_t eos_id, int64_t pad_id, int B, void* stream);
+int vc_step_advance(int32_t* pos_dev, void* stream);
 
 /* ---- Optimiser tail over the flat parameter buffer (dvc.py:112-126). */
 int vc_sumsq(const float* g, int64_t n, float* out_accum, void* stream);               /* out_accum[0] += |g|^2 */

@@ -96,23 +96,31 @@ class TorchOps:
     def _heads(buf, col, B, L, H):
         return buf[:, col:col + H * 64].float().reshape(B, L, H, 64).permute(0, 2, 1, 3)  # B,H,L,64
 
-    def _scores(self, q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale):
-        qh, kh = self._heads(q, q_col, B, Lq, H), self._heads(k, k_col, B, Lk, H)
+    def _scores(self, q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale, qoff=0, kv_rows=0, bias_zero=None):
+        qh = self._heads(q, q_col, B, Lq, H)
+        kvr = kv_rows or Lk
+        kh = k[:, k_col:k_col + H * 64].float().reshape(B, kvr, H, 64)[:, :Lk].permute(0, 2, 1, 3)
         s = (qh @ kh.transpose(-1, -2)) * scale
+        qpos = torch.arange(Lq, device=s.device)[:, None] + qoff
         if bias_rel is not None:
-            idx = (torch.arange(Lk, device=s.device)[None, :] - torch.arange(Lq, device=s.device)[:, None]) + Lq - 1
+            bz = (Lq - 1) if bias_zero is None else bias_zero
+            idx = (torch.arange(Lk, device=s.device)[None, :] - qpos) + bz
             s = s + bias_rel[:, idx][None]
         masked = torch.zeros(B, 1, Lq, Lk, dtype=torch.bool, device=s.device)
         if kmask is not None:
             masked = masked | (kmask[:, None, None, :] == 0)
         if causal:
-            masked = masked | (torch.arange(Lk, device=s.device)[None, :] > torch.arange(Lq, device=s.device)[:, None])[None, None]
+            masked = masked | (torch.arange(Lk, device=s.device)[None, :] > qpos)[None, None]
         return torch.where(masked, torch.full_like(s, _MASKED), s)
 
     def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
-                 causal=False, scale=1.0, drop=NO_DROP):
-        s = self._scores(q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale)
-        vh = self._heads(v, v_col, B, Lk, H)
+                 causal=False, scale=1.0, drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0,
+                 bias_len=0):
+        qoff = q_offset + (int(q_offset_dev.item()) if q_offset_dev is not None else 0)
+        s = self._scores(q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale, qoff, kv_batch_rows,
+                         bias_zero if bias_len else None)
+        kvr = kv_batch_rows or Lk
+        vh = v[:, v_col:v_col + H * 64].float().reshape(B, kvr, H, 64)[:, :Lk].permute(0, 2, 1, 3)
         dm = drop_mask(drop, _idx(s.shape, s.device)) if drop[1] else 1.0
         if self.flash:
             s2 = s * math.log2(math.e)
@@ -279,6 +287,22 @@ class TorchOps:
 
     def copy_rows_bf16(self, src, dst, B, T, C, E, row_off):
         dst.view(B, E, C)[:, row_off:row_off + T].copy_(src.view(B, T, C))
+
+    # ------------------------------------------------------------------ incremental decoding
+    def kv_append(self, src, cache, pos_dev):
+        cache[:, int(pos_dev.item())].copy_(src)
+
+    def greedy_next(self, logits, done, ids_out, seq, pos_dev, eos_id=1, pad_id=0):
+        nxt = logits.argmax(-1)
+        nxt = torch.where(done.bool(), torch.full_like(nxt, pad_id), nxt)
+        done.copy_((done.bool() | (nxt == eos_id)).to(torch.uint8))
+        ids_out.copy_(nxt)
+        pos = int(pos_dev.item())
+        if pos + 1 < seq.shape[1]:
+            seq[:, pos + 1] = nxt
+
+    def step_advance(self, pos_dev):
+        pos_dev.add_(1)
 
     # ------------------------------------------------------------------ optimiser tail
     def sumsq(self, g, out_accum):

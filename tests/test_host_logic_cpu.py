@@ -203,3 +203,20 @@ def test_dropout_forward_backward_match_replayed_masks(cfg):
     eng._drop_calls -= 1
     loss3, _ = eng.forward(video, inp, inp != 0, out, out != 0, training=True)
     assert loss3.item() == loss2.item()
+
+
+def test_greedy_generate_matches_oracle():
+    """Incremental KV-cache decoding (engine.generate_greedy) vs the uncached greedy restatement of the reference."""
+    cfg = dict(TINY, num_features=10)
+    sd = init_state_dict(cfg, 0)
+    eng = Vid2SeqEngine(cfg, TorchOps(flash_rounding=False), "cpu")
+    for n, t in sd.items():
+        eng.p(n).copy_(t)
+    eng.sync_bf16()
+    video, inp, _ = batch(cfg, B=2, T=10, L=24)
+    memory, mem_mask, B, E = eng.encode(video, inp, inp != 0)
+    seq = eng.generate_greedy(memory, mem_mask, B, E, max_new_tokens=6)
+    o = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, inp[:, :4], inp[:, :4] != 0, emulate_bf16=True)
+    assert rel(memory.float().view(B, E, -1), O._r(o["memory"])) < 2e-3
+    ref = O.greedy_decode(sd, cfg, O._r(o["memory"]), mem_mask.long(), max_new_tokens=6, emulate_bf16=True)
+    assert torch.equal(seq[:, :ref.shape[1]], ref), (seq, ref)

@@ -41,6 +41,28 @@ def test_gemm_layouts(cuda_ops, torch_ops, M, N, K, a_mn, b_mn, tile_n):
         assert rel(out, ref) < tol
 
 
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,tile_n", [
+    (2048, 1024, 512, 0, 0, 256), (2048, 1024, 512, 0, 1, 256), (2048, 1024, 512, 1, 0, 256), (2048, 1024, 512, 1, 1, 256),
+    (1000, 776, 320, 0, 0, 128), (1000, 776, 320, 0, 1, 128), (1000, 776, 320, 1, 1, 128), (16000, 3072, 768, 0, 0, 0),
+    (4096, 32200, 768, 0, 0, 0), (3072, 768, 16000, 1, 1, 0),
+])
+def test_gemm_cta_pair_kernel(cuda_ops, torch_ops, M, N, K, a_mn, b_mn, tile_n):
+    """Shapes / forced tiles that take the 2-CTA (cta_group::2) kernel when VIDCHAP_GEMM_PAIR != 0."""
+    g = gen(M + N + K + 7)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    B = (torch.randn(N, K, generator=g) * 0.5).to(DEV).bfloat16()
+    A_st = A.t().contiguous() if a_mn else A
+    B_st = B.t().contiguous() if b_mn else B
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = torch.zeros(M, N, device=DEV)
+    ref = torch.zeros(M, N, device=DEV)
+    splits = 3 if (a_mn and b_mn) else 1
+    kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), bias=bias, atomic=splits > 1, splits=splits)
+    cuda_ops.gemm(A_st, B_st, out, tile_n=tile_n, **kw)
+    torch_ops.gemm(A_st, B_st, ref, **kw)
+    assert rel(out, ref) < F32_TOL
+
+
 @pytest.mark.parametrize("act", [0, 1, 2, 3, 4])
 def test_gemm_epilogues(cuda_ops, torch_ops, act):
     M, N, K = 520, 2048, 768

@@ -377,6 +377,8 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   VC_CHECK(a != nullptr, "vc_attn_bwd: null args");
   const vc_attn_args* f = &a->fwd;
   VC_CHECK(f->B > 0 && f->H > 0 && f->Lq > 0 && f->Lk > 0 && f->head_dim == 64, "vc_attn_bwd: bad dims");
+  VC_CHECK(f->q_offset == 0 && f->q_offset_dev == nullptr && f->kv_batch_rows == 0 && f->bias_len == 0,
+           "vc_attn_bwd: the incremental-decoding fields are forward-only");
   VC_CHECK(((f->Lq + kBT - 1) / kBT) * kBT + kBT <= kBwdRelMax, "vc_attn_bwd: Lq=%d too long for the d(bias) scratch", f->Lq);
   VC_CHECK(f->lse2 && a->delta && a->dq_acc && a->dk && a->dv && a->dout, "vc_attn_bwd: null buffers");
   VC_CHECK(a->ld_dq % 4 == 0 && a->ld_dk % 8 == 0 && a->ld_dv % 8 == 0 && a->ld_do % 8 == 0, "vc_attn_bwd: strides");

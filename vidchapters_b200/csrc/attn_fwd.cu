@@ -37,6 +37,9 @@ struct AttnFwdParams {
   int causal;
   float scale_log2e;
   uint32_t drop_seed, drop_p16;
+  int q_offset;              // absolute position of query row 0 (incremental decoding), added to *q_offset_dev
+  const int* q_offset_dev;   // optional device scalar (CUDA-graph friendly decode step counter)
+  int bias_zero, bias_len;   // bias row: index of relative position 0, row length
 };
 
 // smem: Q 16K | K 2x16K | V 16K | P 32K | bias window (Lk+128 floats) | key mask (Lk bytes) | barriers.
@@ -72,6 +75,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * kTQ;
+  const int qoff = p.q_offset + (p.q_offset_dev ? __ldg(p.q_offset_dev) : 0);  // queries sit at positions q + qoff
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) __trap();
@@ -88,14 +92,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   // stage this query tile's bias window (index k + 127 - r == (k - q + Lq - 1) - (Lq - 128 - q0)) and the key mask
   {
-    const int win0 = p.Lq - 128 - q0;  // global bias index of window slot 0 (may be negative: clamp, never used)
+    const int win0 = p.bias_zero - 127 - q0 - qoff;  // global bias index of window slot 0 (may be negative: never used)
     // Both arrays are always filled (zeros / ones without bias / mask) and padded to whole tiles so that the
     // softmax loops below are branch-free: conditional loads compiled to one divergence region per element and
     // serialised the whole tile (profiles/r01_attn_notes.md).
-    const float* brow = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) : nullptr;
+    const float* brow = p.bias_rel ? p.bias_rel + (long long)h * p.bias_len : nullptr;
     for (int i = threadIdx.x; i < lk_pad + 128; i += blockDim.x) {
       const int gi = win0 + i;
-      sBias[i] = (brow && gi >= 0 && gi < p.Lq + p.Lk - 1) ? __ldg(brow + gi) * kLog2e : 0.f;
+      sBias[i] = (brow && gi >= 0 && gi < p.bias_len) ? __ldg(brow + gi) * kLog2e : 0.f;
     }
     const uint8_t* mrow = p.kmask ? p.kmask + (long long)b * p.Lk : nullptr;
     for (int i = threadIdx.x; i < lk_pad; i += blockDim.x)
@@ -111,7 +115,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   // number of key tiles this query tile visits (causal: skip tiles entirely above the diagonal)
   int nkt = (p.Lk + kTK - 1) / kTK;
-  if (p.causal) nkt = min(nkt, (q0 + kTQ - 1) / kTK + 1);
+  if (p.causal) nkt = min(nkt, (q0 + qoff + kTQ - 1) / kTK + 1);
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -159,7 +163,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ===================== softmax / epilogue =====================
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // row in tile == TMEM lane
-    const int q = q0 + r;
+    const int q = q0 + r;            // row inside this call's query block (output / lse index)
+    const int q_abs = q + qoff;      // its sequence position (bias window, causal mask)
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float* brow = sBias + (127 - r);  // brow[k] = bias(k - q) * log2e
     float m_run = -INFINITY, l_run = 0.0f;
@@ -172,7 +177,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       // ---- pass 1: row max of s2 over the tile.  s2 = min(acc*scale*log2e + bias*log2e, pen[k]); causal tiles add k<=q.
-      const bool causal_tile = p.causal && (k0 + kTK - 1 > q0);   // uniform: only tiles touching the diagonal
+      const bool causal_tile = p.causal && (k0 + kTK - 1 > q0 + qoff);   // uniform: only tiles touching the diagonal
       float m_tile = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -180,7 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(tmem_S + lane_off + c * 32, v);
         const float4* pen4 = reinterpret_cast<const float4*>(sPen + k0 + c * 32);
         const float* bk = brow + k0 + c * 32;
-        const int tq = q - k0 - c * 32;  // column i is causally masked iff i > tq
+        const int tq = q_abs - k0 - c * 32;  // column i is causally masked iff i > tq
         tmem_ld_wait();
         if (causal_tile) {
 #pragma unroll
@@ -217,7 +222,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(tmem_S + lane_off + c * 32, v);
         const float4* pen4 = reinterpret_cast<const float4*>(sPen + k0 + c * 32);
         const float* bk = brow + k0 + c * 32;
-        const int tq = q - k0 - c * 32;
+        const int tq = q_abs - k0 - c * 32;
         tmem_ld_wait();
         // the normaliser l uses the un-dropped probabilities (dropout acts on softmax's output)
         if (causal_tile) {
@@ -316,9 +321,11 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tmQ, tmK, tmV;
   int s;
+  const uint64_t kv_rows = a->kv_batch_rows > 0 ? a->kv_batch_rows : a->Lk;  // rows between batches of K/V in memory
+  VC_CHECK(kv_rows >= (uint64_t)a->Lk, "vc_attn_fwd: kv_batch_rows < Lk");
   if ((s = make_tmap_3d(&tmQ, a->q, a->ldq, a->Lq, a->B, a->ldq, (uint64_t)a->Lq * a->ldq, 64, kTQ)) != VC_OK) return s;
-  if ((s = make_tmap_3d(&tmK, a->k, a->ldk, a->Lk, a->B, a->ldk, (uint64_t)a->Lk * a->ldk, 64, kTK)) != VC_OK) return s;
-  if ((s = make_tmap_3d(&tmV, a->v, a->ldv, a->Lk, a->B, a->ldv, (uint64_t)a->Lk * a->ldv, 64, kTK)) != VC_OK) return s;
+  if ((s = make_tmap_3d(&tmK, a->k, a->ldk, a->Lk, a->B, a->ldk, kv_rows * a->ldk, 64, kTK)) != VC_OK) return s;
+  if ((s = make_tmap_3d(&tmV, a->v, a->ldv, a->Lk, a->B, a->ldv, kv_rows * a->ldv, 64, kTK)) != VC_OK) return s;
   AttnFwdParams p;
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
   p.q_col = a->q_col; p.k_col = a->k_col; p.v_col = a->v_col;
@@ -326,6 +333,9 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   p.lse2 = a->lse2; p.bias_rel = a->bias_rel; p.kmask = a->kmask; p.causal = a->causal;
   p.scale_log2e = a->scale * kLog2e;
   p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16;
+  p.q_offset = a->q_offset; p.q_offset_dev = a->q_offset_dev;
+  p.bias_zero = a->bias_len > 0 ? a->bias_zero : a->Lq - 1;
+  p.bias_len = a->bias_len > 0 ? a->bias_len : a->Lq + a->Lk - 1;
   VC_CHECK(a->Lk <= kAttnMaxLk, "vc_attn_fwd: Lk=%d exceeds the %d keys the bias/mask staging supports", a->Lk, kAttnMaxLk);
   const int lk_pad = ((a->Lk + kTK - 1) / kTK) * kTK;
   const int smem_bytes = kAttnFwdTiles + (lk_pad + 128) * 4 + lk_pad * 4 + 128;

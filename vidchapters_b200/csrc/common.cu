@@ -86,7 +86,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1
 
 }  // namespace vc
 
-extern "C" int vc_version(void) { return 2; }
+extern "C" int vc_version(void) { return 3; }
 extern "C" const char* vc_last_error(void) { return vc::g_err; }
 extern "C" int vc_device_check(void) {
   int dev = 0;

@@ -1,0 +1,181 @@
+// Shared pieces of the tcgen05 GEMM kernels (1-CTA gemm.cu, 2-CTA gemm2.cu): parameters and the fused epilogue.
+#pragma once
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+struct GemmParams {
+  int M, N, K;
+  int m_blocks, n_blocks, splits, kb_per_split, num_kb;
+  // epilogue
+  void* out;             // bf16 or fp32 [M][ldo]
+  long long ldo;
+  int out_fp32;
+  int atomic;            // fp32 out: atomicAdd instead of store
+  const float* bias;     // [N] or null
+  const float* residual; // fp32 [M][ldr] or null  (may alias out)
+  long long ldr;
+  int act;               // 0 none, 1 relu, 2 gelu(erf), 3 mul relu'(aux), 4 mul gelu'(aux)
+  __nv_bfloat16* pre_out;  // bf16 [M][ldo] pre-activation copy (act=2) or null
+  const __nv_bfloat16* aux;  // bf16 [M][ld_aux] for act 3/4
+  long long ld_aux;
+  float alpha;
+  const float* alpha_dev;  // optional device scalar multiplied into alpha
+  uint32_t drop_seed, drop_p16;  // dropout applied after the activation, before the residual add (p16 = 0: off)
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// One 32-column chunk of one accumulator row: TMEM -> registers -> fused epilogue -> global.
+// Epilogue order: *alpha, +bias, (pre_out copy), activation / activation-backward, dropout, +residual, store.
+// Side inputs (residual, aux) are requested BEFORE waiting for the TMEM load so their latency overlaps it.
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_t taddr, int row, bool row_ok, int col0,
+                                                    float alpha) {
+          float v[32];
+          tmem_ld32(taddr, v);
+          const int ncols = min(32, p.N - col0);
+          const bool full = row_ok && ncols == 32;  // fast path: whole 32-column chunk in range
+          float4 rs[8];
+          uint4 ax[4];
+          if (full) {
+            if (p.residual) {
+              const float4* rp = reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + col0);
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) rs[j] = rp[j];
+            }
+            if (p.act >= 3) {
+              const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ld_aux + col0);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) ax[j] = __ldg(ap + j);
+            }
+          }
+          tmem_ld_wait();
+          if (!row_ok || ncols <= 0) return;
+  #pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= alpha;
+          if (p.bias) {
+            if (full) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(bp + j);
+                v[j * 4] += b4.x; v[j * 4 + 1] += b4.y; v[j * 4 + 2] += b4.z; v[j * 4 + 3] += b4.w;
+              }
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+            }
+          }
+          if (p.act == 2 && p.pre_out) {
+            __nv_bfloat16* dstp = p.pre_out + (long long)row * p.ldo + col0;
+            if (full) {
+              uint4* dst = reinterpret_cast<uint4*>(dstp);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                    pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) dstp[j] = __float2bfloat16(v[j]);
+            }
+          }
+          if (p.act == 1) {
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else if (p.act == 2) {
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act >= 3) {
+            if (!full) {  // ragged tail: gather the aux values element-wise
+              const __nv_bfloat16* axp = p.aux + (long long)row * p.ld_aux + col0;
+              uint32_t w[16];
+  #pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float lo = e * 2 < ncols ? __bfloat162float(axp[e * 2]) : 0.f;
+                const float hi = e * 2 + 1 < ncols ? __bfloat162float(axp[e * 2 + 1]) : 0.f;
+                w[e] = pack_bf16x2(lo, hi);
+              }
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) ax[j] = make_uint4(w[j * 4], w[j * 4 + 1], w[j * 4 + 2], w[j * 4 + 3]);
+            }
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {ax[j].x, ax[j].y, ax[j].z, ax[j].w};
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+                if (p.act == 3) {
+                  v[j * 8 + e * 2] = lo > 0.0f ? v[j * 8 + e * 2] : 0.0f;
+                  v[j * 8 + e * 2 + 1] = hi > 0.0f ? v[j * 8 + e * 2 + 1] : 0.0f;
+                } else {
+                  v[j * 8 + e * 2] *= gelu_erf_grad(lo);
+                  v[j * 8 + e * 2 + 1] *= gelu_erf_grad(hi);
+                }
+              }
+            }
+          }
+          if (p.drop_p16) {
+            const float sc = drop_scale(p.drop_p16);
+            const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + col0;
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = drop_keep(p.drop_seed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
+          }
+          if (p.residual) {
+            if (full) {
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[j * 4 + 0] += rs[j].x; v[j * 4 + 1] += rs[j].y; v[j * 4 + 2] += rs[j].z; v[j * 4 + 3] += rs[j].w;
+              }
+            } else {
+              const float* rsp = p.residual + (long long)row * p.ldr + col0;
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += rsp[j];
+            }
+          }
+          if (p.out_fp32) {
+            float* dstf = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
+            if (full) {
+              float4* dst = reinterpret_cast<float4*>(dstf);
+              if (p.atomic) {
+  #pragma unroll
+                for (int j = 0; j < 8; ++j) atomicAdd(dst + j, make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]));
+              } else {
+  #pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+              }
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < ncols) {
+                  if (p.atomic) atomicAdd(dstf + j, v[j]); else dstf[j] = v[j];
+                }
+              }
+            }
+          } else {
+            __nv_bfloat16* dstb = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
+            if (full) {
+              uint4* dst = reinterpret_cast<uint4*>(dstb);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                    pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) dstb[j] = __float2bfloat16(v[j]);
+            }
+          }
+}
+
+}  // namespace vc

@@ -577,6 +577,143 @@ class Vid2SeqEngine:
         assert i == 0, i
         return dvideo_out
 
+    # ------------------------------------------------------------------ inference: encode + greedy decode
+    @torch.no_grad()
+    def encode(self, video, input_ids, input_mask):
+        """Visual encoder + text encoder -> (memory bf16 [B*E, d], mem_mask u8 [B, E], B, E) as in the first half of
+        Vid2Seq.generate (model/vid2seq.py:129-148).  Reuses the training forward's sub-layers with dropout off."""
+        ops, cfg, d = self.ops, self.cfg, self.d
+        bf = torch.bfloat16
+        self._begin_dropout(False)
+        tape: List[dict] = []
+        B = video.shape[0] if self.use_video else input_ids.shape[0]
+        T = video.shape[1] if self.use_video else 0
+        L = input_ids.shape[1] if self.use_speech else 0
+        E = T + L
+        memory = self._e(B * E, d, dtype=bf)
+        parts = []
+        if self.use_video:
+            C = self.C
+            xv = self._e(B * T, C)
+            ops.add_pos(video.contiguous().float(), self.p("visual_encoder.pos_embed"), xv.view(B, T, C), cfg["num_features"])
+            for sa, ff in self.vit_blocks:
+                xv = self._sa_fwd(xv, sa, B, T, None, None, False, tape, dk="vis")
+                xv = self._ff_fwd(xv, ff, tape, dk="vis")
+            if d == 768 and C == 768:
+                ops.norm_fwd(1, xv, self.pv("visual_encoder.norm.weight"), self.pv("visual_encoder.norm.bias"),
+                             out_bf16=memory, eps=1e-5, rows_per_batch=T, out_batch_stride=E, out_row_offset=0)
+            else:
+                vn = self._e(B * T, C, dtype=bf)
+                ops.norm_fwd(1, xv, self.pv("visual_encoder.norm.weight"), self.pv("visual_encoder.norm.bias"),
+                             out_bf16=vn, eps=1e-5)
+                tmp = self._e(B * T, d, dtype=bf)
+                ops.gemm(vn, self.pb("proj_v2t.weight"), tmp, bias=self.pv("proj_v2t.bias"))
+                ops.copy_rows_bf16(tmp, memory, B, T, d, E, 0)
+            parts.append(torch.ones(B, T, dtype=torch.uint8, device=self.device))
+        if self.use_speech:
+            x = self._e(B * L, d)
+            ops.embed_fwd(input_ids.contiguous(), self.p("t5_model.shared.weight"), x)
+            bias_e = self._e(self.H, 2 * L - 1)
+            ops.bias_expand(self.p(self.enc_bias_name), self.lut(L, L, True), bias_e)
+            kmask_e = self._mask_u8(input_mask)
+            for sa, ff in self.enc_blocks:
+                x = self._sa_fwd(x, sa, B, L, bias_e, kmask_e, False, tape, dk="enc")
+                x = self._ff_fwd(x, ff, tape, dk="enc")
+            ops.norm_fwd(0, x, self.pv("t5_model.encoder.final_layer_norm.weight"), None, out_bf16=memory, eps=1e-6,
+                         rows_per_batch=L, out_batch_stride=E, out_row_offset=T)
+            parts.append(kmask_e)
+        tape.clear()
+        return memory, torch.cat(parts, dim=1).contiguous(), B, E
+
+    @torch.no_grad()
+    def generate_greedy(self, memory, mem_mask, B, E, max_new_tokens=256, use_graph=None, check_every=16):
+        """Greedy decoding with a KV cache (HF-4.28 greedy semantics: start id 0, argmax, sequences that emitted eos=1
+        continue with pad=0, stop when all are done or after max_new_tokens).  Returns int64 [B, 1 + n] ids including
+        the start token, like `t5_model.generate` (model/vid2seq.py:150-162 with num_beams=1).
+        One decode step = a fixed launch sequence driven by a DEVICE step counter -> captured once as a CUDA graph."""
+        ops, d, H, inner = self.ops, self.d, self.H, self.inner
+        bf, dev = torch.bfloat16, self.device
+        S = int(max_new_tokens)
+        nl = len(self.dec_blocks)
+        if use_graph is None:
+            use_graph = dev.type == "cuda" and getattr(ops, "name", "") == "cuda"
+        # cross-attention K/V of every layer once (modeling_t5.py:516-524), self-attention caches
+        kvmem = []
+        for sa, ca, ff in self.dec_blocks:
+            kv = self._e(B * E, 2 * inner, dtype=bf)
+            ops.gemm(memory, self.pb(ca.kv_w, 2 * inner), kv)
+            kvmem.append(kv)
+        caches = [torch.zeros(B, S, 2 * inner, dtype=bf, device=dev) for _ in range(nl)]
+        bias_d = self._e(H, 2 * S - 1)
+        ops.bias_expand(self.p(self.dec_bias_name), self.lut(S, S, False), bias_d)
+        pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        ids = torch.zeros(B, dtype=torch.int64, device=dev)            # decoder_start_token_id = 0
+        seq = torch.zeros(B, S + 1, dtype=torch.int64, device=dev)
+        done = torch.zeros(B, dtype=torch.uint8, device=dev)
+        Vp = (self.V + 7) // 8 * 8
+        x = self._e(B, d)
+        h = self._e(B, d, dtype=bf)
+        q = self._e(B, inner, dtype=bf)
+        kvn = self._e(B, 2 * inner, dtype=bf)
+        ctxb = self._e(B, inner, dtype=bf)
+        act = self._e(B, self.dff, dtype=bf)
+        logits = self._e(B, Vp)[:, :self.V]
+
+        def step():
+            ops.embed_fwd(ids, self.p("t5_model.shared.weight"), x)
+            for li, (sa, ca, ff) in enumerate(self.dec_blocks):
+                ops.norm_fwd(0, x, self.pv(sa.norm_w), None, out_bf16=h, eps=1e-6)
+                ops.gemm(h, self.pb(sa.qkv_w), q)                                   # q rows of the fused [q;k;v]
+                k_name = sa.qkv_w.replace(".q.weight", ".k.weight")
+                ops.gemm(h, self.pb(k_name, 2 * inner), kvn)                         # adjacent k,v weights
+                ops.kv_append(kvn, caches[li], pos)
+                c2 = caches[li].view(B * S, 2 * inner)
+                ops.attn_fwd(q, c2, c2, q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=1, Lk=S, out=ctxb, lse2=None,
+                             bias_rel=bias_d, kmask=None, causal=True, scale=1.0, q_offset_dev=pos, kv_batch_rows=S,
+                             bias_zero=S - 1, bias_len=2 * S - 1)
+                ops.gemm(ctxb, self.pb(sa.o_w), x, residual=x)
+                ops.norm_fwd(0, x, self.pv(ca.norm_w), None, out_bf16=h, eps=1e-6)
+                ops.gemm(h, self.pb(ca.q_w), q)
+                ops.attn_fwd(q, kvmem[li], kvmem[li], q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=1, Lk=E, out=ctxb,
+                             lse2=None, bias_rel=None, kmask=mem_mask, causal=False, scale=1.0)
+                ops.gemm(ctxb, self.pb(ca.o_w), x, residual=x)
+                ops.norm_fwd(0, x, self.pv(ff.norm_w), None, out_bf16=h, eps=1e-6)
+                ops.gemm(h, self.pb(ff.w1), act, act=ACT_RELU)
+                ops.gemm(act, self.pb(ff.w2), x, residual=x)
+            ops.norm_fwd(0, x, self.pv("t5_model.decoder.final_layer_norm.weight"), None, out_bf16=h, eps=1e-6,
+                         out_scale=d ** -0.5)
+            ops.gemm(h, self.pb("t5_model.shared.weight"), logits)
+            ops.greedy_next(logits, done, ids, seq, pos, 1, 0)
+            ops.step_advance(pos)
+
+        graph = None
+        if use_graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step()                                  # warm-up (attribute setup, LUT uploads) ...
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            pos.zero_(); ids.zero_(); seq.zero_(); done.zero_()   # ... then rewind the state
+            for c in caches:
+                c.zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            n = 1
+        else:
+            step()
+            n = 1
+        while n < S:
+            if n % check_every == 0 and bool(done.all().item()):
+                break
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+            n += 1
+        return seq[:, :n + 1].clone()
+
     # ------------------------------------------------------------------ optimiser tail (dvc.py:114-126)
     def zero_grad(self):
         self.flat_g.zero_()

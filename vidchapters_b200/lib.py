@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvidchap.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class GemmArgs(C.Structure):
@@ -46,6 +46,8 @@ class AttnArgs(C.Structure):
         ("causal", C.c_int32),
         ("scale", C.c_float),
         ("drop_seed", C.c_uint32), ("drop_p16", C.c_uint32),
+        ("q_offset", C.c_int32), ("q_offset_dev", C.c_void_p), ("kv_batch_rows", C.c_int32),
+        ("bias_zero", C.c_int32), ("bias_len", C.c_int32),
     ]
 
 
@@ -84,6 +86,9 @@ SIGNATURES = {
     "vc_adam_step": [P, P, P, P, P, I64, F, F, F, F, I, P, F, F, P],
     "vc_renorm_time_tokens": [P, P, I, I, I, P, P],
     "vc_cast_flat_bf16": [P, P, I64, P],
+    "vc_kv_append": [P, I64, P, I, I, I, P, P],
+    "vc_greedy_next": [P, I64, I, P, P, P, I, P, I64, I64, I, P],
+    "vc_step_advance": [P, P],
     "vc_version": [],
     "vc_last_error": [],
     "vc_device_check": [],

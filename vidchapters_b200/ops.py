@@ -89,15 +89,17 @@ class CudaOps:
 
     # ------------------------------------------------------------------ attention
     def _attn_args(self, q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale,
-                   drop=NO_DROP):
+                   drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0, bias_len=0):
         _chk_cuda(q, k, v, out, lse2, bias_rel, kmask)
         for t in (q, k, v, out):
             assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
-        assert q.shape[0] == B * Lq and k.shape[0] == B * Lk and v.shape[0] == B * Lk and out.shape[0] == B * Lq
+        kvr = kv_batch_rows or Lk
+        assert q.shape[0] == B * Lq and k.shape[0] == B * kvr and v.shape[0] == B * kvr and out.shape[0] == B * Lq
         if kmask is not None:
             assert kmask.dtype == torch.uint8 and kmask.shape == (B, Lk) and kmask.is_contiguous()
         if bias_rel is not None:
-            assert bias_rel.dtype == torch.float32 and bias_rel.shape == (H, Lq + Lk - 1) and bias_rel.is_contiguous()
+            assert bias_rel.dtype == torch.float32 and bias_rel.is_contiguous()
+            assert bias_rel.shape == (H, bias_len or (Lq + Lk - 1))
         a = _lib.AttnArgs()
         a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
         a.ldq, a.ldk, a.ldv = q.stride(0), k.stride(0), v.stride(0)
@@ -110,11 +112,15 @@ class CudaOps:
         a.causal = int(causal)
         a.scale = float(scale)
         a.drop_seed, a.drop_p16 = drop
+        a.q_offset, a.kv_batch_rows, a.bias_zero, a.bias_len = q_offset, kv_batch_rows, bias_zero, bias_len
+        a.q_offset_dev = None if q_offset_dev is None else q_offset_dev.data_ptr()
         return a
 
     def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
-                 causal=False, scale=1.0, drop=NO_DROP):
-        a = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale, drop)
+                 causal=False, scale=1.0, drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0,
+                 bias_len=0):
+        a = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale, drop,
+                            q_offset, q_offset_dev, kv_batch_rows, bias_zero, bias_len)
         _lib.check(self.lib.vc_attn_fwd(C.byref(a), self._stream()))
         self.launches += 1
 
@@ -233,6 +239,29 @@ class CudaOps:
     def copy_rows_bf16(self, src, dst, B, T, Cc, E, row_off):
         _chk_cuda(src, dst)
         _lib.check(self.lib.vc_copy_rows_bf16(_ptr(src), _ptr(dst), B, T, Cc, E, row_off, self._stream()))
+        self.launches += 1
+
+    # ------------------------------------------------------------------ incremental decoding
+    def kv_append(self, src, cache, pos_dev):
+        """cache[b, *pos_dev, :] = src[b, :]; src [B, C] bf16 (any row stride), cache [B, cap, C]."""
+        _chk_cuda(src, cache, pos_dev)
+        B, cap, Cc = cache.shape
+        assert src.shape == (B, Cc) and src.stride(1) == 1 and cache.is_contiguous() and pos_dev.dtype == torch.int32
+        _lib.check(self.lib.vc_kv_append(_ptr(src), src.stride(0), _ptr(cache), B, cap, Cc, _ptr(pos_dev), self._stream()))
+        self.launches += 1
+
+    def greedy_next(self, logits, done, ids_out, seq, pos_dev, eos_id=1, pad_id=0):
+        _chk_cuda(logits, done, ids_out, seq, pos_dev)
+        B, V = logits.shape
+        assert logits.dtype == torch.float32 and logits.stride(1) == 1 and done.dtype == torch.uint8
+        assert ids_out.dtype == torch.int64 and seq.dtype == torch.int64 and seq.is_contiguous()
+        _lib.check(self.lib.vc_greedy_next(_ptr(logits), logits.stride(0), V, _ptr(done), _ptr(ids_out), _ptr(seq),
+                                           seq.shape[1], _ptr(pos_dev), eos_id, pad_id, B, self._stream()))
+        self.launches += 1
+
+    def step_advance(self, pos_dev):
+        _chk_cuda(pos_dev)
+        _lib.check(self.lib.vc_step_advance(_ptr(pos_dev), self._stream()))
         self.launches += 1
 
     # ------------------------------------------------------------------ optimiser tail

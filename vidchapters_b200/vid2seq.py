@@ -221,7 +221,20 @@ class Vid2Seq(nn.Module):
     @torch.no_grad()
     def generate(self, video, input_tokenized, use_nucleus_sampling=False, num_beams=4, max_length=256, min_length=1,
                  top_p=0.9, repetition_penalty=1.0, length_penalty=1.0, num_captions=1, temperature=1):
-        raise NotImplementedError("generate(): decoding is SURVEY §8(f) N1 (next after the train step); not built yet")
+        """Greedy decoding (num_beams=1, no sampling) runs on the B200 path with a KV cache and a CUDA-graphed step.
+        Beam search / nucleus sampling (HF-4.28 `generate`, third-party code the reference delegates to) are not
+        built yet and raise."""
+        if use_nucleus_sampling or num_beams != 1 or num_captions != 1 or repetition_penalty != 1.0:
+            raise NotImplementedError("vidchapters_b200.Vid2Seq.generate implements greedy decoding only "
+                                      "(num_beams=1, use_nucleus_sampling=False); beam search is SURVEY §8(f) N1")
+        self._refresh_shadow()
+        eng = self.engine
+        ids = input_tokenized["input_ids"] if self.use_speech else None
+        mask = input_tokenized["attention_mask"] if self.use_speech else None
+        memory, mem_mask, B, E = eng.encode(video, ids, mask)
+        seq = eng.generate_greedy(memory, mem_mask, B, E, max_new_tokens=max_length)
+        self.last_generated_ids = seq
+        return self.t5_tokenizer.batch_decode(seq, skip_special_tokens=True)
 
 
 def build_vid2seq_model(args, tokenizer):
