@@ -80,7 +80,7 @@ int vc_attn_fwd(const vc_attn_args* args, void* stream);
 
 /* ---- Fused attention backward (autograd of the block above).  `fwd` repeats the forward arguments (fwd.out = O and
  * fwd.lse2 as saved by the forward).  dout: bf16 dL/dO [B*Lq, ld_do], head h at cols do_col + 64h.  delta: scratch
- * [B,H,Lq].  dq_acc: ZEROED fp32 [B*Lq, ld_dq] accumulated with atomics (head h at cols 64h).  dk/dv: bf16
+ * [B,H,Lq].  dq_acc: fp32 [B*Lq, ld_dq], cleared by the call then accumulated with atomics (head h at cols 64h).  dk/dv: bf16
  * [B*Lk, ld], head h at cols d*_col + 64h (fully written).  dbias_rel: fp32 [H, Lq+Lk-1] accumulated with atomics
  * (NULL when the bias is not a parameter); bucket_lut [Lq+Lk-1] lets tiles inside one bucket take a fast path. */
 typedef struct vc_attn_bwd_args {

@@ -152,7 +152,7 @@ class TorchOps:
         dvh = pb.transpose(-1, -2) @ do
         dkh = dsb.transpose(-1, -2) @ qh
         dqh = dsb @ kh
-        dq_acc[:, :H * 64].add_(dqh.permute(0, 2, 1, 3).reshape(B * Lq, H * 64))
+        dq_acc[:, :H * 64].copy_(dqh.permute(0, 2, 1, 3).reshape(B * Lq, H * 64))
         dk[:, dk_col:dk_col + H * 64].copy_(dkh.permute(0, 2, 1, 3).reshape(B * Lk, H * 64).to(dk.dtype))
         dv[:, dv_col:dv_col + H * 64].copy_(dvh.permute(0, 2, 1, 3).reshape(B * Lk, H * 64).to(dv.dtype))
         if dbias_rel is not None:

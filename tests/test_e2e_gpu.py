@@ -187,3 +187,31 @@ def test_dropout_training_step_cuda_vs_torch_ops():
     m.train(); l_tr = m(video, it, ot)[0]["loss"].item()
     m.eval(); l_ev = m(video, it, ot)[0]["loss"].item()
     assert abs(l_tr - l_ev) > 1e-3 and abs(l_ev - fx["loss"].item()) < 2e-3 * abs(l_ev)
+
+
+def test_greedy_generate_cuda_matches_oracle():
+    """Vid2Seq.generate (num_beams=1): KV-cache decode with the CUDA-graphed step vs the uncached oracle greedy loop."""
+    from oracle import vid2seq_oracle as O
+    fx = torch.load(os.path.join(GOLD, "tiny.pt"), weights_only=False)
+    cfg = fx["cfg"]
+    m = build(cfg)
+    m.eval()
+
+    class TokD(Tok):
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return [" ".join(str(int(t)) for t in row if not (skip_special_tokens and int(t) in (0, 1))) for row in ids]
+
+    m.t5_tokenizer = TokD(cfg["base_vocab"] + cfg["num_bins"])
+    video, inp = fx["video"].cuda(), fx["input_ids"].cuda()
+    texts = m.generate(video, {"input_ids": inp, "attention_mask": inp != 0}, num_beams=1, max_length=12)
+    seq = m.last_generated_ids
+    assert len(texts) == video.shape[0] and seq.shape[1] <= 13 and bool((seq[:, 0] == 0).all())
+    sd = {k: v.detach() for k, v in m._params.items()}
+    memory, mem_mask, B, E = m.engine.encode(video, inp, inp != 0)
+    ref = O.greedy_decode(sd, cfg, memory.float().view(B, E, -1), mem_mask.long(), max_new_tokens=12, emulate_bf16=True)
+    n = min(seq.shape[1], ref.shape[1])
+    agree = (seq[:, :n] == ref[:, :n]).float().mean().item()
+    print(f"[generate] greedy ids agreement with the oracle: {agree:.3f}  ids[0]={seq[0].tolist()}")
+    assert agree == 1.0
+    with pytest.raises(NotImplementedError):
+        m.generate(video, {"input_ids": inp, "attention_mask": inp != 0}, num_beams=4)

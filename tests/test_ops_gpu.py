@@ -56,8 +56,8 @@ def test_gemm_cta_pair_kernel(cuda_ops, torch_ops, M, N, K, a_mn, b_mn, tile_n):
     bias = torch.randn(N, generator=g).to(DEV)
     out = torch.zeros(M, N, device=DEV)
     ref = torch.zeros(M, N, device=DEV)
-    splits = 3 if (a_mn and b_mn) else 1
-    kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), bias=bias, atomic=splits > 1, splits=splits)
+    splits = 3 if (a_mn and b_mn) else 1   # wgrad-style: split-K with fp32 atomics (no bias: every split would add it)
+    kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), bias=None if splits > 1 else bias, atomic=splits > 1, splits=splits)
     cuda_ops.gemm(A_st, B_st, out, tile_n=tile_n, **kw)
     torch_ops.gemm(A_st, B_st, ref, **kw)
     assert rel(out, ref) < F32_TOL

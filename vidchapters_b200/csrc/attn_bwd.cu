@@ -344,12 +344,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (the "D" term of the softmax backward)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout, long long lddo,
-                  int do_col, float* __restrict__ delta, int B, int H, int Lq) {
+                  int do_col, float* __restrict__ delta, float* __restrict__ dq_acc, long long ld_dq, int B, int H, int Lq) {
   // one warp per (row, 4 heads at a time): lane handles 8 consecutive elements of a 256-wide slab
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)B * Lq) return;
   const int b = (int)(row / Lq), q = (int)(row % Lq);
+  // also clears this row of the fp32 dQ accumulator the main kernel adds into (saves a separate fill launch)
+  for (int c = lane * 4; c < H * 64; c += 128) *reinterpret_cast<float4*>(dq_acc + row * ld_dq + c) = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int h0 = 0; h0 < H; h0 += 4) {
     const int col = h0 * 64 + lane * 8;
     float s = 0.f;
@@ -388,7 +390,7 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
     const long long rows = (long long)f->B * f->Lq;
     attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)f->out, f->ldo,
                                                                  (const __nv_bfloat16*)a->dout, a->ld_do, a->do_col,
-                                                                 a->delta, f->B, f->H, f->Lq);
+                                                                 a->delta, a->dq_acc, a->ld_dq, f->B, f->H, f->Lq);
     VC_CUDA(cudaGetLastError());
   }
   CUtensorMap tmQ, tmK, tmV, tmDO;

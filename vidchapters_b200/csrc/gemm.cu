@@ -237,6 +237,8 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   VC_CHECK(p.splits == 1 || a->atomic, "vc_gemm_bf16: split-K needs atomic fp32 accumulate");
+  VC_CHECK(p.splits == 1 || (!a->bias && !a->residual && a->act == 0 && a->drop_p16 == 0),
+           "vc_gemm_bf16: split-K supports the plain alpha*A.B accumulate epilogue only");
   p.out = a->out; p.ldo = a->ldo; p.out_fp32 = a->out_fp32; p.atomic = a->atomic;
   p.bias = a->bias; p.residual = a->residual; p.ldr = a->ldr; p.act = a->act;
   p.pre_out = reinterpret_cast<__nv_bfloat16*>(a->pre_out);

@@ -317,8 +317,7 @@ class Vid2SeqEngine:
         dctx = ws["dctx"][:M * inner].view(M, inner)
         ops.gemm(dxb, self.pb(sp.o_w), dctx, b_mn=True)
         dqkv = ws["dqkv"][:M * 3 * inner].view(M, 3 * inner)
-        dq_acc = ws["dq_acc"][:M * inner].view(M, inner)
-        dq_acc.zero_()
+        dq_acc = ws["dq_acc"][:M * inner].view(M, inner)   # cleared inside attn_bwd
         delta = ws["delta"][:B * H * L].view(B, H, L)
         qkv = r["qkv"]
         ops.attn_bwd(qkv, qkv, qkv, q_col=0, k_col=inner, v_col=2 * inner, B=B, H=H, Lq=L, Lk=L, out=r["ctx"],
@@ -342,8 +341,7 @@ class Vid2SeqEngine:
         self._wgrad(dxb, r["ctx"], sp.o_w)
         dctx = ws["dctx"][:M * inner].view(M, inner)
         ops.gemm(dxb, self.pb(sp.o_w), dctx, b_mn=True)
-        dq_acc = ws["dq_acc"][:M * inner].view(M, inner)
-        dq_acc.zero_()
+        dq_acc = ws["dq_acc"][:M * inner].view(M, inner)   # cleared inside attn_bwd
         dq = ws["dqkv"][:M * inner].view(M, inner)
         dkv = ws["dkv"][:B * E * 2 * inner].view(B * E, 2 * inner)
         delta = ws["delta"][:B * H * S].view(B, H, S)

@@ -127,7 +127,7 @@ class CudaOps:
     def attn_bwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, dout, do_col=0, delta, dq_acc, dk, dk_col, dv, dv_col, dbias_rel=None,
                  bucket_lut=None, drop=NO_DROP):
-        """dq_acc must be zeroed by the caller (fp32 atomics); dk/dv are fully written; dbias_rel accumulates."""
+        """dq_acc is cleared then accumulated (fp32 atomics); dk/dv are fully written; dbias_rel accumulates."""
         _chk_cuda(dout, delta, dq_acc, dk, dv, dbias_rel, bucket_lut)
         b = _lib.AttnBwdArgs()
         b.fwd = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale,
