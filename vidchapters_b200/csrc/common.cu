@@ -76,6 +76,32 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ou
   return encode(out, base, 2, dims, strides, box);
 }
 
+int make_tmap_2d_ex(CUtensorMap* out, const void* base, int elt_bytes, uint64_t inner, uint64_t outer,
+                    uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return VC_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_elems * (uint64_t)elt_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, elt_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(ex) failed (%d): elt %d dims %llu,%llu stride %llu box %u,%u swz %d base %p", (int)r,
+              elt_bytes, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)strides[0], box_inner,
+              box_outer, swizzle_bytes, base);
+    return VC_ERR_CUDA;
+  }
+  return VC_OK;
+}
+
 int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2, uint64_t s1_elems,
                  uint64_t s2_elems, uint32_t box_inner, uint32_t box_d1) {
   cuuint64_t dims[3] = {inner, d1, d2};

@@ -33,6 +33,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ou
 int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1, uint64_t d2, uint64_t s1_elems,
                  uint64_t s2_elems, uint32_t box_inner, uint32_t box_d1);
 
+// General 2-D map: elt_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 0/32/64/128.
+int make_tmap_2d_ex(CUtensorMap* out, const void* base, int elt_bytes, uint64_t inner, uint64_t outer,
+                    uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+
 int num_sms();
 
 }  // namespace vc

@@ -16,6 +16,7 @@
 //                   alpha, bf16 or fp32 store, or fp32 atomic accumulate (split-K for wgrad).
 // The accumulator is double-buffered in TMEM so tile i's epilogue overlaps tile i+1's MMAs.
 #include <stdlib.h>
+#include <string.h>
 
 #include "gemm_common.cuh"
 
@@ -25,13 +26,14 @@ template <int BN>
 struct GemmCfg {
   static constexpr int kStageBytes = (BM + BN) * BK * 2;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;  // 512 / 256 / 128
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool TMA_EPI>
 __global__ void __launch_bounds__(384, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ EpiMaps em, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kABytes = BM * BK * 2;
@@ -41,11 +43,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;   // 8 x 4 KB staging tiles of the TMA epilogue
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiWarps * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* epi_bar = tmem_empty + 2;   // [8] one per epilogue warp (residual tile landed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -63,6 +67,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 256);
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -147,7 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - 4) >> 2;
     constexpr int kChunks = BN / 64;  // 32-column chunks per warp
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, epi_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int mn = t % tiles_mn;
       const int m0 = (mn % p.m_blocks) * BM, n0 = (mn / p.m_blocks) * BN;
@@ -159,12 +164,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int cc = half * kChunks + c;  // chunk index inside the tile
-        gemm_epilogue_chunk(p, tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16), row, row_ok, n0 + cc * 32, alpha);
+        const uint32_t taddr = tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16);
+        if constexpr (TMA_EPI)
+          gemm_epilogue_chunk_tma(p, em, taddr, m0 + q * 32, lane, n0 + cc * 32, alpha, epi_stage + (warp - 4) * kEpiStageBytes,
+                                  &epi_bar[warp - 4], epi_phase);
+        else
+          gemm_epilogue_chunk(p, taddr, row, row_ok, n0 + cc * 32, alpha);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TMA_EPI && lane == 0) bulk_wait_all();  // staging tiles must outlive the TMA stores that read them
   }
 
   tc_fence_before();
@@ -175,24 +186,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, bool TMA_EPI>
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em, const GemmParams& p, int grid,
+                       cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, TMA_EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, 384, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  kern<<<grid, 384, Cfg::kSmemBytes, st>>>(tmA, tmB, em, p);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em, const GemmParams& p, int grid,
+                       cudaStream_t st) {
+  return p.tma_epi ? launch_gemm_t<BN, A_MN, B_MN, true>(tmA, tmB, em, p, grid, st)
+                   : launch_gemm_t<BN, A_MN, B_MN, false>(tmA, tmB, em, p, grid, st);
 }
 
 }  // namespace vc
 
 namespace vc {
-int launch_gemm_pair(const vc_gemm_args* a, int BN, const GemmParams& p, cudaStream_t st);  // gemm2.cu
+int launch_gemm_pair(const vc_gemm_args* a, int BN, const EpiMaps& em, const GemmParams& p, cudaStream_t st);  // gemm2.cu
+static int tma_epi_mode() {  // VIDCHAP_GEMM_TMA_EPI=0 selects the direct-store epilogue (A/B testing); default on
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("VIDCHAP_GEMM_TMA_EPI");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return mode;
+}
 static int pair_mode() {  // VIDCHAP_GEMM_PAIR=0 disables the 2-CTA kernel (A/B testing); default on
   static int mode = -1;
   if (mode < 0) {
@@ -246,6 +273,14 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   p.alpha = a->alpha;
   p.alpha_dev = a->alpha_dev;
   p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16;
+  p.tma_epi = tma_epi_mode() && (a->ldr % 4 == 0);
+  EpiMaps em;
+  if (p.tma_epi) {
+    int se = make_epi_maps(&em, a);
+    if (se != VC_OK) return se;
+  } else {
+    memset(&em, 0, sizeof(em));
+  }
 
   // CTA-pair kernel (256 x BN tiles) whenever the problem still fills the machine with pairs
   if (pair_mode() && a->tile_n >= 0 && a->M >= 256) {
@@ -259,7 +294,7 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
     if (BN2) {
       GemmParams p2 = p;
       p2.n_blocks = (a->N + BN2 - 1) / BN2;
-      return launch_gemm_pair(a, BN2, p2, st);
+      return launch_gemm_pair(a, BN2, em, p2, st);
     }
   }
 
@@ -277,10 +312,10 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
 
 #define VC_DISPATCH(BN_)                                                                              \
   if (BN == BN_) {                                                                                    \
-    if (!a->a_mn_major && !a->b_mn_major) return launch_gemm<BN_, false, false>(tmA, tmB, p, grid, st); \
-    if (!a->a_mn_major && a->b_mn_major) return launch_gemm<BN_, false, true>(tmA, tmB, p, grid, st);   \
-    if (a->a_mn_major && !a->b_mn_major) return launch_gemm<BN_, true, false>(tmA, tmB, p, grid, st);   \
-    return launch_gemm<BN_, true, true>(tmA, tmB, p, grid, st);                                        \
+    if (!a->a_mn_major && !a->b_mn_major) return launch_gemm<BN_, false, false>(tmA, tmB, em, p, grid, st); \
+    if (!a->a_mn_major && a->b_mn_major) return launch_gemm<BN_, false, true>(tmA, tmB, em, p, grid, st);   \
+    if (a->a_mn_major && !a->b_mn_major) return launch_gemm<BN_, true, false>(tmA, tmB, em, p, grid, st);   \
+    return launch_gemm<BN_, true, true>(tmA, tmB, em, p, grid, st);                                        \
   }
   VC_DISPATCH(256)
   VC_DISPATCH(128)

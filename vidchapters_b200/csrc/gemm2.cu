@@ -71,13 +71,14 @@ struct Gemm2Cfg {
   static constexpr int kBBytes = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (192 * 1024) / kStageBytes;  // BN=256: 6, BN=128: 8
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 + 256;
   static constexpr int kTmemCols = 2 * BN;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool TMA_EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ EpiMaps em, const GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kABytes = Cfg::kABytes, kBBytes = Cfg::kBBytes;
@@ -87,11 +88,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;   // 8 x 4 KB staging tiles of the TMA epilogue
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiWarps * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* epi_bar = tmem_empty + 2;   // [8] one per epilogue warp (residual tile landed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +116,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 512);  // leader's: 256 epilogue threads of each CTA
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
@@ -195,7 +199,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int half = (warp - 4) >> 2;
     constexpr int kChunks = BN / 64;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, epi_phase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int mn = t % tiles_mn;
       const int m0 = (mn % m_blocks2) * 256 + (int)rank * 128, n0 = (mn / m_blocks2) * BN;
@@ -207,12 +211,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int cc = half * kChunks + c;
-        gemm_epilogue_chunk(p, tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16), row, row_ok, n0 + cc * 32, alpha);
+        const uint32_t taddr = tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16);
+        if constexpr (TMA_EPI)
+          gemm_epilogue_chunk_tma(p, em, taddr, m0 + q * 32, lane, n0 + cc * 32, alpha, epi_stage + (warp - 4) * kEpiStageBytes,
+                                  &epi_bar[warp - 4], epi_phase);
+        else
+          gemm_epilogue_chunk(p, taddr, row, row_ok, n0 + cc * 32, alpha);
       }
       tc_fence_before();
       mbar_arrive_cta(&tmem_empty[acc], 0);  // the leader's barrier (remote arrive from the peer CTA)
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TMA_EPI && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -223,22 +233,30 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int clusters, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, bool TMA_EPI>
+static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em, const GemmParams& p, int clusters,
+                        cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
-  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, TMA_EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<2 * clusters, 384, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  kern<<<2 * clusters, 384, Cfg::kSmemBytes, st>>>(tmA, tmB, em, p);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em, const GemmParams& p, int clusters,
+                        cudaStream_t st) {
+  return p.tma_epi ? launch_gemm2_t<BN, A_MN, B_MN, true>(tmA, tmB, em, p, clusters, st)
+                   : launch_gemm2_t<BN, A_MN, B_MN, false>(tmA, tmB, em, p, clusters, st);
+}
+
 // Called by vc_gemm_bf16 (gemm.cu) when the pair kernel applies.  BN in {128, 256}.
-int launch_gemm_pair(const vc_gemm_args* a, int BN, const GemmParams& p, cudaStream_t st) {
+int launch_gemm_pair(const vc_gemm_args* a, int BN, const EpiMaps& em, const GemmParams& p, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   int s;
   if (!a->a_mn_major) s = make_tmap_2d(&tmA, a->A, a->K, a->M, a->lda, 64, 128);
@@ -253,10 +271,10 @@ int launch_gemm_pair(const vc_gemm_args* a, int BN, const GemmParams& p, cudaStr
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
 #define VC_DISPATCH2(BN_)                                                                               \
   if (BN == BN_) {                                                                                      \
-    if (!a->a_mn_major && !a->b_mn_major) return launch_gemm2<BN_, false, false>(tmA, tmB, p, clusters, st); \
-    if (!a->a_mn_major && a->b_mn_major) return launch_gemm2<BN_, false, true>(tmA, tmB, p, clusters, st);   \
-    if (a->a_mn_major && !a->b_mn_major) return launch_gemm2<BN_, true, false>(tmA, tmB, p, clusters, st);   \
-    return launch_gemm2<BN_, true, true>(tmA, tmB, p, clusters, st);                                    \
+    if (!a->a_mn_major && !a->b_mn_major) return launch_gemm2<BN_, false, false>(tmA, tmB, em, p, clusters, st); \
+    if (!a->a_mn_major && a->b_mn_major) return launch_gemm2<BN_, false, true>(tmA, tmB, em, p, clusters, st);   \
+    if (a->a_mn_major && !a->b_mn_major) return launch_gemm2<BN_, true, false>(tmA, tmB, em, p, clusters, st);   \
+    return launch_gemm2<BN_, true, true>(tmA, tmB, em, p, clusters, st);                                    \
   }
   VC_DISPATCH2(256)
   VC_DISPATCH2(128)

@@ -29,7 +29,16 @@ struct GemmParams {
   float alpha;
   const float* alpha_dev;  // optional device scalar multiplied into alpha
   uint32_t drop_seed, drop_p16;  // dropout applied after the activation, before the residual add (p16 = 0: off)
+  int tma_epi;                   // 1: epilogue I/O staged through shared memory and moved by TMA (see below)
 };
+
+// Tensor maps of the epilogue's global operands (32 x 32 boxes; fp32: SWIZZLE_128B, bf16: SWIZZLE_64B).
+struct EpiMaps {
+  CUtensorMap out, pre, resid;
+};
+
+constexpr int kEpiStageBytes = 4096;   // per epilogue warp: 32 rows x 128 B
+constexpr int kEpiWarps = 8;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
@@ -176,6 +185,151 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
               for (int j = 0; j < 32; ++j) if (j < ncols) dstb[j] = __float2bfloat16(v[j]);
             }
           }
+}
+
+// ---- TMA epilogue.
+// Why: with lane <-> accumulator row (the TMEM layout), direct global stores/loads touch 32 different rows per warp
+// instruction in 16-byte pieces; ncu showed the L1TEX pipe ~70 % busy with that traffic while the tensor pipe sat at
+// 46 % (profiles/r01_ncu_prof_gemm1_fwd_r01.txt) — the same L1TEX pipe also carries the TMA fills of the mainloop.
+// Here every warp stages its 32 x 32 block in a swizzled shared-memory tile: the residual block arrives by TMA load,
+// results leave by TMA store (or TMA reduce-add for split-K / accumulate), i.e. whole 128-byte lines on both sides.
+__device__ __forceinline__ uint32_t epi_off_f32(int t, int g) { return t * 128 + ((g ^ (t & 7)) << 4); }        // SWIZZLE_128B
+__device__ __forceinline__ uint32_t epi_off_bf16(int t, int g) { return t * 64 + ((g ^ ((t >> 1) & 3)) << 4); }  // SWIZZLE_64B
+
+__device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, const EpiMaps& em, uint32_t taddr, int row0,
+                                                        int lane, int col0, float alpha, uint8_t* stage, uint64_t* wbar,
+                                                        uint32_t& wphase) {
+  float v[32];
+  tmem_ld32(taddr, v);
+  const int row = row0 + lane;
+  const bool in_rows = row < p.M;
+  const bool full = in_rows && col0 + 32 <= p.N;
+  if (lane == 0) {
+    bulk_wait_read0();  // the previous chunk's store has finished reading this staging tile
+    if (p.residual) {
+      mbar_arrive_expect_tx(wbar, 4096);
+      tma_load_2d(stage, &em.resid, wbar, col0, row0);
+    }
+  }
+  __syncwarp();
+  uint4 ax[4];
+  if (p.act >= 3) {
+    if (full) {
+      const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ld_aux + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ax[j] = __ldg(ap + j);
+    } else {
+      const __nv_bfloat16* axp = p.aux + (long long)row * p.ld_aux + col0;
+      uint32_t w[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float lo = (in_rows && col0 + e * 2 < p.N) ? __bfloat162float(axp[e * 2]) : 0.f;
+        const float hi = (in_rows && col0 + e * 2 + 1 < p.N) ? __bfloat162float(axp[e * 2 + 1]) : 0.f;
+        w[e] = pack_bf16x2(lo, hi);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ax[j] = make_uint4(w[j * 4], w[j * 4 + 1], w[j * 4 + 2], w[j * 4 + 3]);
+    }
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= alpha;
+  if (p.bias) {
+    if (col0 + 32 <= p.N) {
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = __ldg(bp + j);
+        v[j * 4] += b4.x; v[j * 4 + 1] += b4.y; v[j * 4 + 2] += b4.z; v[j * 4 + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+    }
+  }
+  if (p.act == 2 && p.pre_out) {  // pre-activation copy (bf16) leaves first
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(stage + epi_off_bf16(lane, g)) =
+          make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                     pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&em.pre, stage, col0, row0);
+      bulk_commit();
+      bulk_wait_read0();
+    }
+    __syncwarp();
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act >= 3) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w[4] = {ax[j].x, ax[j].y, ax[j].z, ax[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+        if (p.act == 3) {
+          v[j * 8 + e * 2] = lo > 0.0f ? v[j * 8 + e * 2] : 0.0f;
+          v[j * 8 + e * 2 + 1] = hi > 0.0f ? v[j * 8 + e * 2 + 1] : 0.0f;
+        } else {
+          v[j * 8 + e * 2] *= gelu_erf_grad(lo);
+          v[j * 8 + e * 2 + 1] *= gelu_erf_grad(hi);
+        }
+      }
+    }
+  }
+  if (p.drop_p16) {
+    const float sc = drop_scale(p.drop_p16);
+    const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = drop_keep(p.drop_seed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
+  }
+  if (p.residual) {
+    mbar_wait(wbar, wphase);
+    wphase ^= 1;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 r = *reinterpret_cast<const float4*>(stage + epi_off_f32(lane, g));
+      v[g * 4 + 0] += r.x; v[g * 4 + 1] += r.y; v[g * 4 + 2] += r.z; v[g * 4 + 3] += r.w;
+    }
+  }
+  if (p.out_fp32) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      *reinterpret_cast<float4*>(stage + epi_off_f32(lane, g)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+  } else {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(stage + epi_off_bf16(lane, g)) =
+          make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                     pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (p.atomic) tma_reduce_add_2d(&em.out, stage, col0, row0);
+    else tma_store_2d(&em.out, stage, col0, row0);
+    bulk_commit();
+  }
+}
+
+// Host side: the three epilogue maps (unused ones alias `out`).
+inline int make_epi_maps(EpiMaps* em, const vc_gemm_args* a) {
+  const int oe = a->out_fp32 ? 4 : 2;
+  int s = make_tmap_2d_ex(&em->out, a->out, oe, a->N, a->M, a->ldo, 32, 32, a->out_fp32 ? 128 : 64);
+  if (s != VC_OK) return s;
+  em->pre = em->out;
+  em->resid = em->out;
+  if (a->pre_out && (s = make_tmap_2d_ex(&em->pre, a->pre_out, 2, a->N, a->M, a->ldo, 32, 32, 64)) != VC_OK) return s;
+  if (a->residual && (s = make_tmap_2d_ex(&em->resid, a->residual, 4, a->N, a->M, a->ldr, 32, 32, 128)) != VC_OK) return s;
+  return VC_OK;
 }
 
 }  // namespace vc
