@@ -204,9 +204,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
   const int row = row0 + lane;
   const bool in_rows = row < p.M;
   const bool full = in_rows && col0 + 32 <= p.N;
+  const bool two_stores = p.act == 2 && p.pre_out;  // the staging tile is used for the pre-activation copy first
   if (lane == 0) {
     bulk_wait_read0();  // the previous chunk's store has finished reading this staging tile
-    if (p.residual) {
+    if (p.residual && !two_stores) {
       mbar_arrive_expect_tx(wbar, 4096);
       tma_load_2d(stage, &em.resid, wbar, col0, row0);
     }
@@ -247,7 +248,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
       for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
     }
   }
-  if (p.act == 2 && p.pre_out) {  // pre-activation copy (bf16) leaves first
+  if (two_stores) {  // pre-activation copy (bf16) leaves first
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       *reinterpret_cast<uint4*>(stage + epi_off_bf16(lane, g)) =
@@ -259,6 +260,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
       tma_store_2d(&em.pre, stage, col0, row0);
       bulk_commit();
       bulk_wait_read0();
+      if (p.residual) {  // only now may the residual block land in the staging tile
+        mbar_arrive_expect_tx(wbar, 4096);
+        tma_load_2d(stage, &em.resid, wbar, col0, row0);
+      }
     }
     __syncwarp();
   }
