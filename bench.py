@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-gemms", default="")
+    ap.add_argument("--dropout", type=float, default=0.1, help="vis/enc/dec dropout (reference default 0.1, args.py)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -188,7 +189,8 @@ def main():
     from vidchapters_b200 import T5_BASE, GraphedTrainStep, Vid2Seq, Vid2SeqAdam
     cfg = dict(T5_BASE)
     B, T, L, S = args.batch, T_FRAMES, L_ASR, S_TGT
-    model = Vid2Seq("t5-base", tokenizer=Tok(), vis_drop=0.0, enc_drop=0.0, dec_drop=0.0, seed=0).to(dev)
+    model = Vid2Seq("t5-base", tokenizer=Tok(), vis_drop=args.dropout, enc_drop=args.dropout, dec_drop=args.dropout,
+                    seed=0).to(dev)
     model.train()
     opt = Vid2SeqAdam(model, lr=3e-4, clip_max_norm=0.1, world_size=world)
     ops = model.engine.ops
@@ -299,7 +301,7 @@ def main():
         "config": {"workload": "vid2seq t5-base train step (dvc.py:42-133, generative pass): fwd+bwd+clip+adam+renorm, "
                                f"batch {B}/GPU, 100 frames x768, 1000 ASR tok, 256 target tok (BASELINE configs[1])",
                    "global_batch": world * B, "tokens_per_step": tokens_step, "parallelism": f"dp{world}",
-                   "dropout": 0.0, "clip_max_norm": 0.1,
+                   "dropout": args.dropout, "clip_max_norm": 0.1,
                    "l2": "per-step working set (~6 GB of weights+activations) >> 126 MB L2; no explicit flush",
                    "residual_stream": "fp32", "gemm_operands": "bf16", "accumulate": "fp32"},
         "e2e": {"value": tokens_step / (ms_step_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_step_e2e,

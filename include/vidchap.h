@@ -24,6 +24,9 @@ extern "C" {
 int vc_version(void);               /* ABI version, bumps on any signature change */
 const char* vc_last_error(void);    /* thread-local message of the last failure */
 int vc_device_check(void);          /* VC_OK iff the current device is sm_100 (B200); message otherwise */
+/* Device pointer to a 32-bit salt XORed into every dropout seed by every kernel launched afterwards (NULL = none):
+ * a CUDA graph captured once draws fresh masks on each replay when the host bumps the salt between replays. */
+int vc_set_dropout_salt(const uint32_t* dev_ptr);
 
 /* ---- GEMM: out[M,N] = epilogue( alpha * op(A)[M,K] . op(B)[N,K]^T ), bf16 operands, fp32 accumulate (tcgen05).
  * Replaces nn.Linear forward (modeling_t5.py:305,310,528-536,581,1714; vit.py:17-20,41,53) and its autograd

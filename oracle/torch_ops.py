@@ -21,6 +21,7 @@ _MASKED = -3.0e38
 
 NO_DROP = (0, 0)
 _M32 = 0xFFFFFFFF
+_SALT = None   # optional device/host tensor XORed into every seed (mirrors vc_set_dropout_salt)
 
 
 def drop_mask(spec, idx: torch.Tensor) -> torch.Tensor:
@@ -29,6 +30,8 @@ def drop_mask(spec, idx: torch.Tensor) -> torch.Tensor:
     seed, p16 = spec
     if p16 == 0:
         return torch.ones(idx.shape, dtype=torch.float32, device=idx.device)
+    if _SALT is not None:
+        seed = (seed ^ (int(_SALT.item()) & _M32)) & _M32
     x = (((idx >> 1) & _M32) * 0x9E3779B1 + ((idx >> 33) & _M32) * 0x85EBCA77 + seed) & _M32
     x = x ^ (x >> 16)
     x = (x * 0x85EBCA6B) & _M32
@@ -60,6 +63,10 @@ class TorchOps:
         # flash_rounding: round the UN-normalised probabilities 2^(s2 - ceil(rowmax2)) to bf16 before P.V and divide by
         # the row sum afterwards — the attention kernel's rounding points (see oracle/vid2seq_oracle.py::Arith).
         self.flash = flash_rounding
+
+    def set_dropout_salt(self, salt):
+        global _SALT
+        _SALT = salt
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, pre_out=None,

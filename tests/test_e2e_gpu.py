@@ -216,3 +216,35 @@ def test_greedy_generate_cuda_matches_oracle():
     assert agree == 1.0
     with pytest.raises(NotImplementedError):
         m.generate(video, {"input_ids": inp, "attention_mask": inp != 0}, num_beams=4)
+
+
+def test_graphed_train_step_matches_eager_and_redraws_dropout():
+    from vidchapters_b200 import GraphedTrainStep, Vid2SeqAdam
+    fx = torch.load(os.path.join(GOLD, "tiny.pt"), weights_only=False)
+    cfg = fx["cfg"]
+    video, inp, out = fx["video"].cuda(), fx["input_ids"].cuda(), fx["output_ids"].cuda()
+    it = {"input_ids": inp, "attention_mask": inp != 0}
+    ot = {"input_ids": out, "attention_mask": out != 0}
+    # eager reference run (no dropout): 4 steps
+    m1 = build(cfg); m1.train()
+    o1 = Vid2SeqAdam(m1, lr=3e-4, clip_max_norm=0.1, world_size=1)
+    eager = []
+    for _ in range(4):
+        ld, _ = m1(video, it, ot); o1.zero_grad(); ld["loss"].backward(); o1.step(); eager.append(ld["loss"].item())
+    # graphed run from the same init: warm-up step eager (1), then captured replays (3)
+    m2 = build(cfg); m2.train()
+    o2 = Vid2SeqAdam(m2, lr=3e-4, clip_max_norm=0.1, world_size=1)
+    ld, _ = m2(video, it, ot); o2.zero_grad(); ld["loss"].backward(); o2.step()
+    g = GraphedTrainStep(m2, o2, video, inp, out, warmup_steps=0)
+    graphed = [ld["loss"].item()] + [g(video, inp, out).item() for _ in range(3)]
+    for a, b in zip(eager, graphed):
+        assert abs(a - b) < 5e-3 * abs(a), (eager, graphed)
+    # with dropout the same batch gives a different loss on every replay (device-side salt), still finite/decreasing
+    m3 = build(cfg); m3.train()
+    m3.vis_drop = m3.enc_drop = m3.dec_drop = 0.1
+    o3 = Vid2SeqAdam(m3, lr=3e-4, clip_max_norm=0.1, world_size=1)
+    ld, _ = m3(video, it, ot); o3.zero_grad(); ld["loss"].backward(); o3.step()
+    g3 = GraphedTrainStep(m3, o3, video, inp, out, warmup_steps=0)
+    ls = [g3().item() for _ in range(4)]
+    assert len(set(round(x, 4) for x in ls)) == 4 and all(x == x for x in ls), ls
+    m3.engine.ops.set_dropout_salt(None)

@@ -4,15 +4,16 @@
 // log-sum-exp (flash-attention style); nothing of size Lq x Lk touches HBM.
 //
 // One CTA = one (batch, head, 128-key tile), looping over the 128-query tiles that see it.  1 CTA / SM
-// (160 KB smem, 448 TMEM columns).  192 threads:
+// (160 KB smem, 448 TMEM columns).  320 threads:
 //   warp 0 lane 0 : TMA: K,V tile once; (Q_i, dO_i) through a 2-stage ring
 //   warp 1        : TMEM alloc; lane 0 issues per query tile
 //                     S  = Q_i.K^T        dP = dO_i.V^T                       (128x128x64 each, fresh)
 //                     dV += P^T.dO_i      dK += dS^T.Q_i     dQ_i = dS.K      (accumulate / accumulate / fresh)
-//   warps 2..5    : thread = one query row: p = exp2(s2 - lse2), ds = p*(dP - delta); writes bf16 P and scale*dS tiles
-//                   (128B-swizzled; each tile serves as MN-major A for dV/dK and dS also as K-major A for dQ);
-//                   accumulates d(bias) by relative position in shared memory; reads dQ_i from TMEM and
-//                   atomically adds it to the fp32 dQ accumulator; finally stores dK, dV (bf16).
+//   warps 2..9    : 8 compute warps (2 per TMEM lane quarter, 2 column chunks each): p = exp2(s2 - lse2),
+//                   ds = p*(dP - delta); write bf16 P and scale*dS tiles (128B-swizzled; each tile serves as MN-major
+//                   A for dV/dK and dS also as K-major A for dQ); while the MMAs run, every thread sums one diagonal
+//                   of the dS tile into its own slot of the d(bias) window; dQ_i goes from TMEM to the fp32 dQ
+//                   accumulator with atomics; finally dK, dV are stored (bf16).
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -34,21 +35,21 @@ struct AttnBwdParams {
   const int* bucket_lut;  // [Lq+Lk-1] bucket id per relative position (uniform-tile test), or null
   const uint8_t* kmask;   // [B][Lk] or null
   int causal;
-  float scale, scale_log2e;
+  float scale, scale_log2e, inv_scale;
   float* dq_acc;          // fp32 [B*Lq][ld_dq], head h at cols 64h   (atomicAdd)
   long long ld_dq;
   __nv_bfloat16* dk; long long ld_dk; int dk_col;  // bf16 [B*Lk][ld], head h at cols dk_col + 64h
   __nv_bfloat16* dv; long long ld_dv; int dv_col;
   float* dbias_rel;       // fp32 [H][Lq+Lk-1] (atomicAdd) or null
   uint32_t drop_seed, drop_p16;
+  const uint32_t* drop_salt;
 };
 
 constexpr int kBwdSmemTiles = 16384 * 2 /*K,V*/ + 2 * 16384 /*Q ring*/ + 2 * 16384 /*dO ring*/ + 32768 /*P*/ + 32768 /*dS*/;
-constexpr int kBwdRelMax = 1536;  // floats per relative-position window: ceil(Lq/128)*128 + 128 <= 1536 (Lq <= 1408)
-// + 4 per-warp d(bias) windows + bias window + key ceilings + 4 per-warp 32x33 transposition scratches + barriers
-constexpr int kAttnBwdSmem = kBwdSmemTiles + 5 * kBwdRelMax * 4 + 512 + 4 * 32 * 33 * 4 + 256;
+constexpr int kBwdRelMax = 2304;  // floats per relative-position window: ceil(Lq/128)*128 + 128 <= 2304 (Lq <= 2176)
+constexpr int kAttnBwdSmem = kBwdSmemTiles + 2 * kBwdRelMax * 4 + 512 + 256;  // + d(bias) window + bias window + key ceilings
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -58,11 +59,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sDO = sQ + 2 * 16384;   // [2]
   uint8_t* sP = sDO + 2 * 16384;   // 32 KB
   uint8_t* sDS = sP + 32768;       // 32 KB
-  float* s_rel = reinterpret_cast<float*>(sDS + 32768);   // [4 warps][kBwdRelMax]: private d(bias) windows, no atomics
-  float* s_bias = s_rel + 4 * kBwdRelMax;   // bias(k - q) * log2e for this key tile: slot (k - k0) + (Lq - 1 - q)
+  float* s_rel = reinterpret_cast<float*>(sDS + 32768);   // d(bias) window of this key tile: slot (k - k0) + (Lq - 1 - q)
+  float* s_bias = s_rel + kBwdRelMax;       // bias(k - q) * log2e, same slot indexing
   float* s_pen = s_bias + kBwdRelMax;   // per-key ceiling of this tile: +inf attend | kBMasked | -inf out of range
-  float* s_tr = s_pen + 128;            // [4 warps][32][33] skewed scratch for the diagonal sums
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tr + 4 * 32 * 33);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_pen + 128);
   uint64_t* kv_full = bars + 0;
   uint64_t* qd_full = bars + 1;   // [2]
   uint64_t* qd_empty = bars + 3;  // [2]
@@ -82,15 +82,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_read, 128);
+    mbar_init(dq_read, 256);
     fence_barrier_init();
   }
   const int n_rel = p.Lq + kBT;  // relative positions touched by this CTA: (k - q + Lq - 1) - rel_base in [0, Lq+127)
   const int rel_base = k0;       // slot = (k - k0) + (Lq - 1 - q)
   if (p.dbias_rel)
-    for (int i = threadIdx.x; i < 4 * kBwdRelMax; i += blockDim.x) s_rel[i] = 0.f;
+    for (int i = threadIdx.x; i < kBwdRelMax; i += blockDim.x) s_rel[i] = 0.f;
   {  // always filled + padded so the per-element loop below is branch-free (see attn_fwd.cu)
     const float* brow_g = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) : nullptr;
     const int n_pad = ((p.Lq + kBT - 1) / kBT) * kBT + kBT;  // covers slot (k-k0) + (Lq-1-q) for every q of every tile
@@ -160,11 +160,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_commit(dq_full);
     }
   } else if (warp >= 2) {
+    // ===================== compute: 8 warps = 2 per TMEM lane quarter, each taking 2 of the 4 column chunks ==========
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
+    const int ct = (warp - 2) * 32 + lane;   // 0..255: index among the compute threads
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float* rel_w = s_rel + quarter * kBwdRelMax;   // this warp's private window
-    float* tr_w = s_tr + quarter * (32 * 33);
     for (int i = 0; i < nqt; ++i) {
       const int q0 = (qt0 + i) * kBT;
       const int q = q0 + r;
@@ -175,18 +176,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // indexed by k - k0; rows past Lq (zero-filled Q/dO, p forced to 0) clamp to slot 0 to stay inside the window
       const float* brow = s_bias + (q_ok ? (p.Lq - 1 - q) : 0);
       const bool causal_tile = p.causal && (k0 + kBT - 1 > q0);
-      // d(bias): is the whole tile inside one bucket?  then one add per row instead of one per element
-      bool uniform = false;
-      if (p.dbias_rel && p.bucket_lut) {
-        const int rel_lo = max(k0 - (q0 + kBT - 1) + p.Lq - 1, 0);
-        const int rel_hi = min(k0 + kBT - 1 - q0 + p.Lq - 1, p.Lq + p.Lk - 2);
-        uniform = (p.bucket_lut[rel_lo] == p.bucket_lut[rel_hi]);
-      }
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      float ds_rowsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         float sv[32], dp[32];
         tmem_ld32(tS + lane_off + c * 32, sv);
         tmem_ld32(tDP + lane_off + c * 32, dp);
@@ -218,10 +212,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         if (p.drop_p16) {  // O = drop(P).V: dV uses the dropped P, dP flows back through the same mask
           const float sc = drop_scale(p.drop_p16);
+          const uint32_t dseed = drop_salted(p.drop_seed, p.drop_salt);
           const unsigned long long base = (((unsigned long long)b * p.H + h) * p.Lq + q) * p.Lk + k0 + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const bool keep = drop_keep(p.drop_seed, p.drop_p16, base + j);
+            const bool keep = drop_keep(dseed, p.drop_p16, base + j);
             const float dpm = keep ? dp[j] * sc : 0.0f;
             dp[j] = sv[j] * (dpm - delta);
             sv[j] = keep ? sv[j] * sc : 0.0f;
@@ -229,29 +224,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) dp[j] = sv[j] * (dp[j] - delta);
-        }
-        if (p.dbias_rel) {
-          if (uniform) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ds_rowsum += dp[j];
-          } else {
-            // d(bias)[k - q] over this warp's 32x32 block: transpose through a skewed scratch, lane d sums diagonal
-            // k - q = d (and its wrapped partner d - 32), then adds them to its own two slots of the warp-private
-            // window.  No shared-memory float atomics (they compile to CAS spin loops).
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tr_w[lane * 33 + j] = dp[j];
-            __syncwarp();
-            float sa = 0.f, sb = 0.f;
-#pragma unroll
-            for (int l = 0; l < 32; ++l) {
-              const float tv = tr_w[l * 33 + ((lane + l) & 31)];
-              if (lane + l < 32) sa += tv; else sb += tv;
-            }
-            const int base_c = c * 32 + (p.Lq - 1 - (q0 + quarter * 32));   // slot of (k - q) == 0 for this block
-            if (base_c + lane >= 0) rel_w[base_c + lane] += sa;
-            if (base_c + lane - 32 >= 0) rel_w[base_c + lane - 32] += sb;
-            __syncwarp();
-          }
         }
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
         uint8_t* drow = sDS + (c >> 1) * 16384 + r * 128;
@@ -268,23 +240,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                          pack_bf16x2(dp[g * 8 + 6] * p.scale, dp[g * 8 + 7] * p.scale));
         }
       }
-      if (p.dbias_rel && uniform) {
-        if (q_ok) rel_w[p.Lq - 1 - q] += ds_rowsum;   // own slot of the warp-private window
-        __syncwarp();
-      }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
-      // ---- dQ_i: TMEM -> fp32 atomics
+      // ---- d(bias)[k - q]: while the dV/dK/dQ MMAs run, thread ct sums diagonal (k-k0) - (q-q0) = ct - 128 of the
+      // finished dS tile straight from shared memory (bf16, scaled by `scale`) into ITS slot of the window — one owner
+      // per slot, so no atomics.  (The MMAs only read sDS; the next tile's writers are held by the named barrier.)
+      if (p.dbias_rel) {
+        mbar_wait(pds_full, i & 1);   // every compute thread has written its part of dS
+        const int dgl = ct - 128;     // diagonal, -127..127 (ct == 0 -> -128: empty)
+        if (ct > 0) {
+          const int r_lo = max(0, -dgl), r_hi = min(127, 127 - dgl);
+          float acc = 0.f;
+          for (int rr = r_lo; rr <= r_hi; ++rr) {
+            const int cidx = rr + dgl;
+            const uint8_t* e = sDS + (cidx >> 6) * 16384 + rr * 128 + ((((cidx & 63) >> 3) ^ (rr & 7)) << 4) + (cidx & 7) * 2;
+            acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(e));
+          }
+          const int slot = dgl + (p.Lq - 1 - q0);   // (k - k0) + (Lq - 1 - q)
+          if (slot >= 0) s_rel[slot] += acc * p.inv_scale;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // dS(i) fully consumed before anyone rewrites it for tile i+1
+      }
+      // ---- dQ_i: TMEM -> fp32 atomics (this warp: its lane quarter, 32 of the 64 columns)
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         float v[32];
-        tmem_ld32(tDQ + lane_off + c * 32, v);
+        tmem_ld32(tDQ + lane_off + half * 32, v);
         tmem_ld_wait();
         if (q_ok) {
-          float4* dst = reinterpret_cast<float4*>(p.dq_acc + ((long long)b * p.Lq + q) * p.ld_dq + h * kBD + c * 32);
+          float4* dst = reinterpret_cast<float4*>(p.dq_acc + ((long long)b * p.Lq + q) * p.ld_dq + h * kBD + half * 32);
 #pragma unroll
           for (int g = 0; g < 8; ++g) atomicAdd(dst + g, make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]));
         }
@@ -300,18 +286,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
         const long long ld = which == 0 ? p.ld_dv : p.ld_dk;
         const int col = which == 0 ? p.dv_col : p.dk_col;
+        float v[32];
+        tmem_ld32((which == 0 ? tDV : tDK) + lane_off + half * 32, v);
+        tmem_ld_wait();
+        if (kk < p.Lk) {
+          uint4* dst = reinterpret_cast<uint4*>(base + ((long long)b * p.Lk + kk) * ld + col + h * kBD + half * 32);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-          tmem_ld32((which == 0 ? tDV : tDK) + lane_off + c * 32, v);
-          tmem_ld_wait();
-          if (kk < p.Lk) {
-            uint4* dst = reinterpret_cast<uint4*>(base + ((long long)b * p.Lk + kk) * ld + col + h * kBD + c * 32);
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              dst[g] = make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                                  pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
-          }
+          for (int g = 0; g < 4; ++g)
+            dst[g] = make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
         }
       }
     } else if (kk < p.Lk) {  // no query tile sees this key tile: zero gradients
@@ -319,8 +302,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
         const long long ld = which == 0 ? p.ld_dv : p.ld_dk;
         const int col = which == 0 ? p.dv_col : p.dk_col;
-        uint4* dst = reinterpret_cast<uint4*>(base + ((long long)b * p.Lk + kk) * ld + col + h * kBD);
-        for (int g = 0; g < 8; ++g) dst[g] = make_uint4(0, 0, 0, 0);
+        uint4* dst = reinterpret_cast<uint4*>(base + ((long long)b * p.Lk + kk) * ld + col + h * kBD + half * 32);
+        for (int g = 0; g < 4; ++g) dst[g] = make_uint4(0, 0, 0, 0);
       }
     }
   }
@@ -331,7 +314,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float* dst = p.dbias_rel + (long long)h * (p.Lq + p.Lk - 1) + rel_base;
     const int lim = p.Lq + p.Lk - 1 - rel_base;
     for (int i = threadIdx.x; i < n_rel && i < lim; i += blockDim.x) {
-      const float g = s_rel[i] + s_rel[kBwdRelMax + i] + s_rel[2 * kBwdRelMax + i] + s_rel[3 * kBwdRelMax + i];
+      const float g = s_rel[i];
       if (g != 0.f) atomicAdd(dst + i, g);
     }
   }
@@ -403,19 +386,19 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   p.B = f->B; p.H = f->H; p.Lq = f->Lq; p.Lk = f->Lk;
   p.q_col = f->q_col; p.k_col = f->k_col; p.v_col = f->v_col; p.do_col = a->do_col;
   p.lse2 = f->lse2; p.delta = a->delta; p.bias_rel = f->bias_rel; p.bucket_lut = a->bucket_lut; p.kmask = f->kmask;
-  p.causal = f->causal; p.scale = f->scale; p.scale_log2e = f->scale * kBLog2e;
+  p.causal = f->causal; p.scale = f->scale; p.scale_log2e = f->scale * kBLog2e; p.inv_scale = 1.0f / f->scale;
   p.dq_acc = a->dq_acc; p.ld_dq = a->ld_dq;
   p.dk = (__nv_bfloat16*)a->dk; p.ld_dk = a->ld_dk; p.dk_col = a->dk_col;
   p.dv = (__nv_bfloat16*)a->dv; p.ld_dv = a->ld_dv; p.dv_col = a->dv_col;
   p.dbias_rel = a->dbias_rel;
-  p.drop_seed = f->drop_seed; p.drop_p16 = f->drop_p16;
+  p.drop_seed = f->drop_seed; p.drop_p16 = f->drop_p16; p.drop_salt = drop_salt_ptr();
   static bool attr = false;
   if (!attr) {
     VC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
     attr = true;
   }
   dim3 grid((f->Lk + kBT - 1) / kBT, f->H, f->B);
-  attn_bwd_kernel<<<grid, 192, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, p);
+  attn_bwd_kernel<<<grid, 320, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, p);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

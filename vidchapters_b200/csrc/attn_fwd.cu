@@ -37,6 +37,7 @@ struct AttnFwdParams {
   int causal;
   float scale_log2e;
   uint32_t drop_seed, drop_p16;
+  const uint32_t* drop_salt;
   int q_offset;              // absolute position of query row 0 (incremental decoding), added to *q_offset_dev
   const int* q_offset_dev;   // optional device scalar (CUDA-graph friendly decode step counter)
   int bias_zero, bias_len;   // bias row: index of relative position 0, row length
@@ -254,9 +255,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         if (p.drop_p16) {
           const float sc = drop_scale(p.drop_p16);
+          const uint32_t dseed = drop_salted(p.drop_seed, p.drop_salt);
           const unsigned long long base = (((unsigned long long)b * p.H + h) * p.Lq + q) * p.Lk + k0 + c * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = drop_keep(p.drop_seed, p.drop_p16, base + i) ? v[i] * sc : 0.0f;
+          for (int i = 0; i < 32; ++i) v[i] = drop_keep(dseed, p.drop_p16, base + i) ? v[i] * sc : 0.0f;
         }
         // 32 columns = 4 x 16-byte chunks of this row; chunk index within the 64-wide atom: (c&1)*4 + g
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
@@ -332,7 +334,7 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
   p.lse2 = a->lse2; p.bias_rel = a->bias_rel; p.kmask = a->kmask; p.causal = a->causal;
   p.scale_log2e = a->scale * kLog2e;
-  p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16;
+  p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16; p.drop_salt = drop_salt_ptr();
   p.q_offset = a->q_offset; p.q_offset_dev = a->q_offset_dev;
   p.bias_zero = a->bias_len > 0 ? a->bias_zero : a->Lq - 1;
   p.bias_len = a->bias_len > 0 ? a->bias_len : a->Lq + a->Lk - 1;

@@ -110,9 +110,16 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1
   return encode(out, base, 3, dims, strides, box);
 }
 
+static const uint32_t* g_drop_salt = nullptr;
+const uint32_t* drop_salt_ptr() { return g_drop_salt; }
+
 }  // namespace vc
 
-extern "C" int vc_version(void) { return 3; }
+extern "C" int vc_set_dropout_salt(const uint32_t* dev_ptr) {
+  vc::g_drop_salt = dev_ptr;
+  return VC_OK;
+}
+extern "C" int vc_version(void) { return 4; }
 extern "C" const char* vc_last_error(void) { return vc::g_err; }
 extern "C" int vc_device_check(void) {
   int dev = 0;

@@ -39,4 +39,8 @@ int make_tmap_2d_ex(CUtensorMap* out, const void* base, int elt_bytes, uint64_t 
 
 int num_sms();
 
+// Device pointer to a 32-bit salt XORed into every dropout seed (vc_set_dropout_salt); lets a captured CUDA graph draw
+// fresh masks on every replay.  nullptr = no salt.
+const uint32_t* drop_salt_ptr();
+
 }  // namespace vc

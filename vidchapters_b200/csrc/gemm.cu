@@ -272,7 +272,7 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   p.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux); p.ld_aux = a->ld_aux;
   p.alpha = a->alpha;
   p.alpha_dev = a->alpha_dev;
-  p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16;
+  p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16; p.drop_salt = drop_salt_ptr();
   p.tma_epi = tma_epi_mode() && (a->ldr % 4 == 0);
   EpiMaps em;
   if (p.tma_epi) {

@@ -29,6 +29,7 @@ struct GemmParams {
   float alpha;
   const float* alpha_dev;  // optional device scalar multiplied into alpha
   uint32_t drop_seed, drop_p16;  // dropout applied after the activation, before the residual add (p16 = 0: off)
+  const uint32_t* drop_salt;     // optional device salt XORed into drop_seed
   int tma_epi;                   // 1: epilogue I/O staged through shared memory and moved by TMA (see below)
 };
 
@@ -137,9 +138,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
           }
           if (p.drop_p16) {
             const float sc = drop_scale(p.drop_p16);
+            const uint32_t dseed = drop_salted(p.drop_seed, p.drop_salt);
             const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + col0;
   #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = drop_keep(p.drop_seed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
+            for (int j = 0; j < 32; ++j) v[j] = drop_keep(dseed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
           }
           if (p.residual) {
             if (full) {
@@ -292,9 +294,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
   }
   if (p.drop_p16) {
     const float sc = drop_scale(p.drop_p16);
+    const uint32_t dseed = drop_salted(p.drop_seed, p.drop_salt);
     const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + col0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = drop_keep(p.drop_seed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
+    for (int j = 0; j < 32; ++j) v[j] = drop_keep(dseed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
   }
   if (p.residual) {
     mbar_wait(wbar, wphase);

@@ -21,8 +21,9 @@ __device__ __forceinline__ float warp_max_f(float v) {
 
 // ---- embedding gather: out[i,:] = table[ids[i],:]   (model/vid2seq.py:71, modeling_t5.py:972)
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
-                                                       float* __restrict__ out, int n, int d, int V, uint32_t drop_seed,
-                                                       uint32_t drop_p16) {
+                                                       float* __restrict__ out, int n, int d, int V, uint32_t drop_seed_in,
+                                                       uint32_t drop_p16, const uint32_t* salt) {
+  const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const int lane = threadIdx.x & 31;
   const int wt = gridDim.x * (blockDim.x >> 5);
   const float sc = drop_p16 ? drop_scale(drop_p16) : 1.f;
@@ -46,8 +47,9 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restr
 }
 // ---- embedding backward: dtable[ids[i],:] += dout[i,:]   (autograd of nn.Embedding; tied table)
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dout,
-                                                       float* __restrict__ dtable, int n, int d, int V, uint32_t drop_seed,
-                                                       uint32_t drop_p16) {
+                                                       float* __restrict__ dtable, int n, int d, int V, uint32_t drop_seed_in,
+                                                       uint32_t drop_p16, const uint32_t* salt) {
+  const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const int lane = threadIdx.x & 31;
   const int wt = gridDim.x * (blockDim.x >> 5);
   const float sc = drop_p16 ? drop_scale(drop_p16) : 1.f;
@@ -115,7 +117,8 @@ __global__ void bias_fold_kernel(const float* __restrict__ drel, const int* __re
 
 // ---- x + pos_embed (model/vit.py:119-127; nearest interpolation when T != num_features)
 __global__ void add_pos_kernel(const float* __restrict__ x, const float* __restrict__ pos, float* __restrict__ out, int B,
-                               int T, int C, int P, uint32_t drop_seed, uint32_t drop_p16) {
+                               int T, int C, int P, uint32_t drop_seed_in, uint32_t drop_p16, const uint32_t* salt) {
+  const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
   const long long total = (long long)B * T * C / 4;
   if (i < total) {
@@ -137,7 +140,8 @@ __global__ void add_pos_kernel(const float* __restrict__ x, const float* __restr
   }
 }
 __global__ void add_pos_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B, int T, int C, int P,
-                                   uint32_t drop_seed, uint32_t drop_p16) {
+                                   uint32_t drop_seed_in, uint32_t drop_p16, const uint32_t* salt) {
+  const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over T*C
   if (i < T * C) {
     const int t = i / C, c = i % C;
@@ -285,7 +289,7 @@ extern "C" int vc_embed_fwd(const int64_t* ids, const float* table, float* out, 
                             uint32_t drop_p16, void* stream) {
   VC_CHECK(n > 0 && d % 4 == 0, "vc_embed_fwd: bad dims");
   embed_fwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, table, out, n, d, V, drop_seed,
-                                                                  drop_p16);
+                                                                  drop_p16, drop_salt_ptr());
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -293,7 +297,7 @@ extern "C" int vc_embed_bwd(const int64_t* ids, const float* dout, float* dtable
                             uint32_t drop_p16, void* stream) {
   VC_CHECK(n > 0 && d % 4 == 0, "vc_embed_bwd: bad dims");
   embed_bwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, dout, dtable, n, d, V, drop_seed,
-                                                                  drop_p16);
+                                                                  drop_p16, drop_salt_ptr());
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -320,13 +324,13 @@ extern "C" int vc_add_pos(const float* x, const float* pos, float* out, int B, i
                           uint32_t drop_p16, void* stream) {
   VC_CHECK(C % 4 == 0, "vc_add_pos: C must be x4");
   const long long total = (long long)B * T * C / 4;
-  add_pos_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(x, pos, out, B, T, C, P, drop_seed, drop_p16);
+  add_pos_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(x, pos, out, B, T, C, P, drop_seed, drop_p16, drop_salt_ptr());
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C, int P, uint32_t drop_seed,
                               uint32_t drop_p16, void* stream) {
-  add_pos_bwd_kernel<<<(T * C + 255) / 256, 256, 0, ST(stream)>>>(dx, dpos, B, T, C, P, drop_seed, drop_p16);
+  add_pos_bwd_kernel<<<(T * C + 255) / 256, 256, 0, ST(stream)>>>(dx, dpos, B, T, C, P, drop_seed, drop_p16, drop_salt_ptr());
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

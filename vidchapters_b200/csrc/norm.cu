@@ -35,8 +35,9 @@ template <bool LAYERNORM>
 __global__ void __launch_bounds__(256)
 norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, float* __restrict__ rstd_out,
-                float* __restrict__ mean_out, int M, int D, float eps, float out_scale, RowMap map, uint32_t drop_seed,
-                uint32_t drop_p16) {
+                float* __restrict__ mean_out, int M, int D, float eps, float out_scale, RowMap map, uint32_t drop_seed_in,
+                uint32_t drop_p16, const uint32_t* salt) {
+  const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const int lane = threadIdx.x & 31;
   const int nv = D / 128;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -109,8 +110,9 @@ __global__ void __launch_bounds__(256)
 norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ rstd_in, const float* __restrict__ mean_in, float* __restrict__ dx,
                 __nv_bfloat16* __restrict__ dx_bf16, int accumulate_dx, float* __restrict__ dw, float* __restrict__ db,
-                int M, int D, float scale, RowMap map, uint32_t g_drop_seed, uint32_t g_drop_p16, uint32_t dxb_drop_seed,
-                uint32_t dxb_drop_p16) {
+                int M, int D, float scale, RowMap map, uint32_t g_drop_seed_in, uint32_t g_drop_p16, uint32_t dxb_drop_seed_in,
+                uint32_t dxb_drop_p16, const uint32_t* salt) {
+  const uint32_t g_drop_seed = drop_salted(g_drop_seed_in, salt), dxb_drop_seed = drop_salted(dxb_drop_seed_in, salt);
   __shared__ float red[8][kMaxV4 * 128 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = D / 128;
@@ -222,10 +224,10 @@ extern "C" int vc_norm_fwd(int kind, const float* x, const float* w, const float
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (kind == 0)
     norm_fwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
-                                                         eps, out_scale, map, drop_seed, drop_p16);
+                                                         eps, out_scale, map, drop_seed, drop_p16, drop_salt_ptr());
   else
     norm_fwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
-                                                        eps, out_scale, map, drop_seed, drop_p16);
+                                                        eps, out_scale, map, drop_seed, drop_p16, drop_salt_ptr());
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -240,10 +242,10 @@ extern "C" int vc_norm_bwd(int kind, const float* g, const float* x, const float
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (kind == 0)
     norm_bwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map,
-                                                         g_drop_seed, g_drop_p16, dxb_drop_seed, dxb_drop_p16);
+                                                         g_drop_seed, g_drop_p16, dxb_drop_seed, dxb_drop_p16, drop_salt_ptr());
   else
     norm_bwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map,
-                                                         g_drop_seed, g_drop_p16, dxb_drop_seed, dxb_drop_p16);
+                                                         g_drop_seed, g_drop_p16, dxb_drop_seed, dxb_drop_p16, drop_salt_ptr());
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

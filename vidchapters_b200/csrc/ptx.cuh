@@ -166,6 +166,7 @@ __device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t p16, unsigned 
   const uint32_t h = drop_hash(seed, idx);
   return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= p16;
 }
+__device__ __forceinline__ uint32_t drop_salted(uint32_t seed, const uint32_t* salt) { return salt ? seed ^ __ldg(salt) : seed; }
 __device__ __forceinline__ float drop_scale(uint32_t p16) { return 65536.0f / (float)(65536u - p16); }
 
 // ---------------------------------------------------------------- misc

@@ -26,6 +26,10 @@ class GraphedTrainStep:
         self.input_ids = input_ids.to(dev, copy=True).contiguous()
         self.output_ids = output_ids.to(dev, copy=True).contiguous()
         self.graph = torch.cuda.CUDAGraph()
+        # dropout: the captured kernels carry fixed seeds; a device-side salt, bumped before every replay, gives each
+        # step its own masks (forward and backward of one step read the same salt value)
+        self.salt = torch.zeros(1, dtype=torch.int32, device=dev)
+        model.engine.ops.set_dropout_salt(self.salt)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -64,6 +68,7 @@ class GraphedTrainStep:
             self.output_ids.copy_(output_ids, non_blocking=True)
         if not self.model._shadow_valid:     # parameters were changed from outside (load_state_dict, stock optimiser)
             self.model.engine.sync_bf16()
+        self.salt.add_(0x9E3779B)   # new dropout masks for this step
         self.graph.replay()
         self.replays += 1
         self.model.engine.ops.launches += self.launches_per_replay

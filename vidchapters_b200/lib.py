@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvidchap.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class GemmArgs(C.Structure):
@@ -89,6 +89,7 @@ SIGNATURES = {
     "vc_kv_append": [P, I64, P, I, I, I, P, P],
     "vc_greedy_next": [P, I64, I, P, P, P, I, P, I64, I64, I, P],
     "vc_step_advance": [P, P],
+    "vc_set_dropout_salt": [P],
     "vc_version": [],
     "vc_last_error": [],
     "vc_device_check": [],

@@ -42,6 +42,11 @@ class CudaOps:
         _lib.check(self.lib.vc_device_check())
         self.launches = 0  # kernels launched through this table (bench.py reports it as gpu_launches)
 
+    def set_dropout_salt(self, salt):
+        """salt: int32/uint32 device tensor [1] (kept alive by the caller) or None."""
+        self._salt = salt
+        _lib.check(self.lib.vc_set_dropout_salt(None if salt is None else C.c_void_p(salt.data_ptr())))
+
     @staticmethod
     def _stream():
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
