@@ -25,20 +25,24 @@ _SALT = None   # optional device/host tensor XORed into every seed (mirrors vc_s
 
 
 def drop_mask(spec, idx: torch.Tensor) -> torch.Tensor:
-    """Float multiplier (0 or 65536/(65536-p16)) for int64 element indices — the same counter-based hash as
-    vidchapters_b200/csrc/ptx.cuh::drop_keep (murmur3 finaliser of the pair index, 16 bits per element)."""
+    """Float multiplier (0 or 65536/(65536-p16)) for every element of a tensor whose flat int64 indices are `idx`
+    (shape [..., C]): the counter-based hash of vidchapters_b200/csrc/ptx.cuh (row = flat // C, column = flat % C; one
+    32-bit hash per column pair, 16 bits per element)."""
     seed, p16 = spec
     if p16 == 0:
         return torch.ones(idx.shape, dtype=torch.float32, device=idx.device)
     if _SALT is not None:
         seed = (seed ^ (int(_SALT.item()) & _M32)) & _M32
-    x = (((idx >> 1) & _M32) * 0x9E3779B1 + ((idx >> 33) & _M32) * 0x85EBCA77 + seed) & _M32
-    x = x ^ (x >> 16)
-    x = (x * 0x85EBCA6B) & _M32
-    x = x ^ (x >> 13)
-    x = (x * 0xC2B2AE35) & _M32
-    x = x ^ (x >> 16)
-    r = torch.where((idx & 1) == 1, x >> 16, x & 0xFFFF)
+    C = idx.shape[-1]
+    row, col = idx // C, idx % C
+    key = (seed + (row & _M32) * 0x9E3779B1 + ((row >> 32) & _M32) * 0x7F4A7C15) & _M32
+    x = (key + (col >> 1) * 0x85EBCA77) & _M32
+    x = x ^ (x >> 15)
+    x = (x * 0x2C1B3C6D) & _M32
+    x = x ^ (x >> 12)
+    x = (x * 0x297A2D39) & _M32
+    x = x ^ (x >> 15)
+    r = torch.where((col & 1) == 1, x >> 16, x & 0xFFFF)
     return (r >= p16).float() * (65536.0 / (65536.0 - p16))
 
 

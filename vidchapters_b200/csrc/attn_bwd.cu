@@ -212,14 +212,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         if (p.drop_p16) {  // O = drop(P).V: dV uses the dropped P, dP flows back through the same mask
           const float sc = drop_scale(p.drop_p16);
-          const uint32_t dseed = drop_salted(p.drop_seed, p.drop_salt);
-          const unsigned long long base = (((unsigned long long)b * p.H + h) * p.Lq + q) * p.Lk + k0 + c * 32;
+          const uint32_t rk = drop_row_key(drop_salted(p.drop_seed, p.drop_salt), ((unsigned long long)b * p.H + h) * p.Lq + q);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool keep = drop_keep(dseed, p.drop_p16, base + j);
-            const float dpm = keep ? dp[j] * sc : 0.0f;
-            dp[j] = sv[j] * (dpm - delta);
-            sv[j] = keep ? sv[j] * sc : 0.0f;
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t hh = drop_pair_hash(rk, (uint32_t)(k0 + c * 32 + j));
+            const bool k0_ = (hh & 0xFFFFu) >= p.drop_p16, k1_ = (hh >> 16) >= p.drop_p16;
+            const float d0 = k0_ ? dp[j] * sc : 0.0f, d1 = k1_ ? dp[j + 1] * sc : 0.0f;
+            dp[j] = sv[j] * (d0 - delta);
+            dp[j + 1] = sv[j + 1] * (d1 - delta);
+            sv[j] = k0_ ? sv[j] * sc : 0.0f;
+            sv[j + 1] = k1_ ? sv[j + 1] * sc : 0.0f;
           }
         } else {
 #pragma unroll

@@ -254,11 +254,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         if (p.drop_p16) {
-          const float sc = drop_scale(p.drop_p16);
-          const uint32_t dseed = drop_salted(p.drop_seed, p.drop_salt);
-          const unsigned long long base = (((unsigned long long)b * p.H + h) * p.Lq + q) * p.Lk + k0 + c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = drop_keep(dseed, p.drop_p16, base + i) ? v[i] * sc : 0.0f;
+          // mask row = (b, h, q), column = k
+          drop_apply<32>(v, drop_row_key(drop_salted(p.drop_seed, p.drop_salt), ((unsigned long long)b * p.H + h) * p.Lq + q), p.drop_p16,
+                         (uint32_t)(k0 + c * 32), drop_scale(p.drop_p16));
         }
         // 32 columns = 4 x 16-byte chunks of this row; chunk index within the 64-wide atom: (c&1)*4 + g
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;

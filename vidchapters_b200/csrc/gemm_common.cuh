@@ -137,11 +137,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
             }
           }
           if (p.drop_p16) {
-            const float sc = drop_scale(p.drop_p16);
-            const uint32_t dseed = drop_salted(p.drop_seed, p.drop_salt);
-            const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + col0;
-  #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = drop_keep(dseed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
+            drop_apply<32>(v, drop_row_key(drop_salted(p.drop_seed, p.drop_salt), (unsigned long long)row), p.drop_p16, (uint32_t)col0,
+                           drop_scale(p.drop_p16));
           }
           if (p.residual) {
             if (full) {
@@ -293,11 +290,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
     }
   }
   if (p.drop_p16) {
-    const float sc = drop_scale(p.drop_p16);
-    const uint32_t dseed = drop_salted(p.drop_seed, p.drop_salt);
-    const unsigned long long base = (unsigned long long)row * (unsigned long long)p.N + col0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = drop_keep(dseed, p.drop_p16, base + j) ? v[j] * sc : 0.0f;
+    drop_apply<32>(v, drop_row_key(drop_salted(p.drop_seed, p.drop_salt), (unsigned long long)row), p.drop_p16, (uint32_t)col0,
+                   drop_scale(p.drop_p16));
   }
   if (p.residual) {
     mbar_wait(wbar, wphase);

@@ -35,11 +35,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restr
     for (int c = lane; c < d / 4; c += 32) {
       float4 v = __ldg(src + c);
       if (drop_p16) {
-        const unsigned long long base = (unsigned long long)i * d + c * 4;
-        v.x = drop_keep(drop_seed, drop_p16, base + 0) ? v.x * sc : 0.f;
-        v.y = drop_keep(drop_seed, drop_p16, base + 1) ? v.y * sc : 0.f;
-        v.z = drop_keep(drop_seed, drop_p16, base + 2) ? v.z * sc : 0.f;
-        v.w = drop_keep(drop_seed, drop_p16, base + 3) ? v.w * sc : 0.f;
+        drop_apply<4>(&v.x, drop_row_key(drop_seed, (unsigned long long)i), drop_p16, (uint32_t)(c * 4), sc);
       }
       dst[c] = v;
     }
@@ -61,11 +57,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
     for (int c = lane; c < d / 4; c += 32) {
       float4 v = src[c];
       if (drop_p16) {
-        const unsigned long long base = (unsigned long long)i * d + c * 4;
-        v.x = drop_keep(drop_seed, drop_p16, base + 0) ? v.x * sc : 0.f;
-        v.y = drop_keep(drop_seed, drop_p16, base + 1) ? v.y * sc : 0.f;
-        v.z = drop_keep(drop_seed, drop_p16, base + 2) ? v.z * sc : 0.f;
-        v.w = drop_keep(drop_seed, drop_p16, base + 3) ? v.w * sc : 0.f;
+        drop_apply<4>(&v.x, drop_row_key(drop_seed, (unsigned long long)i), drop_p16, (uint32_t)(c * 4), sc);
       }
       atomicAdd(dst + c, v);
     }
@@ -129,12 +121,9 @@ __global__ void add_pos_kernel(const float* __restrict__ x, const float* __restr
     const float4 b = __ldg(reinterpret_cast<const float4*>(pos) + (long long)src_t * (C / 4) + c4);
     float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
     if (drop_p16) {
-      const float sc = drop_scale(drop_p16);
-      const unsigned long long base = (unsigned long long)i * 4;
-      v.x = drop_keep(drop_seed, drop_p16, base + 0) ? v.x * sc : 0.f;
-      v.y = drop_keep(drop_seed, drop_p16, base + 1) ? v.y * sc : 0.f;
-      v.z = drop_keep(drop_seed, drop_p16, base + 2) ? v.z * sc : 0.f;
-      v.w = drop_keep(drop_seed, drop_p16, base + 3) ? v.w * sc : 0.f;
+      // mask row = (b, t), column = channel
+      drop_apply<4>(&v.x, drop_row_key(drop_seed, (unsigned long long)(i / (C / 4))), drop_p16, (uint32_t)(c4 * 4),
+                    drop_scale(drop_p16));
     }
     reinterpret_cast<float4*>(out)[i] = v;
   }
@@ -149,9 +138,9 @@ __global__ void add_pos_bwd_kernel(const float* __restrict__ dx, float* __restri
     float s = 0.f;
     const float sc = drop_p16 ? drop_scale(drop_p16) : 1.f;
     for (int b = 0; b < B; ++b) {
-      const unsigned long long idx = ((unsigned long long)b * T + t) * C + c;
-      const float g = dx[idx];
-      s += (!drop_p16 || drop_keep(drop_seed, drop_p16, idx)) ? g * sc : 0.f;
+      const unsigned long long rowi = (unsigned long long)b * T + t;
+      const float g = dx[rowi * C + c];
+      s += (!drop_p16 || drop_keep(drop_row_key(drop_seed, rowi), drop_p16, (uint32_t)c)) ? g * sc : 0.f;
     }
     atomicAdd(dpos + src_t * C + c, s);
   }

@@ -87,12 +87,7 @@ norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
         }
         y.x *= out_scale; y.y *= out_scale; y.z *= out_scale; y.w *= out_scale;
         if (drop_p16) {  // dropout on the normalised output (T5Stack final dropout, modeling_t5.py:1114)
-          const float sc = drop_scale(drop_p16);
-          const unsigned long long base = (unsigned long long)row * D + c;
-          y.x = drop_keep(drop_seed, drop_p16, base + 0) ? y.x * sc : 0.f;
-          y.y = drop_keep(drop_seed, drop_p16, base + 1) ? y.y * sc : 0.f;
-          y.z = drop_keep(drop_seed, drop_p16, base + 2) ? y.z * sc : 0.f;
-          y.w = drop_keep(drop_seed, drop_p16, base + 3) ? y.w * sc : 0.f;
+          drop_apply<4>(&y.x, drop_row_key(drop_seed, (unsigned long long)row), drop_p16, (uint32_t)c, drop_scale(drop_p16));
         }
         if (out)
           *reinterpret_cast<uint2*>(out + orow * D + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
@@ -133,12 +128,8 @@ norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const 
         const float4 xv = xr[lane + 32 * i];
         float4 gv = gr[lane + 32 * i];
         if (g_drop_p16) {  // the forward dropped the normalised output: the incoming gradient passes the same mask
-          const float sc = drop_scale(g_drop_p16);
-          const unsigned long long base = (unsigned long long)row * D + (lane + 32 * i) * 4;
-          gv.x = drop_keep(g_drop_seed, g_drop_p16, base + 0) ? gv.x * sc : 0.f;
-          gv.y = drop_keep(g_drop_seed, g_drop_p16, base + 1) ? gv.y * sc : 0.f;
-          gv.z = drop_keep(g_drop_seed, g_drop_p16, base + 2) ? gv.z * sc : 0.f;
-          gv.w = drop_keep(g_drop_seed, g_drop_p16, base + 3) ? gv.w * sc : 0.f;
+          drop_apply<4>(&gv.x, drop_row_key(g_drop_seed, (unsigned long long)row), g_drop_p16, (uint32_t)((lane + 32 * i) * 4),
+                        drop_scale(g_drop_p16));
         }
         const float4 wv = *reinterpret_cast<const float4*>(w + (lane + 32 * i) * 4);
         xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd; xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
@@ -167,12 +158,8 @@ norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const 
         if (dx_bf16) {
           // bf16 copy = the dY of the sub-layer below, whose output went through dropout before the residual add
           if (dxb_drop_p16) {
-            const float sc = drop_scale(dxb_drop_p16);
-            const unsigned long long base = (unsigned long long)row * D + (lane + 32 * i) * 4;
-            o.x = drop_keep(dxb_drop_seed, dxb_drop_p16, base + 0) ? o.x * sc : 0.f;
-            o.y = drop_keep(dxb_drop_seed, dxb_drop_p16, base + 1) ? o.y * sc : 0.f;
-            o.z = drop_keep(dxb_drop_seed, dxb_drop_p16, base + 2) ? o.z * sc : 0.f;
-            o.w = drop_keep(dxb_drop_seed, dxb_drop_p16, base + 3) ? o.w * sc : 0.f;
+            drop_apply<4>(&o.x, drop_row_key(dxb_drop_seed, (unsigned long long)row), dxb_drop_p16,
+                          (uint32_t)((lane + 32 * i) * 4), drop_scale(dxb_drop_p16));
           }
           *reinterpret_cast<uint2*>(dx_bf16 + (long long)row * D + (lane + 32 * i) * 4) =
               make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));

@@ -153,18 +153,31 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 constexpr uint32_t kSwizzleAtomBytes = 1024;
 
 // ---------------------------------------------------------------- dropout (counter-based, stateless)
-// keep(idx) = rnd16(seed, idx) >= p16 with p16 = round(p * 65536); kept values are scaled by 65536 / (65536 - p16).
-// Two consecutive elements share one 32-bit hash (murmur3 finaliser of the pair index), so forward and backward
-// regenerate the same mask from (seed, element index) and nothing is stored.  Reference semantics: nn.Dropout /
+// Element (r, c) of a 2-D tensor is kept iff a 16-bit hash of (seed, r, c) >= p16, p16 = round(p * 65536); kept values
+// are scaled by 65536 / (65536 - p16).  One 32-bit hash serves the two columns 2j, 2j+1 of a row, so forward and
+// backward regenerate the same mask from (seed, row, column) and nothing is stored.  Reference semantics: nn.Dropout /
 // F.dropout (modeling_t5.py:307,353,572-574,618,1019,1114; vit.py:20,22,49,54,126) — same distribution, own stream.
-__device__ __forceinline__ uint32_t drop_hash(uint32_t seed, unsigned long long idx) {
-  uint32_t x = (uint32_t)(idx >> 1) * 0x9E3779B1u + (uint32_t)(idx >> 33) * 0x85EBCA77u + seed;
-  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+__device__ __forceinline__ uint32_t drop_row_key(uint32_t seed, unsigned long long r) {
+  return seed + (uint32_t)r * 0x9E3779B1u + (uint32_t)(r >> 32) * 0x7F4A7C15u;
+}
+__device__ __forceinline__ uint32_t drop_pair_hash(uint32_t row_key, uint32_t c) {   // c = column, bit 0 ignored
+  uint32_t x = row_key + (c >> 1) * 0x85EBCA77u;
+  x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
   return x;
 }
-__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t p16, unsigned long long idx) {
-  const uint32_t h = drop_hash(seed, idx);
-  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= p16;
+__device__ __forceinline__ bool drop_keep(uint32_t row_key, uint32_t p16, uint32_t c) {
+  const uint32_t h = drop_pair_hash(row_key, c);
+  return ((c & 1) ? (h >> 16) : (h & 0xFFFFu)) >= p16;
+}
+// Apply to n (even) consecutive columns c0.. (c0 even) held in v[]: one hash per pair.
+template <int N>
+__device__ __forceinline__ void drop_apply(float* v, uint32_t row_key, uint32_t p16, uint32_t c0, float sc) {
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    const uint32_t h = drop_pair_hash(row_key, c0 + j);
+    v[j] = (h & 0xFFFFu) >= p16 ? v[j] * sc : 0.0f;
+    v[j + 1] = (h >> 16) >= p16 ? v[j + 1] * sc : 0.0f;
+  }
 }
 __device__ __forceinline__ uint32_t drop_salted(uint32_t seed, const uint32_t* salt) { return salt ? seed ^ __ldg(salt) : seed; }
 __device__ __forceinline__ float drop_scale(uint32_t p16) { return 65536.0f / (float)(65536u - p16); }

@@ -213,7 +213,7 @@ class Vid2SeqEngine:
 
     def _splits(self, n_out, k_out, red):
         tiles = ((n_out + 127) // 128) * ((k_out + 255) // 256)
-        s = max(1, min((red + 63) // 64 // 2, -(-296 // tiles)))
+        s = max(1, min((red + 63) // 64 // 4, -(-222 // tiles)))   # ~1.5 waves of tiles, >= 4 k-blocks per split
         return s
 
     # ------------------------------------------------------------------ sub-layers: forward
