@@ -105,10 +105,10 @@ int vc_attn_bwd(const vc_attn_bwd_args* args, void* stream);
 int vc_norm_fwd(int kind, const float* x, const float* w, const float* bias, void* out_bf16, float* out_f32, float* rstd,
                 float* mean, int M, int D, float eps, float out_scale, int rows_per_batch, int out_batch_stride,
                 int out_row_offset, uint32_t drop_seed, uint32_t drop_p16, void* stream);
-/* g = dL/dy fp32, read through the same row map (and through the forward's output-dropout mask g_drop_*).
+/* g = dL/dy (fp32, or bf16 when g_bf16), read through the same row map (and through the forward's output-dropout mask g_drop_*).
  * dx (+)= d/dx; dx_bf16 (optional) = bf16 copy of the final dx, masked by dxb_drop_* (the output dropout of the
  * sub-layer below, whose dY it is); dw/db accumulated with atomics (db only for kind 1; either may be NULL). */
-int vc_norm_bwd(int kind, const float* g, const float* x, const float* w, const float* rstd, const float* mean, float* dx,
+int vc_norm_bwd(int kind, const void* g, int g_bf16 /* g is bf16 instead of fp32 */, const float* x, const float* w, const float* rstd, const float* mean, float* dx,
                 void* dx_bf16, int accumulate_dx, float* dw, float* db, int M, int D, float scale, int rows_per_batch,
                 int g_batch_stride, int g_row_offset, uint32_t g_drop_seed, uint32_t g_drop_p16, uint32_t dxb_drop_seed,
                 uint32_t dxb_drop_p16, void* stream);

@@ -210,7 +210,7 @@ class TorchOps:
                  rows_per_batch=0, g_batch_stride=0, g_row_offset=0, g_drop=NO_DROP, dxb_drop=NO_DROP):
         M, D = x.shape
         rows = self._rows(M, rows_per_batch, g_batch_stride, g_row_offset, x.device)
-        gg = g.view(-1, D)[rows] * scale
+        gg = g.view(-1, D)[rows].float() * scale
         if g_drop[1]:
             gg = gg * drop_mask(g_drop, _idx(gg.shape, gg.device))
         mu = mean[:, None] if kind == 1 else 0.0

@@ -203,7 +203,7 @@ def test_norms(cuda_ops, torch_ops, kind, D):
         dxb = torch.zeros(M, D, device=DEV, dtype=torch.bfloat16)
         dw = torch.zeros(D, device=DEV)
         db = torch.zeros(D, device=DEV)
-        ops.norm_bwd(kind, gy, x, w, rstd, mean, dx=dx, dx_bf16=dxb, accumulate_dx=True, dw=dw, db=db if kind else None,
+        ops.norm_bwd(kind, gy if kind else gy.bfloat16(), x, w, rstd, mean, dx=dx, dx_bf16=dxb, accumulate_dx=True, dw=dw, db=db if kind else None,
                      scale=0.5, rows_per_batch=L, g_batch_stride=E, g_row_offset=T)
         outs.append((ob, of, rstd, mean, dx, dxb, dw, db))
     a, r = outs

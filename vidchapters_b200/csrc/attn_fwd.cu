@@ -188,6 +188,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float* bk = brow + k0 + c * 32;
         const int tq = q_abs - k0 - c * 32;  // column i is causally masked iff i > tq
         tmem_ld_wait();
+        // s2 = min(acc*scale*log2e + bias*log2e, pen[k]) (+ causal) is written back to TMEM so that pass 2 only has to
+        // subtract the max and exponentiate (no second bias / ceiling lookup).
         if (causal_tile) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -197,6 +199,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int e = 0; e < 4; ++e) {
               float s2 = fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]);
               s2 = (i + e > tq) ? fminf(s2, kMasked) : s2;
+              v[i + e] = s2;
               m_tile = fmaxf(m_tile, s2);
             }
           }
@@ -206,10 +209,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const float4 pe = pen4[i >> 2];
             const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) m_tile = fmaxf(m_tile, fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]));
+            for (int e = 0; e < 4; ++e) {
+              v[i + e] = fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]);
+              m_tile = fmaxf(m_tile, v[i + e]);
+            }
           }
         }
+        tmem_st32(tmem_S + lane_off + c * 32, v);
       }
+      tmem_st_wait();
       // Integer running max (log2 domain): every rescale factor is an exact power of two, so the bf16 rounding of
       // P = 2^(s2 - m) does not depend on the tiling / on when the maximum was discovered.
       m_tile = ceilf(m_tile);
@@ -221,37 +229,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int c = 0; c < 4; ++c) {
         float v[32];
         tmem_ld32(tmem_S + lane_off + c * 32, v);
-        const float4* pen4 = reinterpret_cast<const float4*>(sPen + k0 + c * 32);
-        const float* bk = brow + k0 + c * 32;
-        const int tq = q_abs - k0 - c * 32;
         tmem_ld_wait();
         // the normaliser l uses the un-dropped probabilities (dropout acts on softmax's output)
-        if (causal_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 pe = pen4[i >> 2];
-            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float s2 = fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]);
-              s2 = (i + e > tq) ? fminf(s2, kMasked) : s2;
-              const float pv = fast_exp2(s2 - m_new);
-              l_tile += pv;
-              v[i + e] = pv;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 pe = pen4[i >> 2];
-            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float pv = fast_exp2(fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]) - m_new);
-              l_tile += pv;
-              v[i + e] = pv;
-            }
-          }
+        for (int i = 0; i < 32; ++i) {
+          const float pv = fast_exp2(v[i] - m_new);
+          l_tile += pv;
+          v[i] = pv;
         }
         if (p.drop_p16) {
           // mask row = (b, h, q), column = k

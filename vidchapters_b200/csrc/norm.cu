@@ -100,9 +100,9 @@ norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
 // Backward.  g = dL/dy (fp32, read through the same RowMap as the forward output), y = ((x-mean)*rstd*w + b)*scale.
 //   dxhat = g*w*scale;  dx = rstd*(dxhat - mean(dxhat) [LN only] - xhat*mean(dxhat*xhat));  dx_accum (+)= dx
 //   dw += sum_rows g*xhat*scale;  db += sum_rows g*scale
-template <bool LAYERNORM>
+template <bool LAYERNORM, bool G_BF16>
 __global__ void __launch_bounds__(256)
-norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
+norm_bwd_kernel(const void* __restrict__ g_raw, const float* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ rstd_in, const float* __restrict__ mean_in, float* __restrict__ dx,
                 __nv_bfloat16* __restrict__ dx_bf16, int accumulate_dx, float* __restrict__ dw, float* __restrict__ db,
                 int M, int D, float scale, RowMap map, uint32_t g_drop_seed_in, uint32_t g_drop_p16, uint32_t dxb_drop_seed_in,
@@ -117,7 +117,7 @@ norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const 
   for (int i = 0; i < kMaxV4; ++i) { dw_acc[i] = make_float4(0, 0, 0, 0); db_acc[i] = make_float4(0, 0, 0, 0); }
   for (int row = blockIdx.x * (blockDim.x >> 5) + warp; row < M; row += warps_total) {
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
-    const float4* gr = reinterpret_cast<const float4*>(g + map(row) * D);
+    const long long grow = map(row);
     const float rstd = rstd_in[row];
     const float mean = LAYERNORM ? mean_in[row] : 0.f;
     float4 xh[kMaxV4], dh[kMaxV4];
@@ -126,7 +126,13 @@ norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, const 
     for (int i = 0; i < kMaxV4; ++i) {
       if (i < nv) {
         const float4 xv = xr[lane + 32 * i];
-        float4 gv = gr[lane + 32 * i];
+        float4 gv;
+        if (G_BF16) {
+          const uint2 gb = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g_raw) + grow * D)[lane + 32 * i];
+          gv = make_float4(bf16_lo(gb.x), bf16_hi(gb.x), bf16_lo(gb.y), bf16_hi(gb.y));
+        } else {
+          gv = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g_raw) + grow * D)[lane + 32 * i];
+        }
         if (g_drop_p16) {  // the forward dropped the normalised output: the incoming gradient passes the same mask
           drop_apply<4>(&gv.x, drop_row_key(g_drop_seed, (unsigned long long)row), g_drop_p16, (uint32_t)((lane + 32 * i) * 4),
                         drop_scale(g_drop_p16));
@@ -219,7 +225,7 @@ extern "C" int vc_norm_fwd(int kind, const float* x, const float* w, const float
   return VC_OK;
 }
 
-extern "C" int vc_norm_bwd(int kind, const float* g, const float* x, const float* w, const float* rstd, const float* mean,
+extern "C" int vc_norm_bwd(int kind, const void* g, int g_bf16, const float* x, const float* w, const float* rstd, const float* mean,
                            float* dx, void* dx_bf16, int accumulate_dx, float* dw, float* db, int M, int D, float scale,
                            int rows_per_batch, int g_batch_stride, int g_row_offset, uint32_t g_drop_seed, uint32_t g_drop_p16,
                            uint32_t dxb_drop_seed, uint32_t dxb_drop_p16, void* stream) {
@@ -227,12 +233,13 @@ extern "C" int vc_norm_bwd(int kind, const float* g, const float* x, const float
   VC_CHECK(kind == 0 || kind == 1, "vc_norm_bwd: kind 0=rms 1=layernorm");
   RowMap map{rows_per_batch, g_batch_stride, g_row_offset};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (kind == 0)
-    norm_bwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map,
-                                                         g_drop_seed, g_drop_p16, dxb_drop_seed, dxb_drop_p16, drop_salt_ptr());
-  else
-    norm_bwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map,
-                                                         g_drop_seed, g_drop_p16, dxb_drop_seed, dxb_drop_p16, drop_salt_ptr());
+#define VC_NB(LN, GB)                                                                                              \
+  norm_bwd_kernel<LN, GB><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, \
+                                                        db, M, D, scale, map, g_drop_seed, g_drop_p16, dxb_drop_seed,   \
+                                                        dxb_drop_p16, drop_salt_ptr())
+  if (kind == 0) { if (g_bf16) VC_NB(false, true); else VC_NB(false, false); }
+  else           { if (g_bf16) VC_NB(true, true); else VC_NB(true, false); }
+#undef VC_NB
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -301,7 +301,7 @@ class Vid2SeqEngine:
         if sp.b1:
             ops.colsum_bf16(dact, self.gv(sp.b1))
         self._wgrad(dact, r["h"], sp.w1)
-        dh = ws["dh"][:M * D].view(M, D)
+        dh = ws["dhb"][:M * D].view(M, D)
         ops.gemm(dact, self.pb(sp.w1), dh, b_mn=True)
         ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
                      accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b), dxb_drop=next_drop)
@@ -328,7 +328,7 @@ class Vid2SeqEngine:
         if sp.qkv_b:
             ops.colsum_bf16(dqkv, self.gv(sp.qkv_b))
         self._wgrad(dqkv, r["h"], sp.qkv_w, rows=3 * inner)
-        dh = ws["dh"][:M * D].view(M, D)
+        dh = ws["dhb"][:M * D].view(M, D)
         ops.gemm(dqkv, self.pb(sp.qkv_w, 3 * inner), dh, b_mn=True)
         ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
                      accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b), dxb_drop=next_drop)
@@ -351,7 +351,7 @@ class Vid2SeqEngine:
                      drop=r["d_attn"])
         ops.cast_f32_bf16(dq_acc, dq)
         self._wgrad(dq, r["h"], sp.q_w)
-        dh = ws["dh"][:M * D].view(M, D)
+        dh = ws["dhb"][:M * D].view(M, D)
         ops.gemm(dq, self.pb(sp.q_w), dh, b_mn=True)
         ops.norm_bwd(0, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], None, dx=dx, dx_bf16=dxb, accumulate_dx=True,
                      dw=self.gv(sp.norm_w), dxb_drop=next_drop)
@@ -492,6 +492,7 @@ class Vid2SeqEngine:
         inner_max = max(self.inner, self.C)
         ws = dict(
             dact=self._e(Mmax * max(self.dff, self.mlp), dtype=bf), dh=self._e(Mmax * max(d, self.C)),
+            dhb=self._e(Mmax * max(d, self.C), dtype=bf),   # d(normed activations): bf16 is enough, halves the traffic
             dctx=self._e(Mmax * inner_max, dtype=bf), dqkv=self._e(Mmax * 3 * inner_max, dtype=bf),
             dq_acc=self._e(Mmax * inner_max), delta=self._e(B * max(self.H, self.Hv) * max(T, L, S)),
             dkv=self._e(B * E * 2 * self.inner, dtype=bf))

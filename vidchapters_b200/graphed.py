@@ -40,7 +40,6 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         model._refresh_shadow()            # outside the graph: the fused optimiser keeps the shadow valid afterwards
         model._shadow_valid = True
-        optimizer.zero_grad(set_to_none=True)   # so the captured backward starts by zeroing the flat gradient buffer
         ops = model.engine.ops
         n0 = ops.launches
         with torch.cuda.graph(self.graph):
@@ -49,13 +48,17 @@ class GraphedTrainStep:
         self.replays = 0
 
     def _fwd_bwd(self):
+        """Forward + backward through the engine directly (no autograd engine inside the capture: its cross-stream
+        bookkeeping for leaf tensors is not capture-safe); gradients land in the flat buffer that `p.grad` views."""
         m = self.model
-        it = {"input_ids": self.input_ids, "attention_mask": self.input_ids != 0}
-        ot = {"input_ids": self.output_ids, "attention_mask": self.output_ids != 0}
-        loss_dict, _ = m(self.video, it, ot)
-        self.optimizer.zero_grad(set_to_none=True)
-        loss_dict["loss"].backward()
-        return loss_dict["loss"].detach()
+        eng = m.engine
+        eng.drop_rates = dict(vis=m.vis_drop, enc=m.enc_drop, dec=m.dec_drop)
+        ids, out = self.input_ids, self.output_ids
+        loss, ectx = eng.forward(self.video, ids, ids != 0, out, out != 0, training=m.training)
+        eng.zero_grad()
+        eng.backward(ectx)
+        m._end_backward()          # host-side: make every Parameter's .grad a view of the flat gradient buffer
+        return loss.view(())
 
     def __call__(self, video=None, input_ids=None, output_ids=None):
         """Copies the batch (host pinned or device tensors) into the static buffers, replays forward+backward, runs the

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvidchap.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class GemmArgs(C.Structure):
@@ -70,7 +70,7 @@ SIGNATURES = {
     "vc_attn_fwd": [C.POINTER(AttnArgs), P],
     "vc_attn_bwd": [C.POINTER(AttnBwdArgs), P],
     "vc_norm_fwd": [I, P, P, P, P, P, P, P, I, I, F, F, I, I, I, U, U, P],
-    "vc_norm_bwd": [I, P, P, P, P, P, P, P, I, P, P, I, I, F, I, I, I, U, U, U, U, P],
+    "vc_norm_bwd": [I, P, I, P, P, P, P, P, P, I, P, P, I, I, F, I, I, I, U, U, U, U, P],
     "vc_embed_fwd": [P, P, P, I, I, I, U, U, P],
     "vc_embed_bwd": [P, P, P, I, I, I, U, U, P],
     "vc_prepare_targets": [P, P, P, P, I, I, I64, P],

@@ -166,8 +166,9 @@ class CudaOps:
                  rows_per_batch=0, g_batch_stride=0, g_row_offset=0, g_drop=NO_DROP, dxb_drop=NO_DROP):
         _chk_cuda(g, x, w, rstd, mean, dx, dx_bf16, dw, db)
         M, D = x.shape
-        assert g.dtype == torch.float32 and dx.dtype == torch.float32 and x.is_contiguous() and dx.is_contiguous()
-        _lib.check(self.lib.vc_norm_bwd(kind, _ptr(g), _ptr(x), _ptr(w), _ptr(rstd), _ptr(mean), _ptr(dx), _ptr(dx_bf16),
+        assert g.dtype in (torch.float32, torch.bfloat16) and g.is_contiguous()
+        assert dx.dtype == torch.float32 and x.is_contiguous() and dx.is_contiguous()
+        _lib.check(self.lib.vc_norm_bwd(kind, _ptr(g), int(g.dtype == torch.bfloat16), _ptr(x), _ptr(w), _ptr(rstd), _ptr(mean), _ptr(dx), _ptr(dx_bf16),
                                         int(accumulate_dx), _ptr(dw), _ptr(db), M, D, scale, rows_per_batch,
                                         g_batch_stride, g_row_offset, g_drop[0], g_drop[1], dxb_drop[0], dxb_drop[1],
                                         self._stream()))
