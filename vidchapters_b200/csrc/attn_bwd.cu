@@ -47,11 +47,12 @@ struct AttnBwdParams {
 
 constexpr int kBwdSmemTiles = 16384 * 2 /*K,V*/ + 2 * 16384 /*Q ring*/ + 2 * 16384 /*dO ring*/ + 32768 /*P*/ + 32768 /*dS*/;
 constexpr int kBwdRelMax = 2304;  // floats per relative-position window: ceil(Lq/128)*128 + 128 <= 2304 (Lq <= 2176)
-constexpr int kAttnBwdSmem = kBwdSmemTiles + 2 * kBwdRelMax * 4 + 512 + 256;  // + d(bias) window + bias window + key ceilings
+constexpr int kAttnBwdSmem = kBwdSmemTiles + 32768 + 2 * kBwdRelMax * 4 + 512 + 256;  // + dQ staging + d(bias)/bias windows + key ceilings
 
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + 16384;
@@ -59,7 +60,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sDO = sQ + 2 * 16384;   // [2]
   uint8_t* sP = sDO + 2 * 16384;   // 32 KB
   uint8_t* sDS = sP + 32768;       // 32 KB
-  float* s_rel = reinterpret_cast<float*>(sDS + 32768);   // d(bias) window of this key tile: slot (k - k0) + (Lq - 1 - q)
+  uint8_t* sDQ = sDS + 32768;      // 32 KB: dQ_i staged as two 128-row x 32-col fp32 boxes (SWIZZLE_128B) for TMA reduce-add
+  float* s_rel = reinterpret_cast<float*>(sDQ + 32768);   // d(bias) window of this key tile: slot (k - k0) + (Lq - 1 - q)
   float* s_bias = s_rel + kBwdRelMax;       // bias(k - q) * log2e, same slot indexing
   float* s_pen = s_bias + kBwdRelMax;   // per-key ceiling of this tile: +inf attend | kBMasked | -inf out of range
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_pen + 128);
@@ -78,7 +80,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) __trap();
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
     mbar_init(s_full, 1);
@@ -264,22 +266,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // dS(i) fully consumed before anyone rewrites it for tile i+1
       }
-      // ---- dQ_i: TMEM -> fp32 atomics (this warp: its lane quarter, 32 of the 64 columns)
+      // ---- dQ_i: TMEM -> swizzled smem staging -> ONE TMA reduce-add per 32-column half (whole 128-byte lines into the
+      // fp32 dQ accumulator) instead of 2048 scattered 16-byte atomics per tile.
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
       {
         float v[32];
         tmem_ld32(tDQ + lane_off + half * 32, v);
+        if (ct == 0) bulk_wait_read0();               // the previous tile's reduce has finished reading the staging
+        asm volatile("bar.sync 2, 256;" ::: "memory");
         tmem_ld_wait();
-        if (q_ok) {
-          float4* dst = reinterpret_cast<float4*>(p.dq_acc + ((long long)b * p.Lq + q) * p.ld_dq + h * kBD + half * 32);
+        uint8_t* drow_q = sDQ + half * 16384 + r * 128;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) atomicAdd(dst + g, make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]));
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(drow_q + ((g ^ (r & 7)) << 4)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (ct == 0) {   // rows past Lq carry zeros (p = 0 there); rows past the tensor are clipped by TMA
+          tma_reduce_add_2d(&tmDQ, sDQ, h * kBD, b * p.Lq + q0);
+          tma_reduce_add_2d(&tmDQ, sDQ + 16384, h * kBD + 32, b * p.Lq + q0);
+          bulk_commit();
         }
       }
       tc_fence_before();
       mbar_arrive(dq_read);
     }
+    if (ct == 0) bulk_wait_all();
     // ---- dV, dK: rows = keys of this tile.  (The last dq_full wait above also covers the final dV/dK MMAs.)
     const int kk = k0 + r;
     if (nqt > 0) {
@@ -378,8 +390,10 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
                                                                  a->delta, a->dq_acc, a->ld_dq, f->B, f->H, f->Lq);
     VC_CUDA(cudaGetLastError());
   }
-  CUtensorMap tmQ, tmK, tmV, tmDO;
+  CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
   int s;
+  VC_CHECK(((uintptr_t)a->dq_acc & 15) == 0, "vc_attn_bwd: dq_acc must be 16-byte aligned");
+  if ((s = make_tmap_2d_ex(&tmDQ, a->dq_acc, 4, (uint64_t)f->H * 64, (uint64_t)f->B * f->Lq, a->ld_dq, 32, 128, 128)) != VC_OK) return s;
   if ((s = make_tmap_3d(&tmQ, f->q, f->ldq, f->Lq, f->B, f->ldq, (uint64_t)f->Lq * f->ldq, 64, kBT)) != VC_OK) return s;
   if ((s = make_tmap_3d(&tmK, f->k, f->ldk, f->Lk, f->B, f->ldk, (uint64_t)f->Lk * f->ldk, 64, kBT)) != VC_OK) return s;
   if ((s = make_tmap_3d(&tmV, f->v, f->ldv, f->Lk, f->B, f->ldv, (uint64_t)f->Lk * f->ldv, 64, kBT)) != VC_OK) return s;
@@ -400,7 +414,7 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
     attr = true;
   }
   dim3 grid((f->Lk + kBT - 1) / kBT, f->H, f->B);
-  attn_bwd_kernel<<<grid, 320, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, p);
+  attn_bwd_kernel<<<grid, 320, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
