@@ -109,11 +109,17 @@ def _attn_case(B, H, Lq, Lk, causal, with_bias, with_mask, scale, self_attn, see
         k = v = (torch.randn(B * Lk, 2 * inner, generator=g) * 0.5).to(DEV).bfloat16()
         cols = dict(q_col=0, k_col=0, v_col=inner)
     bias = (torch.randn(H, Lq + Lk - 1, generator=g)).to(DEV) if with_bias else None
+    if with_bias == "t5":   # bucketed like T5: constant beyond +-128 positions -> uniform tiles take the kernels' fast path
+        bias = torch.randn(33, H, generator=g).to(DEV)[_t5ish_lut(Lq, Lk).long()].t().contiguous()
     kmask = None
     if with_mask:
         lens = torch.randint(max(1, Lk // 2), Lk + 1, (B,), generator=g)
         kmask = (torch.arange(Lk)[None, :] < lens[:, None]).to(torch.uint8).to(DEV)
     return q, k, v, cols, bias, kmask
+
+
+def _t5ish_lut(Lq, Lk):
+    return (((torch.arange(Lq + Lk - 1) - (Lq - 1)).clamp(-128, 128) + 128) // 8).to(torch.int32).to(DEV)
 
 
 ATTN_CASES = [
@@ -125,6 +131,9 @@ ATTN_CASES = [
     (1, 4, 37, 130, False, True, True, 1.0, False),          # ragged
     (1, 2, 10, 10, False, False, False, 0.125, True),        # tiny (config 1 ViT)
     (1, 2, 32, 32, True, True, False, 1.0, True),
+    (2, 4, 640, 640, False, "t5", False, 1.0, True),         # bucketed bias, all keys attend: constant-bias fast tiles
+    (2, 4, 600, 600, False, "t5", True, 1.0, True),          # + ragged tail and key masks
+    (1, 4, 500, 500, True, "t5", False, 1.0, True),          # + causal
 ]
 
 
@@ -158,6 +167,8 @@ def test_attn_bwd(cuda_ops, torch_ops, case):
     lut = None
     if wb:
         lut = (torch.arange(Lq + Lk - 1) // 7).to(torch.int32).to(DEV)  # any monotone bucketisation exercises both paths
+        if wb == "t5":
+            lut = _t5ish_lut(Lq, Lk)
     res = []
     for ops in (cuda_ops, torch_ops):
         delta = torch.zeros(B, H, Lq, device=DEV)
@@ -316,7 +327,7 @@ def test_dropout_gemm_epilogue(cuda_ops, torch_ops):
         assert 0.05 < zeros < 0.6   # ~10% dropped (more with relu)
 
 
-@pytest.mark.parametrize("case", [ATTN_CASES[1], ATTN_CASES[2], ATTN_CASES[4]])
+@pytest.mark.parametrize("case", [ATTN_CASES[1], ATTN_CASES[2], ATTN_CASES[4], ATTN_CASES[7]])
 def test_dropout_attention(cuda_ops, torch_ops, case):
     B, H, Lq, Lk, causal, wb, wm, scale, sa = case
     q, k, v, cols, bias, kmask = _attn_case(B, H, Lq, Lk, causal, wb, wm, scale, sa, seed=8)

@@ -13,8 +13,9 @@ inner = H * 64
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "attn"):
     qkv = (torch.randn(B * L, 3 * inner, generator=g) * 0.5).to(dev).bfloat16()
-    bias = torch.randn(H, 2 * L - 1, generator=g).to(dev)
-    lens = torch.randint(L // 2, L + 1, (B,), generator=g)
+    lut = relative_position_bucket(torch.arange(2 * L - 1) - (L - 1), True).to(torch.int32).to(dev)
+    bias = torch.randn(32, H, generator=g).to(dev)[lut.long()].t().contiguous()   # T5 bucketed bias, as in the train step
+    lens = torch.randint(L // 2, L + 1, (B,), generator=g)                        # bench.py's ragged ASR lengths
     kmask = (torch.arange(L)[None] < lens[:, None]).to(torch.uint8).to(dev)
     out = torch.zeros(B * L, inner, device=dev, dtype=torch.bfloat16)
     lse = torch.zeros(B, H, L, device=dev)
@@ -23,7 +24,8 @@ if which in ("all", "attn"):
     delta = torch.zeros(B, H, L, device=dev); dq = torch.zeros(B * L, inner, device=dev)
     dqkv = torch.zeros(B * L, 3 * inner, device=dev, dtype=torch.bfloat16)
     db = torch.zeros(H, 2 * L - 1, device=dev)
-    lut = relative_position_bucket(torch.arange(2 * L - 1) - (L - 1), True).to(torch.int32).to(dev)
+    drop = (0xC0FFEE, 6554) if os.environ.get("PROFILE_DROPOUT", "1") == "1" else (0, 0)   # reference default p = 0.1
+    kw["drop"] = drop
     for _ in range(3):
         ops.attn_fwd(qkv, qkv, qkv, out=out, lse2=lse, **kw)
         ops.attn_bwd(qkv, qkv, qkv, out=out, lse2=lse, dout=dout, do_col=0, delta=delta, dq_acc=dq, dk=dqkv, dk_col=inner,

@@ -47,7 +47,7 @@ struct AttnBwdParams {
 
 constexpr int kBwdSmemTiles = 16384 * 2 /*K,V*/ + 2 * 16384 /*Q ring*/ + 2 * 16384 /*dO ring*/ + 32768 /*P*/ + 32768 /*dS*/;
 constexpr int kBwdRelMax = 2304;  // floats per relative-position window: ceil(Lq/128)*128 + 128 <= 2304 (Lq <= 2176)
-constexpr int kAttnBwdSmem = kBwdSmemTiles + 32768 + 2 * kBwdRelMax * 4 + 512 + 256;  // + dQ staging + d(bias)/bias windows + key ceilings
+constexpr int kAttnBwdSmem = kBwdSmemTiles + 32768 + 2 * kBwdRelMax * 4 + 512 + 512;  // + dQ staging + d(bias)/bias windows + key ceilings
 
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -73,6 +73,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* dq_full = bars + 7;
   uint64_t* dq_read = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  // per query tile: the bias over the whole (query tile x this key tile) window is not one value / not one bucket
+  int* s_nonuni_v = reinterpret_cast<int*>(bars + 10);   // [24]
+  int* s_nonuni_b = s_nonuni_v + 24;                      // [24]
+  int* s_anypen = s_nonuni_b + 24;                        // [1] some key of this tile is masked / out of range
+  int* s_tile_att = s_anypen + 1;                         // [1] some key of this tile attends
+  int* s_row_att = s_anypen + 2;                          // [1] some key of this batch row attends (causal: key 0 does)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -89,6 +95,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(dq_read, 256);
     fence_barrier_init();
   }
+  const int nqt_all = (p.Lq + kBT - 1) / kBT;
+  if (threadIdx.x < 51) s_nonuni_v[threadIdx.x] = 0;   // (all flag arrays)
+  __syncthreads();
   const int n_rel = p.Lq + kBT;  // relative positions touched by this CTA: (k - q + Lq - 1) - rel_base in [0, Lq+127)
   const int rel_base = k0;       // slot = (k - k0) + (Lq - 1 - q)
   if (p.dbias_rel)
@@ -100,17 +109,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       s_bias[i] = (brow_g && rel_base + i < p.Lq + p.Lk - 1) ? __ldg(brow_g + rel_base + i) * kBLog2e : 0.f;
     if (threadIdx.x < 128) {
       const int k = k0 + (int)threadIdx.x;
-      s_pen[threadIdx.x] = (k >= p.Lk) ? -INFINITY : ((p.kmask && p.kmask[(long long)b * p.Lk + k] == 0) ? kBMasked : INFINITY);
+      const float pen = (k >= p.Lk) ? -INFINITY : ((p.kmask && p.kmask[(long long)b * p.Lk + k] == 0) ? kBMasked : INFINITY);
+      s_pen[threadIdx.x] = pen;
+      if (pen != INFINITY) *s_anypen = 1;
+      else *s_tile_att = 1;
     }
+    if (!p.kmask) {
+      if (threadIdx.x == 0) *s_row_att = 1;
+    } else if (p.causal) {
+      if (threadIdx.x == 0 && p.kmask[(long long)b * p.Lk] != 0) *s_row_att = 1;
+    } else {
+      for (int i = threadIdx.x; i < p.Lk; i += blockDim.x)
+        if (p.kmask[(long long)b * p.Lk + i] != 0) *s_row_att = 1;
+    }
+  }
+  __syncthreads();
+  if (*s_tile_att == 0 && *s_row_att != 0) {
+    // Every key of this tile is masked (padding) while each query row attends to some other key: the tile's
+    // probabilities are exp2(finfo.min - lse) == 0 exactly, so dK = dV = 0 and it adds nothing to dQ / d(bias).
+    const int half = (threadIdx.x >> 7) & 1, r = threadIdx.x & 127, kk = k0 + r;
+    if (threadIdx.x < 256 && kk < p.Lk) {
+      uint4* d1 = reinterpret_cast<uint4*>(p.dv + ((long long)b * p.Lk + kk) * p.ld_dv + p.dv_col + h * kBD + half * 32);
+      uint4* d2 = reinterpret_cast<uint4*>(p.dk + ((long long)b * p.Lk + kk) * p.ld_dk + p.dk_col + h * kBD + half * 32);
+      for (int g = 0; g < 4; ++g) { d1[g] = make_uint4(0, 0, 0, 0); d2[g] = make_uint4(0, 0, 0, 0); }
+    }
+    return;
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Uniform-tile flags.  Query tile t touches window slots [max(w0,0), w0+254], w0 = Lq-128-128t.  With T5's buckets every
+  // tile further than 128 positions from the diagonal sees ONE bias value (one bucket): s2 = acc*scale + c without any
+  // per-element lookup, and d(bias) of the tile is one sum instead of 255 diagonal sums.
+  for (int idx = threadIdx.x; idx < nqt_all * 256; idx += blockDim.x) {
+    const int t = idx >> 8, w0 = p.Lq - kBT - t * kBT;
+    const int i = max(w0, 0) + 1 + (idx & 255);
+    if (i <= w0 + 254) {
+      if (s_bias[i] != s_bias[i - 1]) s_nonuni_v[t] = 1;
+      if (p.dbias_rel) {
+        const int gi = rel_base + i;
+        if (!p.bucket_lut || gi >= p.Lq + p.Lk - 1 || __ldg(p.bucket_lut + gi) != __ldg(p.bucket_lut + gi - 1)) s_nonuni_b[t] = 1;
+      }
+    }
+  }
+  __syncthreads();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
 
-  const int nqt_all = (p.Lq + kBT - 1) / kBT;
   const int qt0 = p.causal ? min(kt, nqt_all) : 0;  // causal: query tiles before the key tile see nothing of it
   const int nqt = nqt_all - qt0;
 
@@ -178,6 +224,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // indexed by k - k0; rows past Lq (zero-filled Q/dO, p forced to 0) clamp to slot 0 to stay inside the window
       const float* brow = s_bias + (q_ok ? (p.Lq - 1 - q) : 0);
       const bool causal_tile = p.causal && (k0 + kBT - 1 > q0);
+      // uniform over the CTA (flags per query tile): constant bias, every key attends, no causal edge
+      const bool fast = !causal_tile && (s_nonuni_v[qt0 + i] | *s_anypen) == 0;
+      const bool tile_sum = p.dbias_rel && !causal_tile && (s_nonuni_b[qt0 + i] | *s_anypen) == 0 && fast;
+      const float c_fast = s_bias[max(p.Lq - kBT - q0, 0) + 1] - lse2;
+      float ds_sum = 0.f;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -190,7 +241,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float* bk = brow + c * 32;
         const int tq = q - k0 - c * 32;  // column j is causally masked iff j > tq
         tmem_ld_wait();
-        if (causal_tile) {
+        if (fast) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sv[j] = fast_exp2(fmaf(sv[j], p.scale_log2e, c_fast));
+        } else if (causal_tile) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 pe = pen4[j >> 2];
@@ -229,6 +283,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 32; ++j) dp[j] = sv[j] * (dp[j] - delta);
         }
+        if (tile_sum) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ds_sum += dp[j];
+        } else if (p.dbias_rel) {
+          // d(bias)[k - q] of this warp's 32x32 block: element (row l', col j) lies on diagonal j - l'.  Lane L
+          // collects the diagonals congruent to L (mod 32): for each j one shuffle from lane (j - L) mod 32 brings it
+          // the element of diagonal L (j >= L) or L - 32 (j < L).  No shared-memory traffic, no load imbalance.
+          float a_pos = 0.f, a_neg = 0.f;
+          const int neg_l = 32 - lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float w = __shfl_sync(0xffffffffu, dp[j], neg_l + j);   // source lane taken modulo 32
+            if (j >= lane) a_pos += w; else a_neg += w;
+          }
+          const int slot = c * 32 - quarter * 32 + (p.Lq - 1 - q0) + lane;   // (k - k0) + (Lq - 1 - q) of diagonal +lane
+          if (slot >= 0 && a_pos != 0.f) atomicAdd(&s_rel[slot], a_pos);
+          if (slot >= 32 && a_neg != 0.f) atomicAdd(&s_rel[slot - 32], a_neg);
+        }
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
         uint8_t* drow = sDS + (c >> 1) * 16384 + r * 128;
 #pragma unroll
@@ -247,24 +319,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
-      // ---- d(bias)[k - q]: while the dV/dK/dQ MMAs run, thread ct sums diagonal (k-k0) - (q-q0) = ct - 128 of the
-      // finished dS tile straight from shared memory (bf16, scaled by `scale`) into ITS slot of the window — one owner
-      // per slot, so no atomics.  (The MMAs only read sDS; the next tile's writers are held by the named barrier.)
-      if (p.dbias_rel) {
-        mbar_wait(pds_full, i & 1);   // every compute thread has written its part of dS
-        const int dgl = ct - 128;     // diagonal, -127..127 (ct == 0 -> -128: empty)
-        if (ct > 0) {
-          const int r_lo = max(0, -dgl), r_hi = min(127, 127 - dgl);
-          float acc = 0.f;
-          for (int rr = r_lo; rr <= r_hi; ++rr) {
-            const int cidx = rr + dgl;
-            const uint8_t* e = sDS + (cidx >> 6) * 16384 + rr * 128 + ((((cidx & 63) >> 3) ^ (rr & 7)) << 4) + (cidx & 7) * 2;
-            acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(e));
-          }
-          const int slot = dgl + (p.Lq - 1 - q0);   // (k - k0) + (Lq - 1 - q)
-          if (slot >= 0) s_rel[slot] += acc * p.inv_scale;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // dS(i) fully consumed before anyone rewrites it for tile i+1
+      if (tile_sum) {
+        // one bucket for the whole tile: deposit the tile's total at one of its relative positions (k = k0, q = q0)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ds_sum += __shfl_xor_sync(0xffffffffu, ds_sum, o);
+        if (lane == 0) atomicAdd(&s_rel[p.Lq - 1 - q0], ds_sum);
       }
       // ---- dQ_i: TMEM -> swizzled smem staging -> ONE TMA reduce-add per 32-column half (whole 128-byte lines into the
       // fp32 dQ accumulator) instead of 2048 scattered 16-byte atomics per tile.

@@ -72,6 +72,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* o_full = bars + 9;
   uint64_t* o_read = bars + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  // Fast-path flags per 128-slot block: the bias changes inside the block / some key of the block is masked or out of
+  // range.  A key tile whose bias window is one constant and whose keys all attend (T5: every tile further than 128
+  // positions from the diagonal; cross-attention and the ViT: every full tile) needs no per-element bias / ceiling
+  // lookup: s2 = acc*scale + c.
+  int* sFlagB = reinterpret_cast<int*>(bars + 12);   // [16]
+  int* sFlagP = sFlagB + 16;                          // [16]
+  int* sLastKey = sFlagP + 16;                        // index of the last key that attends (-1: none)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -91,6 +98,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(o_read, 128);
     fence_barrier_init();
   }
+  if (threadIdx.x < 32) sFlagB[threadIdx.x] = 0;   // (covers sFlagP too)
+  if (threadIdx.x == 32) *sLastKey = -1;
+  __syncthreads();
   // stage this query tile's bias window (index k + 127 - r == (k - q + Lq - 1) - (Lq - 128 - q0)) and the key mask
   {
     const int win0 = p.bias_zero - 127 - q0 - qoff;  // global bias index of window slot 0 (may be negative: never used)
@@ -100,11 +110,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float* brow = p.bias_rel ? p.bias_rel + (long long)h * p.bias_len : nullptr;
     for (int i = threadIdx.x; i < lk_pad + 128; i += blockDim.x) {
       const int gi = win0 + i;
-      sBias[i] = (brow && gi >= 0 && gi < p.bias_len) ? __ldg(brow + gi) * kLog2e : 0.f;
+      const float val = (brow && gi >= 0 && gi < p.bias_len) ? __ldg(brow + gi) * kLog2e : 0.f;
+      sBias[i] = val;
+      if (brow && i > 0) {
+        const float prev = (gi - 1 >= 0 && gi - 1 < p.bias_len) ? __ldg(brow + gi - 1) * kLog2e : 0.f;
+        if (val != prev) sFlagB[i >> 7] = 1;
+      }
     }
     const uint8_t* mrow = p.kmask ? p.kmask + (long long)b * p.Lk : nullptr;
-    for (int i = threadIdx.x; i < lk_pad; i += blockDim.x)
-      sPen[i] = (i >= p.Lk) ? -INFINITY : ((mrow && mrow[i] == 0) ? kMasked : INFINITY);
+    for (int i = threadIdx.x; i < lk_pad; i += blockDim.x) {
+      const float pen = (i >= p.Lk) ? -INFINITY : ((mrow && mrow[i] == 0) ? kMasked : INFINITY);
+      sPen[i] = pen;
+      if (pen != INFINITY) sFlagP[i >> 7] = 1;
+      else atomicMax(sLastKey, i);
+    }
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -117,6 +136,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // number of key tiles this query tile visits (causal: skip tiles entirely above the diagonal)
   int nkt = (p.Lk + kTK - 1) / kTK;
   if (p.causal) nkt = min(nkt, (q0 + qoff + kTQ - 1) / kTK + 1);
+  // Trailing key tiles made only of masked (padding) keys contribute exp2(finfo.min - m) == 0 exactly to every row as
+  // long as the row attends to at least one key (key 0 of a padded sequence always does; causal rows see key 0), so
+  // they are skipped.  With no attended key at all the reference degenerates to a uniform softmax: keep every tile.
+  if (*sLastKey >= 0 && (!p.causal || sPen[0] == INFINITY)) nkt = min(nkt, *sLastKey / kTK + 1);
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -179,7 +202,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       // ---- pass 1: row max of s2 over the tile.  s2 = min(acc*scale*log2e + bias*log2e, pen[k]); causal tiles add k<=q.
       const bool causal_tile = p.causal && (k0 + kTK - 1 > q0 + qoff);   // uniform: only tiles touching the diagonal
+      // uniform over the CTA: the tile's whole bias window is one value and every key attends
+      const bool fast = !causal_tile && (sFlagB[j] | sFlagB[j + 1] | sFlagP[j]) == 0;
+      const float cb = sBias[k0 + 127];
       float m_tile = -INFINITY;
+      if (fast) {
+#pragma unroll 1
+        for (int c = 0; c < 4; c += 2) {
+          float v[32], w[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld32(tmem_S + lane_off + c * 32 + 32, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, fmaxf(v[i], w[i]));
+        }
+        m_tile = fmaf(m_tile, p.scale_log2e, cb);   // scale > 0: max commutes with the affine map
+      } else {
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float v[32];
@@ -218,6 +256,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st32(tmem_S + lane_off + c * 32, v);
       }
       tmem_st_wait();
+      }
       // Integer running max (log2 domain): every rescale factor is an exact power of two, so the bf16 rounding of
       // P = 2^(s2 - m) does not depend on the tiling / on when the maximum was discovered.
       m_tile = ceilf(m_tile);
@@ -225,6 +264,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float corr = fast_exp2(m_run - m_new);  // m_run=-inf on first tile -> 0
       // ---- pass 2: p = exp2(s2 - m_new), write bf16 P (swizzled, K-major A operand), row sum
       float l_tile = 0.0f;
+      // fast tiles still hold the raw accumulator: one FMA folds scale, bias and the max; slow tiles hold s2
+      const float e_mul = fast ? p.scale_log2e : 1.0f;
+      const float e_add = fast ? cb - m_new : -m_new;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float v[32];
@@ -233,7 +275,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // the normaliser l uses the un-dropped probabilities (dropout acts on softmax's output)
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float pv = fast_exp2(v[i] - m_new);
+          const float pv = fast_exp2(fmaf(v[i], e_mul, e_add));
           l_tile += pv;
           v[i] = pv;
         }
@@ -322,11 +364,12 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   p.bias_len = a->bias_len > 0 ? a->bias_len : a->Lq + a->Lk - 1;
   VC_CHECK(a->Lk <= kAttnMaxLk, "vc_attn_fwd: Lk=%d exceeds the %d keys the bias/mask staging supports", a->Lk, kAttnMaxLk);
   const int lk_pad = ((a->Lk + kTK - 1) / kTK) * kTK;
-  const int smem_bytes = kAttnFwdTiles + (lk_pad + 128) * 4 + lk_pad * 4 + 128;
+  VC_CHECK(a->scale > 0.f, "vc_attn_fwd: scale must be positive");
+  const int smem_bytes = kAttnFwdTiles + (lk_pad + 128) * 4 + lk_pad * 4 + 256;
   static bool attr = false;
   if (!attr) {
     VC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kAttnFwdTiles + (kAttnMaxLk + 128) * 4 + kAttnMaxLk * 4 + 128));
+                                 kAttnFwdTiles + (kAttnMaxLk + 128) * 4 + kAttnMaxLk * 4 + 256));
     attr = true;
   }
   dim3 grid((a->Lq + kTQ - 1) / kTQ, a->H, a->B);

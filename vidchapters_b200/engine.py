@@ -480,9 +480,22 @@ class Vid2SeqEngine:
         return loss, ctx
 
     # ------------------------------------------------------------------ backward
-    def backward(self, ctx, grad_loss: Optional[torch.Tensor] = None, grad_video: Optional[torch.Tensor] = None):
+    def decoder_grad_range(self):
+        """[lo, hi) of flat_g that is final once the head + decoder backward (phase 1) is done: every decoder
+        parameter.  (`shared` still receives the encoder's embedding gradient in phase 2.)"""
+        names = [n for n in self.layout if n.startswith("t5_model.decoder.")]
+        lo = min(self.layout[n][0] for n in names)
+        hi = max(self.layout[n][0] + self.layout[n][2] for n in names)
+        return lo, hi
+
+    def backward(self, ctx, grad_loss: Optional[torch.Tensor] = None, grad_video: Optional[torch.Tensor] = None,
+                 phase: Optional[int] = None):
         """Accumulates d(loss)/d(params) * grad_loss into flat_g.  Returns d/d(cached video) when the forward consumed
-        a cached visual-encoder output (so it can flow back to the pass that produced it), else None."""
+        a cached visual-encoder output (so it can flow back to the pass that produced it), else None.
+        phase=None runs everything; phase=1 runs head + decoder only (the decoder's gradients are then final and can be
+        all-reduced while phase=2, text encoder + visual encoder, runs)."""
+        if phase == 2:
+            return self._backward_phase2(ctx, grad_video)
         ops, d = self.ops, self.d
         bf = torch.bfloat16
         tape = ctx["tape"]
@@ -522,6 +535,20 @@ class Vid2SeqEngine:
             i -= 3
         ops.bias_fold(drel_d, ctx["lut_d"], self.g(self.dec_bias_name))
         ops.embed_bwd(ctx["dec_in"].view(-1), dy, self.g("t5_model.shared.weight"), drop=ctx["d_emb_d"])
+        ctx["_bwd_state"] = (dmem, i, ws)
+        if phase == 1:
+            return None
+        return self._backward_phase2(ctx, grad_video)
+
+    def _backward_phase2(self, ctx, grad_video):
+        ops, d = self.ops, self.d
+        bf = torch.bfloat16
+        tape = ctx["tape"]
+        B, T, L, S, E = ctx["B"], ctx["T"], ctx["L"], ctx["S"], ctx["E"]
+        dmem, i, ws = ctx.pop("_bwd_state")
+
+        def out_drop(j):
+            return tape[j]["d_out"] if j >= 0 else NO_DROP
         if grad_video is not None and self.use_video:
             dmem.view(B, E, d)[:, :T].add_(grad_video.reshape(B, T, d).to(dmem.dtype))
         # ---- text encoder

@@ -42,12 +42,29 @@ class GraphedTrainStep:
         model._shadow_valid = True
         ops = model.engine.ops
         n0 = ops.launches
-        with torch.cuda.graph(self.graph):
-            self.loss = self._fwd_bwd()
-        self.launches_per_replay = ops.launches - n0   # libvidchap kernels inside the captured graph
+        self.world = getattr(optimizer, "world_size", 1)
+        self.graph2 = None
+        if self.world > 1:
+            # data parallel: two graphs, so the decoder's gradients (final after phase 1) are all-reduced by NCCL while
+            # the encoder / visual-encoder backward (phase 2) still runs
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd(phase=1)
+            self.graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
+                self._bwd_phase2()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd()
+        self.launches_per_replay = ops.launches - n0   # libvidchap kernels inside the captured graph(s)
         self.replays = 0
 
-    def _fwd_bwd(self):
+    def _bwd_phase2(self):
+        eng = self.model.engine
+        eng.backward(self._ectx, phase=2)
+        self._ectx = None
+        self.model._end_backward()
+
+    def _fwd_bwd(self, phase=None):
         """Forward + backward through the engine directly (no autograd engine inside the capture: its cross-stream
         bookkeeping for leaf tensors is not capture-safe); gradients land in the flat buffer that `p.grad` views."""
         m = self.model
@@ -56,8 +73,11 @@ class GraphedTrainStep:
         ids, out = self.input_ids, self.output_ids
         loss, ectx = eng.forward(self.video, ids, ids != 0, out, out != 0, training=m.training)
         eng.zero_grad()
-        eng.backward(ectx)
-        m._end_backward()          # host-side: make every Parameter's .grad a view of the flat gradient buffer
+        eng.backward(ectx, phase=phase)
+        if phase == 1:
+            self._ectx = ectx      # phase 2 is captured into the second graph
+        else:
+            m._end_backward()      # host-side: make every Parameter's .grad a view of the flat gradient buffer
         return loss.view(())
 
     def __call__(self, video=None, input_ids=None, output_ids=None):
@@ -75,5 +95,17 @@ class GraphedTrainStep:
         self.graph.replay()
         self.replays += 1
         self.model.engine.ops.launches += self.launches_per_replay
-        self.optimizer.step()
+        if self.graph2 is None:
+            self.optimizer.step()
+            return self.loss
+        eng = self.model.engine
+        lo, hi = eng.decoder_grad_range()
+        pg = self.optimizer.pg
+        w1 = torch.distributed.all_reduce(eng.flat_g[lo:hi], group=pg, async_op=True)   # overlaps graph2 below
+        self.graph2.replay()
+        w2 = torch.distributed.all_reduce(eng.flat_g[:lo], group=pg, async_op=True)
+        w3 = torch.distributed.all_reduce(eng.flat_g[hi:], group=pg, async_op=True)
+        for w in (w1, w2, w3):
+            w.wait()
+        self.optimizer.step(grads_already_reduced=True)
         return self.loss

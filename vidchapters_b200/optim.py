@@ -34,12 +34,13 @@ class Vid2SeqAdam:
             elif p.grad is not None:
                 p.grad.zero_()
 
-    def step(self):
+    def step(self, grads_already_reduced: bool = False):
         eng = self.model.engine
         g = self.param_groups[0]
         grad_scale = 1.0
         if self.world_size > 1:
-            torch.distributed.all_reduce(eng.flat_g, group=self.pg)  # SUM over ranks; averaged by grad_scale below
+            if not grads_already_reduced:   # (GraphedTrainStep overlaps the all-reduce with the backward itself)
+                torch.distributed.all_reduce(eng.flat_g, group=self.pg)  # SUM over ranks; averaged by grad_scale below
             grad_scale = 1.0 / self.world_size
         self.last_grad_norm_sq = eng.optimizer_step(g["lr"], betas=g["betas"], eps=g["eps"],
                                                     clip_max_norm=self.clip_max_norm, grad_scale=grad_scale,
