@@ -24,10 +24,19 @@ _M32 = 0xFFFFFFFF
 _SALT = None   # optional device/host tensor XORed into every seed (mirrors vc_set_dropout_salt)
 
 
-def drop_mask(spec, idx: torch.Tensor) -> torch.Tensor:
-    """Float multiplier (0 or 65536/(65536-p16)) for every element of a tensor whose flat int64 indices are `idx`
-    (shape [..., C]): the counter-based hash of vidchapters_b200/csrc/ptx.cuh (row = flat // C, column = flat % C; one
-    32-bit hash per column pair, 16 bits per element)."""
+def _lane_mult(i: torch.Tensor) -> torch.Tensor:
+    """A[i] of vidchapters_b200/csrc/ptx.cuh::drop_lane_mult (fixed odd multiplier of in-block column i)."""
+    x = ((i + 1) * 0x9E3779B1) & _M32
+    x = x ^ (x >> 15)
+    x = (x * 0x85EBCA6B) & _M32
+    x = x ^ (x >> 13)
+    return x | 1
+
+
+def drop_mask(spec, idx: torch.Tensor, scaled: bool = True) -> torch.Tensor:
+    """Float multiplier (0 or 65536/(65536-p16); 0/1 with scaled=False) for every element of a tensor whose flat int64
+    indices are `idx` (shape [..., C]): the counter-based mask of vidchapters_b200/csrc/ptx.cuh (row = flat // C, column
+    = flat % C; one strong odd hash H per 32-column block, element value = top 16 bits of H * A[column % 32])."""
     seed, p16 = spec
     if p16 == 0:
         return torch.ones(idx.shape, dtype=torch.float32, device=idx.device)
@@ -36,14 +45,15 @@ def drop_mask(spec, idx: torch.Tensor) -> torch.Tensor:
     C = idx.shape[-1]
     row, col = idx // C, idx % C
     key = (seed + (row & _M32) * 0x9E3779B1 + ((row >> 32) & _M32) * 0x7F4A7C15) & _M32
-    x = (key + (col >> 1) * 0x85EBCA77) & _M32
+    x = (key + (col >> 5) * 0x85EBCA77) & _M32
     x = x ^ (x >> 15)
     x = (x * 0x2C1B3C6D) & _M32
     x = x ^ (x >> 12)
     x = (x * 0x297A2D39) & _M32
     x = x ^ (x >> 15)
-    r = torch.where((col & 1) == 1, x >> 16, x & 0xFFFF)
-    return (r >= p16).float() * (65536.0 / (65536.0 - p16))
+    h = x | 1
+    r = ((h * _lane_mult(col & 31)) & _M32) >> 16
+    return (r >= p16).float() * ((65536.0 / (65536.0 - p16)) if scaled else 1.0)
 
 
 def _idx(shape, device):
@@ -132,13 +142,16 @@ class TorchOps:
                          bias_zero if bias_len else None)
         kvr = kv_batch_rows or Lk
         vh = v[:, v_col:v_col + H * 64].float().reshape(B, kvr, H, 64)[:, :Lk].permute(0, 2, 1, 3)
-        dm = drop_mask(drop, _idx(s.shape, s.device)) if drop[1] else 1.0
+        # kernel rounding points: the kept probabilities are rounded to bf16 UNSCALED; 1/(1-p) multiplies the output
+        dm = drop_mask(drop, _idx(s.shape, s.device), scaled=False) if drop[1] else 1.0
+        sc = 65536.0 / (65536.0 - drop[1]) if drop[1] else 1.0
         if self.flash:
             s2 = s * math.log2(math.e)
             e = torch.exp2(s2 - torch.ceil(s2.max(-1, keepdim=True).values))
             o = ((e * dm).to(torch.bfloat16).float() @ vh) / e.sum(-1, keepdim=True)
+            o = o * sc if drop[1] else o
         else:
-            o = (torch.softmax(s, dim=-1) * dm).to(torch.bfloat16).float() @ vh
+            o = ((torch.softmax(s, dim=-1) * dm).to(torch.bfloat16).float() @ vh) * sc
         out[:, :H * 64].copy_(o.permute(0, 2, 1, 3).reshape(B * Lq, H * 64).to(out.dtype))
         if lse2 is not None:
             lse2.copy_(torch.logsumexp(s, dim=-1) * math.log2(math.e))
@@ -158,9 +171,10 @@ class TorchOps:
         if dm is not None:
             dp = dp * dm
         ds = p * (dp - dlt)
-        pb = (p if dm is None else p * dm).to(torch.bfloat16).float()
+        sc = 65536.0 / (65536.0 - drop[1]) if drop[1] else 1.0
+        pb = (p if dm is None else p * (dm > 0)).to(torch.bfloat16).float()   # masked, unscaled (as the kernel)
         dsb = (ds * scale).to(torch.bfloat16).float()
-        dvh = pb.transpose(-1, -2) @ do
+        dvh = (pb.transpose(-1, -2) @ do) * sc
         dkh = dsb.transpose(-1, -2) @ qh
         dqh = dsb @ kh
         dq_acc[:, :H * 64].copy_(dqh.permute(0, 2, 1, 3).reshape(B * Lq, H * 64))

@@ -95,7 +95,11 @@ class Arith:
         # makes the rounding independent of the kernel's tiling), dropped, multiplied by V, then divided by sum(P~).
         s2 = scores * 1.4426950408889634
         e = torch.exp2(s2 - torch.ceil(s2.max(-1, keepdim=True).values))
-        return self.matmul(self.dropout(which, e), v) / e.sum(-1, keepdim=True)
+        m = self.dp.mask(which, e) if self.dp is not None else None
+        if m is None:
+            return self.matmul(e, v) / e.sum(-1, keepdim=True)
+        # the kernel rounds the KEPT probabilities unscaled and folds 1/(1-p) into the final normalisation
+        return self.matmul(e * (m > 0).to(e.dtype), v) / e.sum(-1, keepdim=True) * m.max()
 
     def matmul(self, a, b):
         if self.emu:

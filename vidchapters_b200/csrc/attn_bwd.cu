@@ -4,16 +4,18 @@
 // log-sum-exp (flash-attention style); nothing of size Lq x Lk touches HBM.
 //
 // One CTA = one (batch, head, 128-key tile), looping over the 128-query tiles that see it.  1 CTA / SM
-// (160 KB smem, 448 TMEM columns).  320 threads:
+// (215 KB smem, 448 TMEM columns).  64 + 32 NCW threads (NCW = 16 compute warps by default):
 //   warp 0 lane 0 : TMA: K,V tile once; (Q_i, dO_i) through a 2-stage ring
 //   warp 1        : TMEM alloc; lane 0 issues per query tile
 //                     S  = Q_i.K^T        dP = dO_i.V^T                       (128x128x64 each, fresh)
 //                     dV += P^T.dO_i      dK += dS^T.Q_i     dQ_i = dS.K      (accumulate / accumulate / fresh)
-//   warps 2..9    : 8 compute warps (2 per TMEM lane quarter, 2 column chunks each): p = exp2(s2 - lse2),
+//   warps 2..     : compute warps (NCW/4 per TMEM lane quarter, one or two 32-column chunks each): p = exp2(s2 - lse2),
 //                   ds = p*(dP - delta); write bf16 P and scale*dS tiles (128B-swizzled; each tile serves as MN-major
-//                   A for dV/dK and dS also as K-major A for dQ); while the MMAs run, every thread sums one diagonal
-//                   of the dS tile into its own slot of the d(bias) window; dQ_i goes from TMEM to the fp32 dQ
-//                   accumulator with atomics; finally dK, dV are stored (bf16).
+//                   A for dV/dK and dS also as K-major A for dQ).  Tiles whose bias window is one value and whose keys
+//                   all attend skip every per-element lookup; key tiles made only of padding exit at once.
+//                   d(bias): one sum per tile when the tile lies in one bucket, else per-diagonal sums by warp
+//                   shuffles.  dQ_i goes TMEM -> swizzled smem -> TMA reduce-add into the fp32 dQ accumulator
+//                   (warps 2..9); finally dK, dV are stored (bf16).
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -49,7 +51,8 @@ constexpr int kBwdSmemTiles = 16384 * 2 /*K,V*/ + 2 * 16384 /*Q ring*/ + 2 * 163
 constexpr int kBwdRelMax = 2304;  // floats per relative-position window: ceil(Lq/128)*128 + 128 <= 2304 (Lq <= 2176)
 constexpr int kAttnBwdSmem = kBwdSmemTiles + 32768 + 2 * kBwdRelMax * 4 + 512 + 512;  // + dQ staging + d(bias)/bias windows + key ceilings
 
-__global__ void __launch_bounds__(320, 1)
+template <int NCW>   // compute warps: 8 (two 32-column chunks of the tile per thread) or 16 (one chunk per thread)
+__global__ void __launch_bounds__(64 + NCW * 32, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p) {
@@ -90,7 +93,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 256);
+    mbar_init(pds_full, NCW * 32);
     mbar_init(dq_full, 1);
     mbar_init(dq_read, 256);
     fence_barrier_init();
@@ -210,7 +213,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp >= 2) {
     // ===================== compute: 8 warps = 2 per TMEM lane quarter, each taking 2 of the 4 column chunks ==========
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    constexpr int CPT = 16 / NCW;            // 32-column chunks per thread (4 per row, NCW/4 warps per row quarter)
+    const int part = (warp - 2) >> 2;        // which chunk group of the 128 keys
+    const int half = part & 1;               // which 32 of the 64 head columns (dQ staging, dV/dK epilogue: warps 2..9)
+    const bool io_warp = part < 2;
     const int r = quarter * 32 + lane;
     const int ct = (warp - 2) * 32 + lane;   // 0..255: index among the compute threads
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
@@ -232,8 +238,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(s_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
+      for (int cc = 0; cc < CPT; ++cc) {
+        const int c = part * CPT + cc;
         float sv[32], dp[32];
         tmem_ld32(tS + lane_off + c * 32, sv);
         tmem_ld32(tDP + lane_off + c * 32, dp);
@@ -266,18 +272,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               sv[j + e] = fast_exp2(fminf(fmaf(sv[j + e], p.scale_log2e, bk[j + e]), pen[e]) - lse2);
           }
         }
-        if (p.drop_p16) {  // O = drop(P).V: dV uses the dropped P, dP flows back through the same mask
+        if (p.drop_p16) {
+          // O = (mask.P).V * sc: dV accumulates the masked, UNSCALED P (sc is applied once when dV is stored) and dP
+          // flows back through the same mask: ds = p * (keep ? dP*sc - delta : -delta).
           const float sc = drop_scale(p.drop_p16);
           const uint32_t rk = drop_row_key(drop_salted(p.drop_seed, p.drop_salt), ((unsigned long long)b * p.H + h) * p.Lq + q);
+          const uint32_t hsh = drop_block_hash(rk, (uint32_t)(k0 + c * 32)), thr = drop_threshold(p.drop_p16);
+          const float ndelta = -delta;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const uint32_t hh = drop_pair_hash(rk, (uint32_t)(k0 + c * 32 + j));
-            const bool k0_ = (hh & 0xFFFFu) >= p.drop_p16, k1_ = (hh >> 16) >= p.drop_p16;
-            const float d0 = k0_ ? dp[j] * sc : 0.0f, d1 = k1_ ? dp[j + 1] * sc : 0.0f;
-            dp[j] = sv[j] * (d0 - delta);
-            dp[j + 1] = sv[j + 1] * (d1 - delta);
-            sv[j] = k0_ ? sv[j] * sc : 0.0f;
-            sv[j + 1] = k1_ ? sv[j + 1] * sc : 0.0f;
+          for (int j = 0; j < 32; ++j) {
+            const bool keep = drop_keep_h(hsh, j, thr);
+            dp[j] = sv[j] * (keep ? fmaf(dp[j], sc, ndelta) : ndelta);
+            sv[j] = keep ? sv[j] : 0.0f;
           }
         } else {
 #pragma unroll
@@ -327,6 +333,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // ---- dQ_i: TMEM -> swizzled smem staging -> ONE TMA reduce-add per 32-column half (whole 128-byte lines into the
       // fp32 dQ accumulator) instead of 2048 scattered 16-byte atomics per tile.
+      if (io_warp) {
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
       {
@@ -349,11 +356,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(dq_read);
+      }
     }
     if (ct == 0) bulk_wait_all();
-    // ---- dV, dK: rows = keys of this tile.  (The last dq_full wait above also covers the final dV/dK MMAs.)
+    // ---- dV, dK: rows = keys of this tile, stored by warps 2..9.  (Their last dq_full wait also covers the final dV/dK MMAs.)
     const int kk = k0 + r;
-    if (nqt > 0) {
+    if (!io_warp) {
+    } else if (nqt > 0) {
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
         __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
@@ -362,6 +371,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float v[32];
         tmem_ld32((which == 0 ? tDV : tDK) + lane_off + half * 32, v);
         tmem_ld_wait();
+        if (which == 0 && p.drop_p16) {   // dropout scale of the probabilities, applied once per output instead of per element
+          const float sc = drop_scale(p.drop_p16);
+#pragma unroll
+          for (int g = 0; g < 32; ++g) v[g] *= sc;
+        }
         if (kk < p.Lk) {
           uint4* dst = reinterpret_cast<uint4*>(base + ((long long)b * p.Lk + kk) * ld + col + h * kBD + half * 32);
 #pragma unroll
@@ -469,11 +483,14 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   p.drop_seed = f->drop_seed; p.drop_p16 = f->drop_p16; p.drop_salt = drop_salt_ptr();
   static bool attr = false;
   if (!attr) {
-    VC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
+    VC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
+    VC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
     attr = true;
   }
   dim3 grid((f->Lk + kBT - 1) / kBT, f->H, f->B);
-  attn_bwd_kernel<<<grid, 320, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
+  static const int ncw = [] { const char* e = getenv("VIDCHAP_ATTN_BWD_WARPS"); return e && atoi(e) == 8 ? 8 : 16; }();
+  if (ncw == 8) attn_bwd_kernel<8><<<grid, 320, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
+  else attn_bwd_kernel<16><<<grid, 576, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

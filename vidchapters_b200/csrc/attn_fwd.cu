@@ -5,12 +5,12 @@
 // mask).  The (B,H,Lq,Lk) score / probability tensors of the reference never exist in HBM.
 //
 // One CTA = one (batch, head, 128-query tile); 2 CTAs per SM (112 KB smem, 256 TMEM columns each) so one CTA's
-// softmax overlaps the other's MMAs.  192 threads:
+// softmax overlaps the other's MMAs.  320 threads:
 //   warp 0 lane 0 : TMA producer (Q once; K,V 128-key tiles through a 2-stage ring), 3-D maps zero-fill past Lq/Lk
-//   warp 1        : TMEM alloc; lane 0 issues  S = Q.K^T (128x128x64)  and  O_j = P.V (128x64x128)
-//   warps 2..5    : softmax: thread = one query row.  Pass 1 row max, pass 2 p = exp2(s2 - m) -> bf16 P tile written
-//                   into 128B-swizzled smem (the A operand of the PV MMA); running (m, l) online softmax; the PV
-//                   partial product is read back from TMEM and accumulated in registers with the usual rescale.
+//   warp 1        : TMEM alloc; lane 0 issues  S = Q.K^T (128x128x64)  and  O += P.V (128x64x128, accumulating in TMEM)
+//   warps 2..9    : softmax, two threads per query row (64 keys of the tile each).  Pass 1 row max, pass 2
+//                   p = exp2(s2 - m) -> bf16 P tile written into 128B-swizzled smem (the A operand of the PV MMA);
+//                   online softmax with an integer running max; O is rescaled in TMEM only when that max grows.
 // Scores are handled in the log2 domain: s2 = (acc*scale + bias) * log2(e).  Masked keys (key-padding or causal)
 // take the reference's additive finfo.min semantics (a fully masked row degenerates to uniform, like the reference);
 // columns past Lk are excluded exactly.
@@ -47,9 +47,10 @@ struct AttnFwdParams {
 // The bias/mask staging matters: with two 100 KB CTAs per SM almost no L1 is left, so per-element global loads of the
 // bias row went to L2 and made the kernel 10x slower (profiles/r01_launches_before.txt).
 constexpr int kAttnFwdTiles = 16384 + 2 * 16384 + 16384 + 32768;
-constexpr int kAttnMaxLk = 1792;  // bias window + key ceilings must fit next to 96 KB of tiles, twice per SM: 8*Lk B <= 14 KB
+constexpr int kAttnMaxLk = 1536;  // bias window + key ceilings + row-statistic exchange must fit next to 96 KB of tiles, twice per SM
+constexpr int kAttnFwdTail = 256 + 2048 + 1024;   // barriers + flags | sMx | sL
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(320, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -70,7 +71,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = bars + 7;
   uint64_t* p_full = bars + 8;
   uint64_t* o_full = bars + 9;
-  uint64_t* o_read = bars + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   // Fast-path flags per 128-slot block: the bias changes inside the block / some key of the block is masked or out of
   // range.  A key tile whose bias window is one constant and whose keys all attend (T5: every tile further than 128
@@ -79,6 +79,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   int* sFlagB = reinterpret_cast<int*>(bars + 12);   // [16]
   int* sFlagP = sFlagB + 16;                          // [16]
   int* sLastKey = sFlagP + 16;                        // index of the last key that attends (-1: none)
+  float* sMx = reinterpret_cast<float*>(bars + 32);   // [2 parities][2 halves][128 rows] half-row tile maxima
+  float* sL = sMx + 512;                              // [2 halves][128 rows] half-row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -93,9 +95,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
-    mbar_init(o_read, 128);
     fence_barrier_init();
   }
   if (threadIdx.x < 32) sFlagB[threadIdx.x] = 0;   // (covers sFlagP too)
@@ -170,107 +171,119 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_commit(&k_empty[st]);  // K stage is free as soon as S(j) has been computed
       tc_commit(s_full);
       // P(j) written and S(j) consumed; O(j-1) read back; V(j) landed
-      mbar_wait(p_full, j & 1);
-      if (j > 0) mbar_wait(o_read, (j - 1) & 1);
+      mbar_wait(p_full, j & 1);   // (also covers any in-place rescale of O by the softmax warps)
       mbar_wait(v_full, j & 1);
       tc_fence_after();
       const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 0, 1024);
 #pragma unroll
       for (int k = 0; k < kTK / 16; ++k) {
         const uint64_t pd = make_smem_desc_sw128(smem_u32(sP + (k >> 2) * 16384) + (k & 3) * 32, 0, 1024);
-        tc_mma_bf16(tmem_O, pd, vdesc + (uint64_t)(k * 128), idesc_o, k > 0);
+        tc_mma_bf16(tmem_O, pd, vdesc + (uint64_t)(k * 128), idesc_o, (j > 0 || k > 0));   // O += P(j).V(j)
       }
       tc_commit(v_empty);
-      tc_commit(o_full);
+      if (j == nkt - 1) tc_commit(o_full);
     }
   } else if (warp >= 2) {
-    // ===================== softmax / epilogue =====================
+    // ===================== softmax / epilogue: 8 warps, two threads per query row =====================
+    // Thread (r, hf) owns keys [64 hf, 64 hf + 64) of every tile and output columns [32 hf, 32 hf + 32) of row r (TMEM
+    // lane r: warp w may only touch lanes 32 (w % 4) ..).  The two halves of a row exchange their tile maxima through
+    // shared memory; the running sum stays split until the end.  O accumulates in TMEM across tiles (the PV MMA adds
+    // into it); it is rescaled in place only when a row's INTEGER running maximum grows — after the first tiles almost
+    // never — instead of being read back and re-accumulated in registers every tile.
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;  // row in tile == TMEM lane
     const int q = q0 + r;            // row inside this call's query block (output / lse index)
     const int q_abs = q + qoff;      // its sequence position (bias window, causal mask)
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float* brow = sBias + (127 - r);  // brow[k] = bias(k - q) * log2e
+    const uint32_t drop_rk = drop_row_key(drop_salted(p.drop_seed, p.drop_salt), ((unsigned long long)b * p.H + h) * p.Lq + q);
     float m_run = -INFINITY, l_run = 0.0f;
-    float o_acc[kD];
-#pragma unroll
-    for (int i = 0; i < kD; ++i) o_acc[i] = 0.0f;
 
     for (int j = 0; j < nkt; ++j) {
       const int k0 = j * kTK;
-      mbar_wait(s_full, j & 1);
+      const int kh = k0 + hf * 64;   // first key of this thread's half of the tile
+      mbar_wait(s_full, j & 1);      // (tensor pipe is in order: S(j) done implies PV(j-1) done — sP and O are free)
       tc_fence_after();
       // ---- pass 1: row max of s2 over the tile.  s2 = min(acc*scale*log2e + bias*log2e, pen[k]); causal tiles add k<=q.
       const bool causal_tile = p.causal && (k0 + kTK - 1 > q0 + qoff);   // uniform: only tiles touching the diagonal
       // uniform over the CTA: the tile's whole bias window is one value and every key attends
       const bool fast = !causal_tile && (sFlagB[j] | sFlagB[j + 1] | sFlagP[j]) == 0;
       const float cb = sBias[k0 + 127];
-      float m_tile = -INFINITY;
+      float m_loc = -INFINITY;
       if (fast) {
-#pragma unroll 1
-        for (int c = 0; c < 4; c += 2) {
-          float v[32], w[32];
-          tmem_ld32(tmem_S + lane_off + c * 32, v);
-          tmem_ld32(tmem_S + lane_off + c * 32 + 32, w);
-          tmem_ld_wait();
+        float v[32], w[32];
+        tmem_ld32(tmem_S + lane_off + hf * 64, v);
+        tmem_ld32(tmem_S + lane_off + hf * 64 + 32, w);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, fmaxf(v[i], w[i]));
-        }
-        m_tile = fmaf(m_tile, p.scale_log2e, cb);   // scale > 0: max commutes with the affine map
+        for (int i = 0; i < 32; ++i) m_loc = fmaxf(m_loc, fmaxf(v[i], w[i]));
+        m_loc = fmaf(m_loc, p.scale_log2e, cb);   // scale > 0: max commutes with the affine map
       } else {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        const float4* pen4 = reinterpret_cast<const float4*>(sPen + k0 + c * 32);
-        const float* bk = brow + k0 + c * 32;
-        const int tq = q_abs - k0 - c * 32;  // column i is causally masked iff i > tq
-        tmem_ld_wait();
-        // s2 = min(acc*scale*log2e + bias*log2e, pen[k]) (+ causal) is written back to TMEM so that pass 2 only has to
-        // subtract the max and exponentiate (no second bias / ceiling lookup).
-        if (causal_tile) {
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+          tmem_ld32(tmem_S + lane_off + hf * 64 + c * 32, v);
+          const float4* pen4 = reinterpret_cast<const float4*>(sPen + kh + c * 32);
+          const float* bk = brow + kh + c * 32;
+          const int tq = q_abs - kh - c * 32;  // column i is causally masked iff i > tq
+          tmem_ld_wait();
+          // s2 (+ causal) is written back to TMEM so that pass 2 only has to subtract the max and exponentiate
+          if (causal_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 pe = pen4[i >> 2];
-            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
+            for (int i = 0; i < 32; i += 4) {
+              const float4 pe = pen4[i >> 2];
+              const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float s2 = fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]);
-              s2 = (i + e > tq) ? fminf(s2, kMasked) : s2;
-              v[i + e] = s2;
-              m_tile = fmaxf(m_tile, s2);
+              for (int e = 0; e < 4; ++e) {
+                float s2 = fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]);
+                s2 = (i + e > tq) ? fminf(s2, kMasked) : s2;
+                v[i + e] = s2;
+                m_loc = fmaxf(m_loc, s2);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 pe = pen4[i >> 2];
+              const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[i + e] = fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]);
+                m_loc = fmaxf(m_loc, v[i + e]);
+              }
             }
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 pe = pen4[i >> 2];
-            const float pen[4] = {pe.x, pe.y, pe.z, pe.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[i + e] = fminf(fmaf(v[i + e], p.scale_log2e, bk[i + e]), pen[e]);
-              m_tile = fmaxf(m_tile, v[i + e]);
-            }
-          }
+          tmem_st32(tmem_S + lane_off + hf * 64 + c * 32, v);
         }
-        tmem_st32(tmem_S + lane_off + c * 32, v);
+        tmem_st_wait();
       }
-      tmem_st_wait();
-      }
+      // exchange the half-row maxima (slots double-buffered by tile parity)
+      float* mx = sMx + (j & 1) * 256;
+      mx[hf * 128 + r] = m_loc;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       // Integer running max (log2 domain): every rescale factor is an exact power of two, so the bf16 rounding of
       // P = 2^(s2 - m) does not depend on the tiling / on when the maximum was discovered.
-      m_tile = ceilf(m_tile);
-      const float m_new = fmaxf(m_run, m_tile);
-      const float corr = fast_exp2(m_run - m_new);  // m_run=-inf on first tile -> 0
+      const float m_new = fmaxf(m_run, ceilf(fmaxf(m_loc, mx[(hf ^ 1) * 128 + r])));
+      const float corr = fast_exp2(m_run - m_new);  // first tile: m_run = -inf -> 0
+      if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {   // rare: rescale this warp's 32 rows x 32 columns of O
+        float o[32];
+        tmem_ld32(tmem_O + lane_off + hf * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] *= corr;
+        tmem_st32(tmem_O + lane_off + hf * 32, o);
+        tmem_st_wait();
+      }
       // ---- pass 2: p = exp2(s2 - m_new), write bf16 P (swizzled, K-major A operand), row sum
       float l_tile = 0.0f;
       // fast tiles still hold the raw accumulator: one FMA folds scale, bias and the max; slow tiles hold s2
       const float e_mul = fast ? p.scale_log2e : 1.0f;
       const float e_add = fast ? cb - m_new : -m_new;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld32(tmem_S + lane_off + hf * 64 + c * 32, v);
         tmem_ld_wait();
         // the normaliser l uses the un-dropped probabilities (dropout acts on softmax's output)
 #pragma unroll
@@ -280,15 +293,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           v[i] = pv;
         }
         if (p.drop_p16) {
-          // mask row = (b, h, q), column = k
-          drop_apply<32>(v, drop_row_key(drop_salted(p.drop_seed, p.drop_salt), ((unsigned long long)b * p.H + h) * p.Lq + q), p.drop_p16,
-                         (uint32_t)(k0 + c * 32), drop_scale(p.drop_p16));
+          // mask row = (b, h, q), column = k.  Kept probabilities stay unscaled here: O = (sum mask.p.v) * sc / l, the
+          // factor sc = 1/(1-p) is folded into the final normalisation.
+          drop_select<32>(v, drop_rk, p.drop_p16, (uint32_t)(kh + c * 32));
         }
-        // 32 columns = 4 x 16-byte chunks of this row; chunk index within the 64-wide atom: (c&1)*4 + g
-        uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
+        // 32 columns = 4 x 16-byte chunks of this row; the 64-wide swizzle atom is the thread's half hf
+        uint8_t* prow = sP + hf * 16384 + r * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int ch = ((c & 1) * 4 + g) ^ (r & 7);
+          const int ch = (c * 4 + g) ^ (r & 7);
           *reinterpret_cast<uint4*>(prow + ch * 16) =
               make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
                          pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
@@ -299,30 +312,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive(p_full);
       l_run = l_run * corr + l_tile;
       m_run = m_new;
-      // ---- accumulate O_j
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld32(tmem_O + lane_off + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * corr + v[i];
-      }
-      tc_fence_before();
-      mbar_arrive(o_read);
     }
-    if (q < p.Lq) {
-      const float inv = 1.0f / l_run;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * p.Lq + q) * p.ldo + h * kD);
+    // ---- epilogue: combine the two half-row sums, normalise O (TMEM) and store
+    sL[hf * 128 + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_row = l_run + sL[(hf ^ 1) * 128 + r];
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    {
+      float o[32];
+      tmem_ld32(tmem_O + lane_off + hf * 32, o);
+      tmem_ld_wait();
+      if (q < p.Lq) {
+        const float inv = (p.drop_p16 ? drop_scale(p.drop_p16) : 1.0f) / l_row;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)b * p.Lq + q) * p.ldo + h * kD + hf * 32);
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        dst[g] = make_uint4(pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv),
-                            pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv),
-                            pack_bf16x2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv),
-                            pack_bf16x2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv));
-      if (p.lse2) p.lse2[((long long)b * p.H + h) * p.Lq + q] = m_run + log2f(l_run);
+        for (int g = 0; g < 4; ++g)
+          dst[g] = make_uint4(pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv),
+                              pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv),
+                              pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv),
+                              pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv));
+        if (p.lse2 && hf == 0) p.lse2[((long long)b * p.H + h) * p.Lq + q] = m_run + log2f(l_row);
+      }
     }
   }
 
@@ -365,15 +376,15 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   VC_CHECK(a->Lk <= kAttnMaxLk, "vc_attn_fwd: Lk=%d exceeds the %d keys the bias/mask staging supports", a->Lk, kAttnMaxLk);
   const int lk_pad = ((a->Lk + kTK - 1) / kTK) * kTK;
   VC_CHECK(a->scale > 0.f, "vc_attn_fwd: scale must be positive");
-  const int smem_bytes = kAttnFwdTiles + (lk_pad + 128) * 4 + lk_pad * 4 + 256;
+  const int smem_bytes = kAttnFwdTiles + (lk_pad + 128) * 4 + lk_pad * 4 + kAttnFwdTail;
   static bool attr = false;
   if (!attr) {
     VC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kAttnFwdTiles + (kAttnMaxLk + 128) * 4 + kAttnMaxLk * 4 + 256));
+                                 kAttnFwdTiles + (kAttnMaxLk + 128) * 4 + kAttnMaxLk * 4 + kAttnFwdTail));
     attr = true;
   }
   dim3 grid((a->Lq + kTQ - 1) / kTQ, a->H, a->B);
-  attn_fwd_kernel<<<grid, 192, smem_bytes, st>>>(tmQ, tmK, tmV, p);
+  attn_fwd_kernel<<<grid, 320, smem_bytes, st>>>(tmQ, tmK, tmV, p);
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -181,31 +181,49 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 constexpr uint32_t kSwizzleAtomBytes = 1024;
 
 // ---------------------------------------------------------------- dropout (counter-based, stateless)
-// Element (r, c) of a 2-D tensor is kept iff a 16-bit hash of (seed, r, c) >= p16, p16 = round(p * 65536); kept values
-// are scaled by 65536 / (65536 - p16).  One 32-bit hash serves the two columns 2j, 2j+1 of a row, so forward and
-// backward regenerate the same mask from (seed, row, column) and nothing is stored.  Reference semantics: nn.Dropout /
-// F.dropout (modeling_t5.py:307,353,572-574,618,1019,1114; vit.py:20,22,49,54,126) — same distribution, own stream.
+// Element (r, c) of a 2-D tensor is kept iff its 16-bit random value >= p16, p16 = round(p * 65536); kept values are
+// scaled by 65536 / (65536 - p16).  The value is the top half of  H(seed, r, c / 32) * A[c % 32]  (multiply-shift
+// hashing): H is one strong odd 32-bit hash per 32-column block of a row and A[] are 32 fixed odd multipliers, so an
+// element costs one integer multiply and one compare (the attention and GEMM epilogues are issue-bound: the previous
+// hash-per-pair scheme spent half of the attention kernels' instructions on the mask).  Forward and backward regenerate
+// the same mask from (seed, row, column); nothing is stored.  Reference semantics: nn.Dropout / F.dropout
+// (modeling_t5.py:307,353,572-574,618,1019,1114; vit.py:20,22,49,54,126) — same distribution, own stream.
 __device__ __forceinline__ uint32_t drop_row_key(uint32_t seed, unsigned long long r) {
   return seed + (uint32_t)r * 0x9E3779B1u + (uint32_t)(r >> 32) * 0x7F4A7C15u;
 }
-__device__ __forceinline__ uint32_t drop_pair_hash(uint32_t row_key, uint32_t c) {   // c = column, bit 0 ignored
-  uint32_t x = row_key + (c >> 1) * 0x85EBCA77u;
+__host__ __device__ constexpr uint32_t drop_lane_mult(uint32_t i) {   // A[i], i = c % 32 (folds to a constant when unrolled)
+  uint32_t x = (i + 1u) * 0x9E3779B1u;
+  x ^= x >> 15; x *= 0x85EBCA6Bu; x ^= x >> 13;
+  return x | 1u;
+}
+__device__ __forceinline__ uint32_t drop_block_hash(uint32_t row_key, uint32_t c) {   // c = any column of the block
+  uint32_t x = row_key + (c >> 5) * 0x85EBCA77u;
   x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
-  return x;
+  return x | 1u;
+}
+__device__ __forceinline__ uint32_t drop_threshold(uint32_t p16) { return p16 << 16; }
+// keep test for in-block column i given the block hash: (H * A[i]) >> 16 >= p16
+__device__ __forceinline__ bool drop_keep_h(uint32_t block_hash, uint32_t i, uint32_t thr) {
+  return block_hash * drop_lane_mult(i) >= thr;
 }
 __device__ __forceinline__ bool drop_keep(uint32_t row_key, uint32_t p16, uint32_t c) {
-  const uint32_t h = drop_pair_hash(row_key, c);
-  return ((c & 1) ? (h >> 16) : (h & 0xFFFFu)) >= p16;
+  return drop_keep_h(drop_block_hash(row_key, c), c & 31u, drop_threshold(p16));
 }
-// Apply to n (even) consecutive columns c0.. (c0 even) held in v[]: one hash per pair.
+// Apply to N consecutive columns c0.. held in v[] (c0 % N == 0, N in {4, 32}: never straddles a 32-column block).
 template <int N>
 __device__ __forceinline__ void drop_apply(float* v, uint32_t row_key, uint32_t p16, uint32_t c0, float sc) {
+  const uint32_t hsh = drop_block_hash(row_key, c0), thr = drop_threshold(p16);
+  const uint32_t i0 = (N == 32) ? 0u : (c0 & 31u);
 #pragma unroll
-  for (int j = 0; j < N; j += 2) {
-    const uint32_t h = drop_pair_hash(row_key, c0 + j);
-    v[j] = (h & 0xFFFFu) >= p16 ? v[j] * sc : 0.0f;
-    v[j + 1] = (h >> 16) >= p16 ? v[j + 1] * sc : 0.0f;
-  }
+  for (int j = 0; j < N; ++j) v[j] = drop_keep_h(hsh, i0 + j, thr) ? v[j] * sc : 0.0f;
+}
+// Same mask without the scale (callers that fold 65536/(65536-p16) into a later per-row / per-tile factor).
+template <int N>
+__device__ __forceinline__ void drop_select(float* v, uint32_t row_key, uint32_t p16, uint32_t c0) {
+  const uint32_t hsh = drop_block_hash(row_key, c0), thr = drop_threshold(p16);
+  const uint32_t i0 = (N == 32) ? 0u : (c0 & 31u);
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = drop_keep_h(hsh, i0 + j, thr) ? v[j] : 0.0f;
 }
 __device__ __forceinline__ uint32_t drop_salted(uint32_t seed, const uint32_t* salt) { return salt ? seed ^ __ldg(salt) : seed; }
 __device__ __forceinline__ float drop_scale(uint32_t p16) { return 65536.0f / (float)(65536u - p16); }
