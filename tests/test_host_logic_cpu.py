@@ -62,6 +62,33 @@ def test_engine_matches_oracle(cfg):
     assert rel(ctx["logits"].reshape(o32["logits"].shape), o32["logits"]) < 1.2e-2   # tier B: below the reference's own bf16 error
 
 
+@pytest.mark.parametrize("cfg", [dict(TINY, num_features=10), dict(TINY_PROJ)], ids=["tiny", "tiny-proj"])
+def test_phased_backward_equals_single_backward(cfg):
+    """GraphedTrainStep (data parallel) runs the backward as three phases so that NCCL can all-reduce the regions of the
+    flat gradient buffer that are already final; the phases must add up to exactly the single-call backward."""
+    sd = init_state_dict(cfg, 0)
+    eng = Vid2SeqEngine(cfg, TorchOps(), "cpu")
+    for n, t in sd.items():
+        eng.p(n).copy_(t)
+    eng.sync_bf16()
+    video, inp, out = batch(cfg)
+    grads = []
+    for phases in ((None,), (1, 2, 3)):
+        loss, ctx = eng.forward(video, inp, inp != 0, out, out != 0)
+        eng.zero_grad()
+        for ph in phases:
+            eng.backward(ctx, phase=ph)
+            if ph == 1:   # the decoder region is final after phase 1 ...
+                lo, hi = eng.decoder_grad_range()
+                dec_after_1 = eng.flat_g[lo:hi].clone()
+            if ph == 2:   # ... and [shared | text encoder] after phase 2
+                head_after_2 = eng.flat_g[:lo].clone()
+        grads.append(eng.flat_g.clone())
+    assert torch.equal(grads[0], grads[1])
+    assert torch.equal(dec_after_1, grads[0][lo:hi]) and torch.equal(head_after_2, grads[0][:lo])
+    assert grads[0][hi:].abs().sum() > 0   # the visual encoder region exists and is written by phase 3
+
+
 def test_bucket_lut_known_answers():
     """SURVEY §8c known answers of the reference's _relative_position_bucket (modeling_t5.py:397-443)."""
     f = lambda r, bi: int(relative_position_bucket(torch.tensor([r]), bidirectional=bi)[0])

@@ -93,14 +93,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, NCW * 32);
+    mbar_init(pds_full, NCW);   // one arrival per compute warp
     mbar_init(dq_full, 1);
-    mbar_init(dq_read, 256);
+    mbar_init(dq_read, 8);      // one arrival per staging warp (warps 2..9)
     fence_barrier_init();
   }
   const int nqt_all = (p.Lq + kBT - 1) / kBT;
   if (threadIdx.x < 51) s_nonuni_v[threadIdx.x] = 0;   // (all flag arrays)
   __syncthreads();
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is read from here on
+  pdl_trigger();
   const int n_rel = p.Lq + kBT;  // relative positions touched by this CTA: (k - q + Lq - 1) - rel_base in [0, Lq+127)
   const int rel_base = k0;       // slot = (k - k0) + (Lq - 1 - q)
   if (p.dbias_rel)
@@ -324,7 +326,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
       if (tile_sum) {
         // one bucket for the whole tile: deposit the tile's total at one of its relative positions (k = k0, q = q0)
 #pragma unroll
@@ -355,7 +358,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       tc_fence_before();
-      mbar_arrive(dq_read);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_read);
       }
     }
     if (ct == 0) bulk_wait_all();
@@ -415,6 +419,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout, long long lddo,
                   int do_col, float* __restrict__ delta, float* __restrict__ dq_acc, long long ld_dq, int B, int H, int Lq) {
+  pdl_wait();
+  pdl_trigger();
   // one warp per (row, 4 heads at a time): lane handles 8 consecutive elements of a 256-wide slab
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -458,9 +464,9 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   // delta = rowsum(dO * O)
   {
     const long long rows = (long long)f->B * f->Lq;
-    attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)f->out, f->ldo,
-                                                                 (const __nv_bfloat16*)a->dout, a->ld_do, a->do_col,
-                                                                 a->delta, a->dq_acc, a->ld_dq, f->B, f->H, f->Lq);
+    VC_CUDA(launch_kernel(attn_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, (const __nv_bfloat16*)f->out,
+                          f->ldo, (const __nv_bfloat16*)a->dout, a->ld_do, a->do_col, a->delta, a->dq_acc, a->ld_dq, f->B, f->H,
+                          f->Lq));
     VC_CUDA(cudaGetLastError());
   }
   CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
@@ -489,8 +495,8 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   }
   dim3 grid((f->Lk + kBT - 1) / kBT, f->H, f->B);
   static const int ncw = [] { const char* e = getenv("VIDCHAP_ATTN_BWD_WARPS"); return e && atoi(e) == 8 ? 8 : 16; }();
-  if (ncw == 8) attn_bwd_kernel<8><<<grid, 320, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
-  else attn_bwd_kernel<16><<<grid, 576, kAttnBwdSmem, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
+  if (ncw == 8) VC_CUDA(launch_kernel(attn_bwd_kernel<8>, grid, dim3(320), (size_t)kAttnBwdSmem, st, tmQ, tmK, tmV, tmDO, tmDQ, p));
+  else VC_CUDA(launch_kernel(attn_bwd_kernel<16>, grid, dim3(576), (size_t)kAttnBwdSmem, st, tmQ, tmK, tmV, tmDO, tmDQ, p));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

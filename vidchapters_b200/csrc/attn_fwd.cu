@@ -95,13 +95,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
+    mbar_init(p_full, 8);     // one arrival per softmax warp (each arrival wakes every thread sleeping on a barrier)
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (threadIdx.x < 32) sFlagB[threadIdx.x] = 0;   // (covers sFlagP too)
   if (threadIdx.x == 32) *sLastKey = -1;
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   __syncthreads();
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is read from here on
+  pdl_trigger();
   // stage this query tile's bias window (index k + 127 - r == (k - q + Lq - 1) - (Lq - 128 - q0)) and the key mask
   {
     const int win0 = p.bias_zero - 127 - q0 - qoff;  // global bias index of window slot 0 (may be negative: never used)
@@ -126,7 +129,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       else atomicMax(sLastKey, i);
     }
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -309,7 +311,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
       l_run = l_run * corr + l_tile;
       m_run = m_new;
     }
@@ -384,7 +387,7 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
     attr = true;
   }
   dim3 grid((a->Lq + kTQ - 1) / kTQ, a->H, a->B);
-  attn_fwd_kernel<<<grid, 320, smem_bytes, st>>>(tmQ, tmK, tmV, p);
+  VC_CUDA(launch_kernel(attn_fwd_kernel, grid, dim3(320), (size_t)smem_bytes, st, tmQ, tmK, tmV, p));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

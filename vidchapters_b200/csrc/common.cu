@@ -21,6 +21,11 @@ int check_cuda(cudaError_t e, const char* what) {
   return VC_ERR_CUDA;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("VIDCHAP_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/vidchap.h"
 
@@ -38,6 +39,24 @@ int make_tmap_2d_ex(CUtensorMap* out, const void* base, int elt_bytes, uint64_t 
                     uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
 int num_sms();
+
+// Programmatic dependent launch for every kernel of the library (VIDCHAP_PDL=0 turns it off for A/B runs); see
+// ptx.cuh::pdl_wait.  Inside stream capture the attribute becomes a programmatic dependency edge of the CUDA graph.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // Device pointer to a 32-bit salt XORed into every dropout seed (vc_set_dropout_salt); lets a captured CUDA graph draw
 // fresh masks on every replay.  nullptr = no salt.

@@ -15,6 +15,8 @@ namespace vc {
 // cache[b, *pos, :] = src[b, :]   (src [B][C] bf16 with row stride lds; cache [B][cap][C])
 __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ cache, int B,
                                  int cap, int C, const int* __restrict__ pos_dev) {
+  pdl_wait();
+  pdl_trigger();
   const int pos = *pos_dev;
   const int c8 = C / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -31,6 +33,8 @@ __global__ void __launch_bounds__(256)
 greedy_next_kernel(const float* __restrict__ logits, long long ld, int V, unsigned char* __restrict__ done,
                    long long* __restrict__ ids_out, long long* __restrict__ seq, int seq_ld, const int* __restrict__ pos_dev,
                    long long eos_id, long long pad_id) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
   const int b = blockIdx.x;
@@ -60,7 +64,9 @@ greedy_next_kernel(const float* __restrict__ logits, long long ld, int V, unsign
   }
 }
 
-__global__ void step_advance_kernel(int* pos_dev) { *pos_dev += 1; }
+__global__ void step_advance_kernel(int* pos_dev) {
+  pdl_wait();
+  pdl_trigger(); *pos_dev += 1; }
 
 }  // namespace vc
 
@@ -70,21 +76,21 @@ using namespace vc;
 extern "C" int vc_kv_append(const void* src, int64_t lds, void* cache, int B, int cap, int C, const int32_t* pos_dev,
                             void* stream) {
   VC_CHECK(B > 0 && C % 8 == 0 && lds % 8 == 0, "vc_kv_append: C and lds must be multiples of 8");
-  kv_append_kernel<<<(B * (C / 8) + 255) / 256, 256, 0, ST(stream)>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)cache, B,
-                                                                     cap, C, pos_dev);
+  VC_CUDA(launch_kernel(kv_append_kernel, dim3((B * (C / 8) + 255) / 256), dim3(256), 0, ST(stream), (const __nv_bfloat16*)src, lds, (__nv_bfloat16*)cache, B,
+                                                                     cap, C, pos_dev));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_greedy_next(const float* logits, int64_t ld, int V, uint8_t* done, int64_t* ids_out, int64_t* seq, int seq_ld,
                               const int32_t* pos_dev, int64_t eos_id, int64_t pad_id, int B, void* stream) {
   VC_CHECK(B > 0 && V > 0, "vc_greedy_next: bad dims");
-  greedy_next_kernel<<<B, 256, 0, ST(stream)>>>(logits, ld, V, done, (long long*)ids_out, (long long*)seq, seq_ld, pos_dev,
-                                                eos_id, pad_id);
+  VC_CUDA(launch_kernel(greedy_next_kernel, dim3(B), dim3(256), 0, ST(stream), logits, ld, V, done, (long long*)ids_out, (long long*)seq, seq_ld, pos_dev,
+                                                eos_id, pad_id));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_step_advance(int32_t* pos_dev, void* stream) {
-  step_advance_kernel<<<1, 1, 0, ST(stream)>>>(pos_dev);
+  VC_CUDA(launch_kernel(step_advance_kernel, dim3(1), dim3(1), 0, ST(stream), pos_dev));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -74,6 +74,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();      // prologue above overlapped the previous kernel's tail; from here on global memory is read
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_mn = p.m_blocks * p.n_blocks;
@@ -196,7 +198,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const E
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, 384, Cfg::kSmemBytes, st>>>(tmA, tmB, em, p);
+  VC_CUDA(launch_kernel(kern, dim3(grid), dim3(384), Cfg::kSmemBytes, st, tmA, tmB, em, p));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

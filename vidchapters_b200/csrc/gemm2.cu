@@ -124,6 +124,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  pdl_wait();      // prologue above overlapped the previous kernel's tail; from here on global memory is read
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
 
   // tile scheduler over 256-row blocks
@@ -243,7 +245,7 @@ static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  kern<<<2 * clusters, 384, Cfg::kSmemBytes, st>>>(tmA, tmB, em, p);
+  VC_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(384), Cfg::kSmemBytes, st, tmA, tmB, em, p));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -23,6 +23,8 @@ __device__ __forceinline__ float warp_max_f(float v) {
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
                                                        float* __restrict__ out, int n, int d, int V, uint32_t drop_seed_in,
                                                        uint32_t drop_p16, const uint32_t* salt) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const int lane = threadIdx.x & 31;
   const int wt = gridDim.x * (blockDim.x >> 5);
@@ -45,6 +47,8 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restr
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dout,
                                                        float* __restrict__ dtable, int n, int d, int V, uint32_t drop_seed_in,
                                                        uint32_t drop_p16, const uint32_t* salt) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const int lane = threadIdx.x & 31;
   const int wt = gridDim.x * (blockDim.x >> 5);
@@ -69,6 +73,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
 __global__ void prepare_targets_kernel(const long long* __restrict__ out_ids, long long* __restrict__ dec_in,
                                        long long* __restrict__ labels, float* __restrict__ n_valid, int B, int S,
                                        long long pad_id) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int valid = 0;
   if (i < B * S) {
@@ -90,6 +96,8 @@ __global__ void prepare_targets_kernel(const long long* __restrict__ out_ids, lo
 // ---- relative position bias: out[h][r] = table[lut[r]][h]   (modeling_t5.py:445-460; lut = bucket of r-(Lq-1))
 __global__ void bias_expand_kernel(const float* __restrict__ table, const int* __restrict__ lut, float* __restrict__ out,
                                    int H, int R) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < H * R) {
     const int h = i / R, r = i % R;
@@ -99,6 +107,8 @@ __global__ void bias_expand_kernel(const float* __restrict__ table, const int* _
 // backward: dtable[lut[r]][h] += drel[h][r]
 __global__ void bias_fold_kernel(const float* __restrict__ drel, const int* __restrict__ lut, float* __restrict__ dtable,
                                  int H, int R) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < H * R) {
     const int h = i / R, r = i % R;
@@ -110,6 +120,8 @@ __global__ void bias_fold_kernel(const float* __restrict__ drel, const int* __re
 // ---- x + pos_embed (model/vit.py:119-127; nearest interpolation when T != num_features)
 __global__ void add_pos_kernel(const float* __restrict__ x, const float* __restrict__ pos, float* __restrict__ out, int B,
                                int T, int C, int P, uint32_t drop_seed_in, uint32_t drop_p16, const uint32_t* salt) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
   const long long total = (long long)B * T * C / 4;
@@ -130,6 +142,8 @@ __global__ void add_pos_kernel(const float* __restrict__ x, const float* __restr
 }
 __global__ void add_pos_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B, int T, int C, int P,
                                    uint32_t drop_seed_in, uint32_t drop_p16, const uint32_t* salt) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over T*C
   if (i < T * C) {
@@ -153,6 +167,8 @@ __global__ void __launch_bounds__(256)
 cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                      const float* __restrict__ n_valid_p, float eps, float* __restrict__ loss_out,
                      __nv_bfloat16* __restrict__ dlogits, long long ldd, int V) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8];
   __shared__ float bcast[2];
   const int row = blockIdx.x;
@@ -228,6 +244,8 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
 // ---- column sums of a bf16 matrix (bias gradients of the ViT Linears): out[n] += sum_m x[m][n]
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
                                                          float* __restrict__ out, int M, int N, int rows_per_block) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.x * 256 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
@@ -241,6 +259,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // ---- fp32 -> bf16 cast with independent row strides (e.g. dQ accumulator -> the q columns of the dQKV matrix)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
                                      long long ldd, int M, int N, float scale) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // index over M * N/4
   const int n4 = N / 4;
   if (i < (long long)M * n4) {
@@ -254,6 +274,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long ld
 // ---- copy a bf16 [B,T,C] tensor into rows [row_off, row_off+T) of every batch of a [B,E,C] tensor (memory concat)
 __global__ void copy_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int T,
                                       int C, int E, int row_off) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // uint4 (8 elems) index
   const int c8 = C / 8;
   if (i < (long long)B * T * c8) {
@@ -277,16 +299,16 @@ using namespace vc;
 extern "C" int vc_embed_fwd(const int64_t* ids, const float* table, float* out, int n, int d, int V, uint32_t drop_seed,
                             uint32_t drop_p16, void* stream) {
   VC_CHECK(n > 0 && d % 4 == 0, "vc_embed_fwd: bad dims");
-  embed_fwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, table, out, n, d, V, drop_seed,
-                                                                  drop_p16, drop_salt_ptr());
+  VC_CUDA(launch_kernel(embed_fwd_kernel, dim3(cap_grid((n + 7) / 8)), dim3(256), 0, ST(stream), (const long long*)ids, table, out, n, d, V, drop_seed,
+                                                                  drop_p16, drop_salt_ptr()));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_embed_bwd(const int64_t* ids, const float* dout, float* dtable, int n, int d, int V, uint32_t drop_seed,
                             uint32_t drop_p16, void* stream) {
   VC_CHECK(n > 0 && d % 4 == 0, "vc_embed_bwd: bad dims");
-  embed_bwd_kernel<<<cap_grid((n + 7) / 8), 256, 0, ST(stream)>>>((const long long*)ids, dout, dtable, n, d, V, drop_seed,
-                                                                  drop_p16, drop_salt_ptr());
+  VC_CUDA(launch_kernel(embed_bwd_kernel, dim3(cap_grid((n + 7) / 8)), dim3(256), 0, ST(stream), (const long long*)ids, dout, dtable, n, d, V, drop_seed,
+                                                                  drop_p16, drop_salt_ptr()));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -294,18 +316,18 @@ extern "C" int vc_prepare_targets(const int64_t* out_ids, int64_t* dec_in, int64
                                   int64_t pad_id, void* stream) {
   VC_CHECK(B > 0 && S > 0, "vc_prepare_targets: bad dims");
   VC_CUDA(cudaMemsetAsync(n_valid, 0, sizeof(float), ST(stream)));
-  prepare_targets_kernel<<<(B * S + 255) / 256, 256, 0, ST(stream)>>>((const long long*)out_ids, (long long*)dec_in,
-                                                                     (long long*)labels, n_valid, B, S, pad_id);
+  VC_CUDA(launch_kernel(prepare_targets_kernel, dim3((B * S + 255) / 256), dim3(256), 0, ST(stream), (const long long*)out_ids, (long long*)dec_in,
+                                                                     (long long*)labels, n_valid, B, S, pad_id));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_bias_expand(const float* table, const int32_t* lut, float* out, int H, int R, void* stream) {
-  bias_expand_kernel<<<(H * R + 255) / 256, 256, 0, ST(stream)>>>(table, lut, out, H, R);
+  VC_CUDA(launch_kernel(bias_expand_kernel, dim3((H * R + 255) / 256), dim3(256), 0, ST(stream), table, lut, out, H, R));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_bias_fold(const float* drel, const int32_t* lut, float* dtable, int H, int R, void* stream) {
-  bias_fold_kernel<<<(H * R + 255) / 256, 256, 0, ST(stream)>>>(drel, lut, dtable, H, R);
+  VC_CUDA(launch_kernel(bias_fold_kernel, dim3((H * R + 255) / 256), dim3(256), 0, ST(stream), drel, lut, dtable, H, R));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -313,13 +335,13 @@ extern "C" int vc_add_pos(const float* x, const float* pos, float* out, int B, i
                           uint32_t drop_p16, void* stream) {
   VC_CHECK(C % 4 == 0, "vc_add_pos: C must be x4");
   const long long total = (long long)B * T * C / 4;
-  add_pos_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(x, pos, out, B, T, C, P, drop_seed, drop_p16, drop_salt_ptr());
+  VC_CUDA(launch_kernel(add_pos_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), x, pos, out, B, T, C, P, drop_seed, drop_p16, drop_salt_ptr()));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C, int P, uint32_t drop_seed,
                               uint32_t drop_p16, void* stream) {
-  add_pos_bwd_kernel<<<(T * C + 255) / 256, 256, 0, ST(stream)>>>(dx, dpos, B, T, C, P, drop_seed, drop_p16, drop_salt_ptr());
+  VC_CUDA(launch_kernel(add_pos_bwd_kernel, dim3((T * C + 255) / 256), dim3(256), 0, ST(stream), dx, dpos, B, T, C, P, drop_seed, drop_p16, drop_salt_ptr()));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -327,15 +349,15 @@ extern "C" int vc_cross_entropy(const float* logits, int64_t ld, const int64_t* 
                                 float* loss_out, void* dlogits_bf16, int64_t ldd, int n, int V, void* stream) {
   VC_CHECK(n > 0 && ld % 4 == 0 && (dlogits_bf16 == nullptr || ldd % 8 == 0), "vc_cross_entropy: ld alignment");
   VC_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ST(stream)));
-  cross_entropy_kernel<<<n, 256, 0, ST(stream)>>>(logits, ld, (const long long*)labels, n_valid, smoothing, loss_out,
-                                                  (__nv_bfloat16*)dlogits_bf16, ldd, V);
+  VC_CUDA(launch_kernel(cross_entropy_kernel, dim3(n), dim3(256), 0, ST(stream), logits, ld, (const long long*)labels, n_valid, smoothing, loss_out,
+                                                  (__nv_bfloat16*)dlogits_bf16, ldd, V));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream) {
   const int rpb = 64;
   dim3 grid((N + 255) / 256, (M + rpb - 1) / rpb);
-  colsum_bf16_kernel<<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, ld, out, M, N, rpb);
+  VC_CUDA(launch_kernel(colsum_bf16_kernel, dim3(grid), dim3(256), 0, ST(stream), (const __nv_bfloat16*)x, ld, out, M, N, rpb));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -343,16 +365,16 @@ extern "C" int vc_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_
                                 void* stream) {
   VC_CHECK(N % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "vc_cast_f32_bf16: alignment");
   const long long total = (long long)M * (N / 4);
-  cast_f32_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(src, lds, (__nv_bfloat16*)dst, ldd, M, N,
-                                                                               scale);
+  VC_CUDA(launch_kernel(cast_f32_bf16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), src, lds, (__nv_bfloat16*)dst, ldd, M, N,
+                                                                               scale));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_copy_rows_bf16(const void* src, void* dst, int B, int T, int C, int E, int row_off, void* stream) {
   VC_CHECK(C % 8 == 0, "vc_copy_rows_bf16: C must be x8");
   const long long total = (long long)B * T * (C / 8);
-  copy_rows_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>((const __nv_bfloat16*)src,
-                                                                                (__nv_bfloat16*)dst, B, T, C, E, row_off);
+  VC_CUDA(launch_kernel(copy_rows_bf16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), (const __nv_bfloat16*)src,
+                                                                                (__nv_bfloat16*)dst, B, T, C, E, row_off));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -37,6 +37,8 @@ norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
                 __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, float* __restrict__ rstd_out,
                 float* __restrict__ mean_out, int M, int D, float eps, float out_scale, RowMap map, uint32_t drop_seed_in,
                 uint32_t drop_p16, const uint32_t* salt) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t drop_seed = drop_salted(drop_seed_in, salt);
   const int lane = threadIdx.x & 31;
   const int nv = D / 128;
@@ -107,6 +109,8 @@ norm_bwd_kernel(const void* __restrict__ g_raw, const float* __restrict__ x, con
                 __nv_bfloat16* __restrict__ dx_bf16, int accumulate_dx, float* __restrict__ dw, float* __restrict__ db,
                 int M, int D, float scale, RowMap map, uint32_t g_drop_seed_in, uint32_t g_drop_p16, uint32_t dxb_drop_seed_in,
                 uint32_t dxb_drop_p16, const uint32_t* salt) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t g_drop_seed = drop_salted(g_drop_seed_in, salt), dxb_drop_seed = drop_salted(dxb_drop_seed_in, salt);
   __shared__ float red[8][kMaxV4 * 128 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -216,11 +220,11 @@ extern "C" int vc_norm_fwd(int kind, const float* x, const float* w, const float
   RowMap map{rows_per_batch, out_batch_stride, out_row_offset};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (kind == 0)
-    norm_fwd_kernel<false><<<norm_grid(M), 256, 0, st>>>(x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
-                                                         eps, out_scale, map, drop_seed, drop_p16, drop_salt_ptr());
+    VC_CUDA(launch_kernel(norm_fwd_kernel<false>, dim3(norm_grid(M)), dim3(256), 0, st, x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
+                                                         eps, out_scale, map, drop_seed, drop_p16, drop_salt_ptr()));
   else
-    norm_fwd_kernel<true><<<norm_grid(M), 256, 0, st>>>(x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
-                                                        eps, out_scale, map, drop_seed, drop_p16, drop_salt_ptr());
+    VC_CUDA(launch_kernel(norm_fwd_kernel<true>, dim3(norm_grid(M)), dim3(256), 0, st, x, w, bias, (__nv_bfloat16*)out_bf16, out_f32, rstd, mean, M, D,
+                                                        eps, out_scale, map, drop_seed, drop_p16, drop_salt_ptr()));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -233,10 +237,10 @@ extern "C" int vc_norm_bwd(int kind, const void* g, int g_bf16, const float* x, 
   VC_CHECK(kind == 0 || kind == 1, "vc_norm_bwd: kind 0=rms 1=layernorm");
   RowMap map{rows_per_batch, g_batch_stride, g_row_offset};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define VC_NB(LN, GB)                                                                                              \
-  norm_bwd_kernel<LN, GB><<<norm_grid(M), 256, 0, st>>>(g, x, w, rstd, mean, dx, (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, \
-                                                        db, M, D, scale, map, g_drop_seed, g_drop_p16, dxb_drop_seed,   \
-                                                        dxb_drop_p16, drop_salt_ptr())
+#define VC_NB(LN, GB)                                                                                                   \
+  VC_CUDA(launch_kernel(norm_bwd_kernel<LN, GB>, dim3(norm_grid(M)), dim3(256), 0, st, g, x, w, rstd, mean, dx,         \
+                        (__nv_bfloat16*)dx_bf16, accumulate_dx, dw, db, M, D, scale, map, g_drop_seed, g_drop_p16,      \
+                        dxb_drop_seed, dxb_drop_p16, drop_salt_ptr()))
   if (kind == 0) { if (g_bf16) VC_NB(false, true); else VC_NB(false, false); }
   else           { if (g_bf16) VC_NB(true, true); else VC_NB(true, false); }
 #undef VC_NB

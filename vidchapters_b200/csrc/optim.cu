@@ -14,6 +14,8 @@
 namespace vc {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8];
   float s = 0.f;
   const long long n4 = n / 4;
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             __nv_bfloat16* __restrict__ p_bf16, long long n, float lr, float b1, float b2, float eps, float bc1,
             float rsqrt_bc2, const float* __restrict__ norm_sq, float clip_max_norm, float grad_scale) {
+  pdl_wait();
+  pdl_trigger();
   float coef = grad_scale;
   if (norm_sq && clip_max_norm > 0.f) {
     const float total = sqrtf(*norm_sq) * grad_scale;
@@ -69,6 +73,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 // sums[0] += sum of row norms over rows [0, V-nb);  sums[1] += over rows [V-nb, V).  One warp per row.
 __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ w, int V, int d, int nb, float* __restrict__ sums) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int wt = gridDim.x * (blockDim.x >> 5);
   float acc0 = 0.f, acc1 = 0.f;
@@ -89,6 +95,8 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
 // rows [V-nb, V) /= (mean_train / mean_frozen)
 __global__ void renorm_apply_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ w_bf16, int V, int d, int nb,
                                     const float* __restrict__ sums) {
+  pdl_wait();
+  pdl_trigger();
   const float frozen = sums[0] / (float)(V - nb);
   const float train = sums[1] / (float)nb;
   const float div = train / frozen;
@@ -102,6 +110,8 @@ __global__ void renorm_apply_kernel(float* __restrict__ w, __nv_bfloat16* __rest
 }
 
 __global__ void cast_flat_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(src)[i];
@@ -118,7 +128,7 @@ using namespace vc;
 
 extern "C" int vc_sumsq(const float* g, int64_t n, float* out_accum, void* stream) {
   VC_CHECK(n > 0 && ((uintptr_t)g & 15) == 0, "vc_sumsq: bad args");
-  sumsq_kernel<<<num_sms() * 8, 256, 0, ST(stream)>>>(g, n, out_accum);
+  VC_CUDA(launch_kernel(sumsq_kernel, dim3(num_sms() * 8), dim3(256), 0, ST(stream), g, n, out_accum));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
@@ -128,22 +138,22 @@ extern "C" int vc_adam_step(float* p, const float* g, float* m, float* v, void* 
   VC_CHECK(n > 0 && n % 4 == 0 && step >= 1, "vc_adam_step: n must be a multiple of 4, step >= 1");
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<num_sms() * 8, 256, 0, ST(stream)>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, (float)bc1,
-                                                      (float)(1.0 / sqrt(bc2)), norm_sq, clip_max_norm, grad_scale);
+  VC_CUDA(launch_kernel(adam_kernel, dim3(num_sms() * 8), dim3(256), 0, ST(stream), p, g, m, v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, (float)bc1,
+                                                      (float)(1.0 / sqrt(bc2)), norm_sq, clip_max_norm, grad_scale));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_renorm_time_tokens(float* w, void* w_bf16, int V, int d, int num_bins, float* scratch2, void* stream) {
   VC_CHECK(V > num_bins && num_bins > 0 && d % 4 == 0, "vc_renorm_time_tokens: bad dims");
   VC_CUDA(cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), ST(stream)));
-  rownorm_kernel<<<num_sms() * 4, 256, 0, ST(stream)>>>(w, V, d, num_bins, scratch2);
-  renorm_apply_kernel<<<(num_bins * d + 255) / 256, 256, 0, ST(stream)>>>(w, (__nv_bfloat16*)w_bf16, V, d, num_bins, scratch2);
+  VC_CUDA(launch_kernel(rownorm_kernel, dim3(num_sms() * 4), dim3(256), 0, ST(stream), w, V, d, num_bins, scratch2));
+  VC_CUDA(launch_kernel(renorm_apply_kernel, dim3((num_bins * d + 255) / 256), dim3(256), 0, ST(stream), w, (__nv_bfloat16*)w_bf16, V, d, num_bins, scratch2));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }
 extern "C" int vc_cast_flat_bf16(const float* src, void* dst, int64_t n, void* stream) {
   VC_CHECK(n > 0, "vc_cast_flat_bf16: n");
-  cast_flat_kernel<<<num_sms() * 8, 256, 0, ST(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  VC_CUDA(launch_kernel(cast_flat_kernel, dim3(num_sms() * 8), dim3(256), 0, ST(stream), src, (__nv_bfloat16*)dst, n));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

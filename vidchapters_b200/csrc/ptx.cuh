@@ -228,6 +228,16 @@ __device__ __forceinline__ void drop_select(float* v, uint32_t row_key, uint32_t
 __device__ __forceinline__ uint32_t drop_salted(uint32_t seed, const uint32_t* salt) { return salt ? seed ^ __ldg(salt) : seed; }
 __device__ __forceinline__ float drop_scale(uint32_t p16) { return 65536.0f / (float)(65536u - p16); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (common.h::
+// launch_kernel): its CTAs may become resident — and run their prologue: barrier init, TMEM allocation, tensor-map
+// prefetch — while the previous kernel of the stream is still draining.  pdl_wait() blocks until that kernel has
+// completed and its memory is visible; it must precede the first access to global memory.  pdl_trigger() lets the
+// NEXT kernel start its own launch/prologue early (it still waits in its pdl_wait()).  Both are no-ops for a kernel
+// launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;

@@ -492,10 +492,11 @@ class Vid2SeqEngine:
                  phase: Optional[int] = None):
         """Accumulates d(loss)/d(params) * grad_loss into flat_g.  Returns d/d(cached video) when the forward consumed
         a cached visual-encoder output (so it can flow back to the pass that produced it), else None.
-        phase=None runs everything; phase=1 runs head + decoder only (the decoder's gradients are then final and can be
-        all-reduced while phase=2, text encoder + visual encoder, runs)."""
-        if phase == 2:
-            return self._backward_phase2(ctx, grad_video)
+        phase=None runs everything.  Data-parallel overlap (graphed.py): phase=1 runs head + decoder (the decoder's
+        gradients are then final and are all-reduced while the rest runs), phase=2 the text encoder (after it `shared` and
+        the encoder are final), phase=3 the visual encoder."""
+        if phase in (2, 3):
+            return self._backward_phase2(ctx, grad_video, part=phase)
         ops, d = self.ops, self.d
         bf = torch.bfloat16
         tape = ctx["tape"]
@@ -540,19 +541,21 @@ class Vid2SeqEngine:
             return None
         return self._backward_phase2(ctx, grad_video)
 
-    def _backward_phase2(self, ctx, grad_video):
+    def _backward_phase2(self, ctx, grad_video, part=None):
+        """part None: text encoder + visual encoder; 2: text encoder only; 3: visual encoder only (after 2)."""
         ops, d = self.ops, self.d
         bf = torch.bfloat16
         tape = ctx["tape"]
         B, T, L, S, E = ctx["B"], ctx["T"], ctx["L"], ctx["S"], ctx["E"]
-        dmem, i, ws = ctx.pop("_bwd_state")
+        dmem, i, ws = ctx["_bwd_state"] if part == 2 else ctx.pop("_bwd_state")
+        do_enc = part in (None, 2)
 
         def out_drop(j):
             return tape[j]["d_out"] if j >= 0 else NO_DROP
-        if grad_video is not None and self.use_video:
+        if grad_video is not None and self.use_video and part in (None, 2):
             dmem.view(B, E, d)[:, :T].add_(grad_video.reshape(B, T, d).to(dmem.dtype))
         # ---- text encoder
-        if self.use_speech:
+        if self.use_speech and do_enc:
             dx = self._e(B * L, d)
             dxb = self._e(B * L, d, dtype=bf)
             ops.norm_bwd(0, dmem, ctx["enc_x"], self.pv("t5_model.encoder.final_layer_norm.weight"), ctx["enc_rstd"], None,
@@ -568,6 +571,9 @@ class Vid2SeqEngine:
                 i -= 2
             ops.bias_fold(drel_e, ctx["lut_e"], self.g(self.enc_bias_name))
             ops.embed_bwd(ctx["enc_ids"].view(-1), dx, self.g("t5_model.shared.weight"), drop=ctx["d_emb_e"])
+        if part == 2:   # the saved tape index already points past the text-encoder entries
+            ctx["_bwd_state"] = (dmem, i, ws)
+            return None
         # ---- visual encoder
         dvideo_out = None
         if self.use_video:

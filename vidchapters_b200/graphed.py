@@ -51,16 +51,19 @@ class GraphedTrainStep:
                 self.loss = self._fwd_bwd(phase=1)
             self.graph2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
-                self._bwd_phase2()
+                self.model.engine.backward(self._ectx, phase=2)
+            self.graph3 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph3, pool=self.graph.pool()):
+                self._bwd_phase3()
         else:
             with torch.cuda.graph(self.graph):
                 self.loss = self._fwd_bwd()
         self.launches_per_replay = ops.launches - n0   # libvidchap kernels inside the captured graph(s)
         self.replays = 0
 
-    def _bwd_phase2(self):
+    def _bwd_phase3(self):
         eng = self.model.engine
-        eng.backward(self._ectx, phase=2)
+        eng.backward(self._ectx, phase=3)
         self._ectx = None
         self.model._end_backward()
 
@@ -101,10 +104,13 @@ class GraphedTrainStep:
         eng = self.model.engine
         lo, hi = eng.decoder_grad_range()
         pg = self.optimizer.pg
-        w1 = torch.distributed.all_reduce(eng.flat_g[lo:hi], group=pg, async_op=True)   # overlaps graph2 below
+        # flat_g = [shared | text encoder | decoder | visual encoder, proj]: each region is all-reduced by NCCL (its own
+        # stream) as soon as the phase that finishes it has been enqueued, overlapping the phases that follow
+        w1 = torch.distributed.all_reduce(eng.flat_g[lo:hi], group=pg, async_op=True)   # decoder, during phases 2-3
         self.graph2.replay()
-        w2 = torch.distributed.all_reduce(eng.flat_g[:lo], group=pg, async_op=True)
-        w3 = torch.distributed.all_reduce(eng.flat_g[hi:], group=pg, async_op=True)
+        w2 = torch.distributed.all_reduce(eng.flat_g[:lo], group=pg, async_op=True)     # shared + text encoder, during 3
+        self.graph3.replay()
+        w3 = torch.distributed.all_reduce(eng.flat_g[hi:], group=pg, async_op=True)     # visual encoder (+ proj)
         for w in (w1, w2, w3):
             w.wait()
         self.optimizer.step(grads_already_reduced=True)
