@@ -314,17 +314,20 @@ def main():
         "loss": loss_e2e,
         "step_tflops_algorithmic": step_tflop,
         "step_tensor_frac": (step_tflop / (ms_step * 1e-3)) / sustained,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all %d launches of one step)" % len(rec),
+        "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_kernel / gemm_bf16_kernel (tcgen05 cta_group::2 / ::1; all %d launches of one step, "
+                               "each timed with CUDA events in an eager instrumented step)" % len(rec),
                      "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                      "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
                      "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_step, "traffic": None},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:
-        med, n = cpu_oracle_step_time(dict(T5_BASE), 1, 10, 64, 32, steps=5, warmup=2, budget_s=60)
-        line["cpu_baseline"] = {"value": 106 / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"BASELINE configs[0]: t5-base fp32, 1 video, 10 frames, 64 ASR, 32 target tok; "
-                                          f"full dvc.py step via the oracle port; median of {n} steps = {med:.3f} s"}
+        # bounded sample of the SAME workload: 1 video of configs[1]'s shape per step (the --impl reference arm's sample)
+        med, n = cpu_oracle_step_time(dict(T5_BASE), 1, T, L, S, steps=5, warmup=1, budget_s=40)
+        line["cpu_baseline"] = {"value": (T + L + S) / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"1 video/step of configs[1]'s shape ({T} frames, {L} ASR, {S} target tok), t5-base "
+                                          f"fp32, dropout off; full dvc.py step via the oracle port; median of {n} steps = "
+                                          f"{med:.3f} s"}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -222,6 +222,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = quarter * 32 + lane;
     const int ct = (warp - 2) * 32 + lane;   // 0..255: index among the compute threads
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float drop_sc = p.drop_p16 ? drop_scale(p.drop_p16) : 1.0f;
     for (int i = 0; i < nqt; ++i) {
       const int q0 = (qt0 + i) * kBT;
       const int q = q0 + r;
@@ -236,6 +237,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool fast = !causal_tile && (s_nonuni_v[qt0 + i] | *s_anypen) == 0;
       const bool tile_sum = p.dbias_rel && !causal_tile && (s_nonuni_b[qt0 + i] | *s_anypen) == 0 && fast;
       const float c_fast = s_bias[max(p.Lq - kBT - q0, 0) + 1] - lse2;
+      const float nds = -delta * p.scale;          // -delta * scale
+      const float sc_s = drop_sc * p.scale;        // dropout 1/(1-p) * scale
       float ds_sum = 0.f;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
@@ -274,22 +277,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               sv[j + e] = fast_exp2(fminf(fmaf(sv[j + e], p.scale_log2e, bk[j + e]), pen[e]) - lse2);
           }
         }
+        // ds (already multiplied by `scale`, the factor dK/dQ need) = p * scale * (dP - delta); with dropout
+        // O = (mask.P).V * sc: dV accumulates the masked, UNSCALED P (sc is applied once when dV is stored) and dP flows
+        // back through the same mask: ds = p * scale * (keep ? dP*sc - delta : -delta).
         if (p.drop_p16) {
-          // O = (mask.P).V * sc: dV accumulates the masked, UNSCALED P (sc is applied once when dV is stored) and dP
-          // flows back through the same mask: ds = p * (keep ? dP*sc - delta : -delta).
-          const float sc = drop_scale(p.drop_p16);
           const uint32_t rk = drop_row_key(drop_salted(p.drop_seed, p.drop_salt), ((unsigned long long)b * p.H + h) * p.Lq + q);
           const uint32_t hsh = drop_block_hash(rk, (uint32_t)(k0 + c * 32)), thr = drop_threshold(p.drop_p16);
-          const float ndelta = -delta;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const bool keep = drop_keep_h(hsh, j, thr);
-            dp[j] = sv[j] * (keep ? fmaf(dp[j], sc, ndelta) : ndelta);
+            dp[j] = sv[j] * (keep ? fmaf(dp[j], sc_s, nds) : nds);
             sv[j] = keep ? sv[j] : 0.0f;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dp[j] = sv[j] * (dp[j] - delta);
+          for (int j = 0; j < 32; ++j) dp[j] = sv[j] * fmaf(dp[j], p.scale, nds);
         }
         if (tile_sum) {
 #pragma unroll
@@ -306,8 +308,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (j >= lane) a_pos += w; else a_neg += w;
           }
           const int slot = c * 32 - quarter * 32 + (p.Lq - 1 - q0) + lane;   // (k - k0) + (Lq - 1 - q) of diagonal +lane
-          if (slot >= 0 && a_pos != 0.f) atomicAdd(&s_rel[slot], a_pos);
-          if (slot >= 32 && a_neg != 0.f) atomicAdd(&s_rel[slot - 32], a_neg);
+          if (slot >= 0 && a_pos != 0.f) atomicAdd(&s_rel[slot], a_pos * p.inv_scale);   // d(bias) wants the unscaled ds
+          if (slot >= 32 && a_neg != 0.f) atomicAdd(&s_rel[slot - 32], a_neg * p.inv_scale);
         }
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
         uint8_t* drow = sDS + (c >> 1) * 16384 + r * 128;
@@ -318,10 +320,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               make_uint4(pack_bf16x2(sv[g * 8 + 0], sv[g * 8 + 1]), pack_bf16x2(sv[g * 8 + 2], sv[g * 8 + 3]),
                          pack_bf16x2(sv[g * 8 + 4], sv[g * 8 + 5]), pack_bf16x2(sv[g * 8 + 6], sv[g * 8 + 7]));
           *reinterpret_cast<uint4*>(drow + ch) =
-              make_uint4(pack_bf16x2(dp[g * 8 + 0] * p.scale, dp[g * 8 + 1] * p.scale),
-                         pack_bf16x2(dp[g * 8 + 2] * p.scale, dp[g * 8 + 3] * p.scale),
-                         pack_bf16x2(dp[g * 8 + 4] * p.scale, dp[g * 8 + 5] * p.scale),
-                         pack_bf16x2(dp[g * 8 + 6] * p.scale, dp[g * 8 + 7] * p.scale));
+              make_uint4(pack_bf16x2(dp[g * 8 + 0], dp[g * 8 + 1]), pack_bf16x2(dp[g * 8 + 2], dp[g * 8 + 3]),
+                         pack_bf16x2(dp[g * 8 + 4], dp[g * 8 + 5]), pack_bf16x2(dp[g * 8 + 6], dp[g * 8 + 7]));
         }
       }
       fence_proxy_async_smem();
@@ -332,7 +332,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // one bucket for the whole tile: deposit the tile's total at one of its relative positions (k = k0, q = q0)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ds_sum += __shfl_xor_sync(0xffffffffu, ds_sum, o);
-        if (lane == 0) atomicAdd(&s_rel[p.Lq - 1 - q0], ds_sum);
+        if (lane == 0) atomicAdd(&s_rel[p.Lq - 1 - q0], ds_sum * p.inv_scale);
       }
       // ---- dQ_i: TMEM -> swizzled smem staging -> ONE TMA reduce-add per 32-column half (whole 128-byte lines into the
       // fp32 dQ accumulator) instead of 2048 scattered 16-byte atomics per tile.
@@ -376,9 +376,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32((which == 0 ? tDV : tDK) + lane_off + half * 32, v);
         tmem_ld_wait();
         if (which == 0 && p.drop_p16) {   // dropout scale of the probabilities, applied once per output instead of per element
-          const float sc = drop_scale(p.drop_p16);
 #pragma unroll
-          for (int g = 0; g < 32; ++g) v[g] *= sc;
+          for (int g = 0; g < 32; ++g) v[g] *= drop_sc;
         }
         if (kk < p.Lk) {
           uint4* dst = reinterpret_cast<uint4*>(base + ((long long)b * p.Lk + kk) * ld + col + h * kBD + half * 32);

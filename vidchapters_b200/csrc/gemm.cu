@@ -276,6 +276,7 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   p.alpha_dev = a->alpha_dev;
   p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16; p.drop_salt = drop_salt_ptr();
   p.tma_epi = tma_epi_mode() && (a->ldr % 4 == 0);
+  p.aux_tma = p.tma_epi && epi_aux_by_tma(a);
   EpiMaps em;
   if (p.tma_epi) {
     int se = make_epi_maps(&em, a);

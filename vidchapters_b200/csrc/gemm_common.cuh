@@ -31,6 +31,7 @@ struct GemmParams {
   uint32_t drop_seed, drop_p16;  // dropout applied after the activation, before the residual add (p16 = 0: off)
   const uint32_t* drop_salt;     // optional device salt XORed into drop_seed
   int tma_epi;                   // 1: epilogue I/O staged through shared memory and moved by TMA (see below)
+  int aux_tma;                   // 1: the activation-backward operand `aux` arrives by TMA too (EpiMaps::resid maps it)
 };
 
 // Tensor maps of the epilogue's global operands (32 x 32 boxes; fp32: SWIZZLE_128B, bf16: SWIZZLE_64B).
@@ -209,11 +210,14 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
     if (p.residual && !two_stores) {
       mbar_arrive_expect_tx(wbar, 4096);
       tma_load_2d(stage, &em.resid, wbar, col0, row0);
+    } else if (p.aux_tma) {   // saved pre-activation block (bf16 32 x 32): whole lines instead of 32 scattered rows
+      mbar_arrive_expect_tx(wbar, 2048);
+      tma_load_2d(stage, &em.resid, wbar, col0, row0);
     }
   }
   __syncwarp();
   uint4 ax[4];
-  if (p.act >= 3) {
+  if (p.act >= 3 && !p.aux_tma) {
     if (full) {
       const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ld_aux + col0);
 #pragma unroll
@@ -273,6 +277,13 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   } else if (p.act >= 3) {
+    if (p.aux_tma) {
+      mbar_wait(wbar, wphase);
+      wphase ^= 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ax[j] = *reinterpret_cast<const uint4*>(stage + epi_off_bf16(lane, j));
+      __syncwarp();   // every lane has read its row before the tile is overwritten with the result
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t w[4] = {ax[j].x, ax[j].y, ax[j].z, ax[j].w};
@@ -322,6 +333,12 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
   }
 }
 
+// act-backward GEMMs (no residual): the `resid` map slot carries the bf16 `aux` matrix instead.
+inline bool epi_aux_by_tma(const vc_gemm_args* a) {
+  return a->act >= 3 && a->aux && !a->residual && !(a->act == 2 && a->pre_out) && a->ld_aux % 8 == 0 &&
+         ((uintptr_t)a->aux & 15) == 0;
+}
+
 // Host side: the three epilogue maps (unused ones alias `out`).
 inline int make_epi_maps(EpiMaps* em, const vc_gemm_args* a) {
   const int oe = a->out_fp32 ? 4 : 2;
@@ -331,6 +348,7 @@ inline int make_epi_maps(EpiMaps* em, const vc_gemm_args* a) {
   em->resid = em->out;
   if (a->pre_out && (s = make_tmap_2d_ex(&em->pre, a->pre_out, 2, a->N, a->M, a->ldo, 32, 32, 64)) != VC_OK) return s;
   if (a->residual && (s = make_tmap_2d_ex(&em->resid, a->residual, 4, a->N, a->M, a->ldr, 32, 32, 128)) != VC_OK) return s;
+  if (epi_aux_by_tma(a) && (s = make_tmap_2d_ex(&em->resid, a->aux, 2, a->N, a->M, a->ld_aux, 32, 32, 64)) != VC_OK) return s;
   return VC_OK;
 }
 
