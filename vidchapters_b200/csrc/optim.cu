@@ -13,6 +13,39 @@
 
 namespace vc {
 
+// Deterministic grid reduction: every block writes its partial sums, the last block to finish (atomic ticket) adds
+// them up in index order.  The result must be bit-identical on every data-parallel rank: the clip coefficient and the
+// time-token renorm factor derive from these sums, and ranks that round them differently drift apart (float atomics in
+// arrival order did exactly that: tools/dp_check_gpu.py).  One reduction of each kind in flight at a time (one stream).
+constexpr int kMaxRedBlocks = 4096;
+__device__ float g_red_part[2][kMaxRedBlocks];
+__device__ unsigned int g_red_ticket[2];
+
+// vals[NV] are this block's partials (valid in thread 0); out[k] += total_k.  `slot` selects the scratch (0 sumsq, 1 rownorm).
+template <int NV>
+__device__ __forceinline__ void grid_reduce_ordered(const float (&vals)[NV], int slot, float* out) {
+  __shared__ bool last;
+  float* part = &g_red_part[0][0] + slot * kMaxRedBlocks;   // NV * gridDim.x <= kMaxRedBlocks per slot
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) part[k * gridDim.x + blockIdx.x] = vals[k];
+    __threadfence();
+    last = atomicInc(&g_red_ticket[slot], gridDim.x - 1) == gridDim.x - 1;   // wraps to 0: ready for the next launch
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float t = 0.f;
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) t += __ldcg(part + k * gridDim.x + i);   // fixed order per lane
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);                        // fixed tree
+      if (threadIdx.x == 0) out[k] += t;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
   pdl_wait();
   pdl_trigger();
@@ -29,11 +62,10 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    atomicAdd(out, t);
-  }
+  float t[1] = {0.f};
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 8; ++i) t[0] += red[i];
+  grid_reduce_ordered<1>(t, 0, out);
 }
 
 // p,m,v updated in place; g is multiplied by grad_scale*clip_coef on the fly.  bias corrections follow torch.optim.Adam:
@@ -87,10 +119,13 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
     const float nrm = sqrtf(s);
     if (r < V - nb) acc0 += nrm; else acc1 += nrm;
   }
-  if (lane == 0) {
-    if (acc0 != 0.f) atomicAdd(sums + 0, acc0);
-    if (acc1 != 0.f) atomicAdd(sums + 1, acc1);
-  }
+  __shared__ float red[2][8];
+  if (lane == 0) { red[0][threadIdx.x >> 5] = acc0; red[1][threadIdx.x >> 5] = acc1; }
+  __syncthreads();
+  float t[2] = {0.f, 0.f};
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 8; ++i) { t[0] += red[0][i]; t[1] += red[1][i]; }
+  grid_reduce_ordered<2>(t, 1, sums);
 }
 // rows [V-nb, V) /= (mean_train / mean_frozen)
 __global__ void renorm_apply_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ w_bf16, int V, int d, int nb,
