@@ -211,10 +211,47 @@ class Vid2SeqEngine:
     def _z(self, *shape, dtype=torch.float32):
         return torch.zeros(*shape, dtype=dtype, device=self.device)
 
+    _splits_cache: Dict[tuple, int] = {}
+
     def _splits(self, n_out, k_out, red):
-        tiles = ((n_out + 127) // 128) * ((k_out + 255) // 256)
-        s = max(1, min((red + 63) // 64 // 4, -(-222 // tiles)))   # ~1.5 waves of tiles, >= 4 k-blocks per split
-        return s
+        """Split-K factor of a weight-gradient GEMM dW[n_out, k_out] = dY^T.X over `red` tokens.  Mirrors the tile
+        dispatch of vc_gemm_bf16 (csrc/gemm.cu: CTA-pair kernel, 256 x {256,128} tiles on 74 clusters) and minimises
+        waves x (k-blocks per split + per-tile overhead): e.g. 768x768 over 4096 tokens runs as 8 splits = one full wave
+        of 8 k-blocks instead of 13 splits = 1.6 waves of 5."""
+        import os
+        if os.environ.get("VIDCHAP_SPLITS_OLD") == "1":   # A/B switch for bench runs
+            tiles = ((n_out + 127) // 128) * ((k_out + 255) // 256)
+            return max(1, min((red + 63) // 64 // 4, -(-222 // tiles)))
+        key = (n_out, k_out, red)
+        if key in self._splits_cache:
+            return self._splits_cache[key]
+        kb = (red + 63) // 64
+        clusters, overhead = 74, 6.0      # per-tile prologue + fp32 reduce-add epilogue, in units of one 256x256 k-block
+        tiles1 = ((n_out + 127) // 128) * ((k_out + 255) // 256)
+        s_base = max(1, min(kb // 4, -(-222 // tiles1)))   # baseline: ~1.5 waves of 128x256 tiles, >= 4 k-blocks per split
+        costs = {}
+        best = (float("inf"), 1)
+        for s in range(1, max(1, min(16, kb // 4)) + 1):
+            kbs = -(-kb // s)
+            s_eff = -(-kb // kbs)
+            mb2 = -(-n_out // 256)
+            width = 128
+            for cand in (256, 128):
+                tiles = mb2 * (-(-k_out // cand)) * s_eff
+                if tiles >= clusters or (cand == 128 and tiles >= clusters // 2):
+                    width = cand
+                    break
+            else:
+                tiles = mb2 * (-(-k_out // 128)) * s_eff
+            waves = -(-tiles // clusters)
+            cost = waves * (kbs * (width / 256.0) + overhead)
+            costs[s] = cost
+            if cost < best[0] - 1e-9:
+                best = (cost, s_eff)
+        # keep the baseline unless the model predicts a clear win (its constants are rough)
+        pick = best[1] if best[0] < 0.85 * costs.get(min(s_base, max(costs)), float("inf")) else s_base
+        self._splits_cache[key] = pick
+        return pick
 
     # ------------------------------------------------------------------ sub-layers: forward
     def _sa_fwd(self, x0, sp: _Sub, B, L, bias_rel, kmask, causal, tape, dk="enc"):
