@@ -146,6 +146,14 @@ int vc_kv_append(const void* src, int64_t lds, void* cache, int B, int cap, int 
 int vc_greedy_next(const float* logits, int64_t ld, int V, uint8_t* done, int64_t* ids_out, int64_t* seq, int seq_ld,
                    const int32_t* pos_dev, int64_t eos_id, int64_t pad_id, int B, void* stream);
 int vc_step_advance(int32_t* pos_dev, void* stream);
+/* Beam search (vid2seq.py:150-162 with num_beams > 1; HF-4.28 GenerationMixin.beam_search, third-party): for every batch
+ * item the 2*num_beams best  log_softmax(logits[b*num_beams + r])[v] + beam_scores[b*num_beams + r]  over (r, v), sorted
+ * descending -> out_scores / out_tokens (v) / out_beams (r), each [B, 2*num_beams].  num_beams <= 8. */
+int vc_beam_topk(const float* logits, int64_t ld, int V, const float* beam_scores, int num_beams, int B, float* out_scores,
+                 int32_t* out_tokens, int32_t* out_beams, void* stream);
+/* KV-cache rows [0, n) of every sequence follow their beam: dst[b] = src[beam_idx[b]] (HF _reorder_cache,
+ * modeling_t5.py:1771-1793).  src/dst: bf16 [Bn, cap, C], distinct buffers. */
+int vc_kv_reorder(const void* src, void* dst, const int32_t* beam_idx, int Bn, int cap, int C, int n, void* stream);
 
 /* ---- Optimiser tail over the flat parameter buffer (dvc.py:112-126). */
 int vc_sumsq(const float* g, int64_t n, float* out_accum, void* stream);               /* out_accum[0] += |g|^2 */

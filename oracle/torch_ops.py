@@ -326,6 +326,18 @@ class TorchOps:
         if pos + 1 < seq.shape[1]:
             seq[:, pos + 1] = nxt
 
+    def beam_topk(self, logits, beam_scores, num_beams, out_scores, out_tokens, out_beams):
+        Bn, V = logits.shape
+        B = Bn // num_beams
+        sc = torch.log_softmax(logits.float(), dim=-1) + beam_scores.view(-1, 1)
+        s, i = torch.topk(sc.view(B, num_beams * V), 2 * num_beams, dim=1, largest=True, sorted=True)
+        out_scores.copy_(s)
+        out_tokens.copy_((i % V).to(torch.int32))
+        out_beams.copy_((i // V).to(torch.int32))
+
+    def kv_reorder(self, src, dst, beam_idx, n):
+        dst[:, :n].copy_(src[beam_idx.long(), :n])
+
     def step_advance(self, pos_dev):
         pos_dev.add_(1)
 

@@ -317,3 +317,98 @@ def greedy_decode(sd, cfg, memory, mem_mask, max_new_tokens=256, emulate_bf16=Fa
         if bool(done.all()):
             break
     return ids
+
+
+# --------------------------------------------------------------------------------------
+# Beam search (vid2seq.py:150-162 with num_beams>1 -> transformers==4.28.0 GenerationMixin.beam_search +
+# BeamSearchScorer; third-party code that is NOT under /root/reference and not installable here, so this restates the
+# published algorithm: PARITY UNPINNED for this function — no reference test or golden vector exercises it).
+# --------------------------------------------------------------------------------------
+class _BeamHyps:
+    """One batch item's n-best list (transformers 4.28 BeamHypotheses, early_stopping=False)."""
+
+    def __init__(self, num_beams, length_penalty):
+        self.nb, self.lp, self.beams, self.worst = num_beams, length_penalty, [], 1e9
+
+    def add(self, hyp, sum_logprobs):
+        score = sum_logprobs / (hyp.shape[-1] ** self.lp)      # normalised by the length BEFORE the eos token
+        if len(self.beams) < self.nb or score > self.worst:
+            self.beams.append((score, hyp))
+            if len(self.beams) > self.nb:
+                srt = sorted((s, i) for i, (s, _) in enumerate(self.beams))
+                del self.beams[srt[0][1]]
+                self.worst = srt[1][0]
+            else:
+                self.worst = min(score, self.worst)
+
+    def is_done(self, best_sum_logprobs, cur_len):
+        if len(self.beams) < self.nb:
+            return False
+        return self.worst >= best_sum_logprobs / cur_len ** self.lp
+
+
+def beam_search_decode(sd, cfg, memory, mem_mask, num_beams=4, max_new_tokens=256, length_penalty=1.0,
+                       emulate_bf16=False, eos_id=1, pad_id=0):
+    """HF-4.28 beam search as called by Vid2Seq.generate: decoder_start 0, log_softmax scores, top 2*num_beams per
+    batch item, eos candidates ranked below num_beams are dropped, finished hypotheses scored by
+    sum_logprobs / len**length_penalty, early_stopping=False heuristic, max_new_tokens stop, best hypothesis + eos.
+    Uncached decoder (O(S^2)); for small cases."""
+    ar = Arith(emulate_bf16)
+    B, nb, d = memory.shape[0], num_beams, cfg["d_model"]
+    dev = memory.device
+    mem = memory.repeat_interleave(nb, 0)
+    mm = mem_mask.repeat_interleave(nb, 0)
+    ids = torch.zeros(B * nb, 1, dtype=torch.long, device=dev)
+    beam_scores = torch.zeros(B, nb)
+    beam_scores[:, 1:] = -1e9
+    beam_scores = beam_scores.view(-1)
+    hyps = [_BeamHyps(nb, length_penalty) for _ in range(B)]
+    done = [False] * B
+    max_length = 1 + max_new_tokens
+    while True:
+        mask = torch.ones_like(ids, dtype=torch.bool)
+        seq = t5_decoder(sd, cfg, ids, mask, mem, mm, ar)[:, -1:] * (d ** -0.5)
+        logits = ar.linear(seq, sd["t5_model.shared.weight"])[:, 0].float()
+        scores = torch.log_softmax(logits, dim=-1).cpu() + beam_scores[:, None]
+        V = scores.shape[-1]
+        top_s, top_i = torch.topk(scores.view(B, nb * V), 2 * nb, dim=1, largest=True, sorted=True)
+        top_b, top_t = top_i // V, top_i % V
+        cur_len = ids.shape[-1]
+        n_scores = torch.zeros(B, nb)
+        n_tokens = torch.zeros(B, nb, dtype=torch.long)
+        n_index = torch.zeros(B, nb, dtype=torch.long)
+        for b in range(B):
+            if done[b]:
+                n_tokens[b] = pad_id           # scores 0, indices 0 (finished batch items are padded)
+                continue
+            k = 0
+            for rank in range(2 * nb):
+                tok, sc, bi = int(top_t[b, rank]), float(top_s[b, rank]), b * nb + int(top_b[b, rank])
+                if tok == eos_id:
+                    if rank >= nb:
+                        continue
+                    hyps[b].add(ids[bi].clone().cpu(), sc)
+                else:
+                    n_scores[b, k], n_tokens[b, k], n_index[b, k] = sc, tok, bi
+                    k += 1
+                if k == nb:
+                    break
+            done[b] = done[b] or hyps[b].is_done(float(top_s[b].max()), cur_len)
+        beam_scores = n_scores.view(-1)
+        ids = torch.cat([ids[n_index.view(-1).to(dev)], n_tokens.view(-1, 1).to(dev)], 1)
+        if all(done) or ids.shape[-1] >= max_length:
+            break
+    out = []
+    for b in range(B):
+        if not done[b]:
+            for j in range(nb):
+                hyps[b].add(ids[b * nb + j].clone().cpu(), float(beam_scores[b * nb + j]))
+        best = sorted(hyps[b].beams, key=lambda x: x[0])[-1][1]
+        out.append(best)
+    sent_max = min(max(len(h) for h in out) + 1, max_length)
+    dec = torch.full((B, sent_max), pad_id, dtype=torch.long)
+    for b, h in enumerate(out):
+        dec[b, :len(h)] = h
+        if len(h) < sent_max:
+            dec[b, len(h)] = eos_id
+    return dec

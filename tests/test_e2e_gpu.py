@@ -220,7 +220,49 @@ def test_greedy_generate_cuda_matches_oracle():
     print(f"[generate] greedy ids agreement with the oracle: {agree:.3f}  ids[0]={seq[0].tolist()}")
     assert agree == 1.0
     with pytest.raises(NotImplementedError):
-        m.generate(video, {"input_ids": inp, "attention_mask": inp != 0}, num_beams=4)
+        m.generate(video, {"input_ids": inp, "attention_mask": inp != 0}, num_beams=4, use_nucleus_sampling=True)
+
+
+def test_beam_search_generate_cuda_matches_oracle():
+    """Vid2Seq.generate with the reference's default num_beams=4 (and greedy) on a model that has learnt something:
+    KV-cache decode, vc_beam_topk / vc_kv_reorder and the host n-best bookkeeping vs the uncached oracle restatement of
+    HF-4.28 beam search (oracle/vid2seq_oracle.py::beam_search_decode; parity of THAT against HF is unpinned)."""
+    from oracle import vid2seq_oracle as O
+    from vidchapters_b200 import Vid2SeqAdam
+    fx = torch.load(os.path.join(GOLD, "tiny.pt"), weights_only=False)
+    cfg = fx["cfg"]
+    video, inp, out = fx["video"].cuda(), fx["input_ids"].cuda(), fx["output_ids"].cuda()
+    it = {"input_ids": inp, "attention_mask": inp != 0}
+    ot = {"input_ids": out, "attention_mask": out != 0}
+
+    class TokD(Tok):
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return [" ".join(str(int(t)) for t in row if not (skip_special_tokens and int(t) in (0, 1))) for row in ids]
+
+    for steps in (10, 40):          # a half-trained (flat distributions) and a memorised model
+        m = build(cfg)
+        m.train()
+        opt = Vid2SeqAdam(m, lr=2e-3, clip_max_norm=1.0, world_size=1)
+        for _ in range(steps):
+            ld, _ = m(video, it, ot); opt.zero_grad(); ld["loss"].backward(); opt.step()
+        m.eval()
+        m.t5_tokenizer = TokD(cfg["base_vocab"] + cfg["num_bins"])
+        sd = {k: v.detach().clone() for k, v in m._params.items()}
+        memory, mem_mask, B, E = m.engine.encode(video, inp, inp != 0)
+        mem32 = memory.float().view(B, E, -1)
+        for nb in (1, 4):
+            m.generate(video, it, num_beams=nb, max_length=16)
+            seq = m.last_generated_ids
+            ref = (O.greedy_decode if nb == 1 else lambda *a, **k: O.beam_search_decode(*a, num_beams=nb, **k))(
+                sd, cfg, mem32, mem_mask.long(), max_new_tokens=16, emulate_bf16=True).to(seq.device)
+            n = min(seq.shape[1], ref.shape[1])
+            agree = (seq[:, :n] == ref[:, :n]).float().mean().item()
+            print(f"[generate] steps={steps} num_beams={nb}: ids agreement with the oracle {agree:.3f}; ids[0]={seq[0].tolist()}")
+            # flat distributions (10 steps) may break a near-tie differently under bf16 rounding flips; the memorised model may not
+            assert agree >= (1.0 if steps == 40 else 0.7) and bool((seq[:, n:] == 0).all()) and bool((ref[:, n:] == 0).all())
+        if steps == 40:             # the memorised model reproduces its targets
+            tgt = out[0][out[0] != 0]
+            assert seq[0, 1:1 + len(tgt)].tolist() == tgt.tolist()
 
 
 def test_graphed_train_step_matches_eager_and_redraws_dropout():

@@ -382,3 +382,34 @@ def test_dropout_norm_embed_pos(cuda_ops, torch_ops):
         assert rel(a, r) < (BF16_TOL if a.dtype == torch.bfloat16 else 1e-4), i
     assert 0.08 < (res[0][4] == 0).float().mean().item() < 0.12
     assert 0.17 < (res[0][2] == 0).float().mean().item() < 0.23   # dxb_drop p = 0.2
+
+
+@pytest.mark.parametrize("B,nb,V", [(3, 4, 32200), (2, 1, 1100), (5, 8, 777)])
+def test_beam_topk_and_kv_reorder(cuda_ops, torch_ops, B, nb, V):
+    g = gen(41)
+    Vp = (V + 7) // 8 * 8
+    logits = (torch.randn(B * nb, Vp, generator=g) * 3).to(DEV)[:, :V]
+    bs = (torch.randn(B * nb, generator=g) * 2).to(DEV)
+    bs[1::2] = -1e9 if nb > 1 else bs[1::2]          # dead beams, as at the first step of HF beam search
+    res = []
+    for ops in (cuda_ops, torch_ops):
+        s_ = torch.zeros(B, 2 * nb, device=DEV)
+        t_ = torch.zeros(B, 2 * nb, device=DEV, dtype=torch.int32)
+        b_ = torch.zeros(B, 2 * nb, device=DEV, dtype=torch.int32)
+        ops.beam_topk(logits, bs, nb, s_, t_, b_)
+        res.append((s_, t_, b_))
+    torch.cuda.synchronize()
+    (s0, t0, b0), (s1, t1, b1) = res
+    live = s1 > -1e8                                   # candidates of dead beams tie at -1e9 (fp32): order unspecified
+    assert torch.allclose(s0[live], s1[live], atol=2e-5, rtol=1e-6)
+    assert torch.equal(t0[live], t1[live]) and torch.equal(b0[live], b1[live])
+    assert bool((s0[~live] < -1e8).all())
+    # cache reorder
+    Bn, cap, C, n = B * nb, 24, 2 * 64 * 2, 17
+    src = torch.randn(Bn, cap, C, generator=g).to(DEV).bfloat16()
+    idx = torch.randint(0, Bn, (Bn,), generator=g).to(torch.int32).to(DEV)
+    d0 = torch.zeros_like(src); d1 = torch.zeros_like(src)
+    cuda_ops.kv_reorder(src, d0, idx, n)
+    torch_ops.kv_reorder(src, d1, idx, n)
+    torch.cuda.synchronize()
+    assert torch.equal(d0, d1)

@@ -124,7 +124,7 @@ extern "C" int vc_set_dropout_salt(const uint32_t* dev_ptr) {
   vc::g_drop_salt = dev_ptr;
   return VC_OK;
 }
-extern "C" int vc_version(void) { return 5; }
+extern "C" int vc_version(void) { return 6; }
 extern "C" const char* vc_last_error(void) { return vc::g_err; }
 extern "C" int vc_device_check(void) {
   int dev = 0;

@@ -783,6 +783,172 @@ class Vid2SeqEngine:
             n += 1
         return seq[:, :n + 1].clone()
 
+    def generate_beam(self, memory, mem_mask, B, E, num_beams=4, max_new_tokens=256, length_penalty=1.0, use_graph=None,
+                      eos_id=1, pad_id=0):
+        """Beam search with a KV cache (model/vid2seq.py:150-162 with num_beams > 1, i.e. the reference's default
+        num_beams=4: HF-4.28 `beam_search` + `BeamSearchScorer`, early_stopping=False, length_penalty as given).
+        Device: one decode step for all B*num_beams hypotheses (the greedy step's launch sequence), `vc_beam_topk`
+        (log-softmax + beam scores + top 2*num_beams per batch item) and `vc_kv_reorder` (caches follow their beams,
+        ping-pong between two cache sets so each parity's step is one fixed CUDA graph).  Host: the n-best bookkeeping on
+        B x 2*num_beams candidates per step, as HF does.  Returns int64 [B, <= 1 + max_new_tokens] ids (start token,
+        best hypothesis, eos, pad)."""
+        ops, d, H, inner = self.ops, self.d, self.H, self.inner
+        bf, dev = torch.bfloat16, self.device
+        nb, S = int(num_beams), int(max_new_tokens)
+        Bn, K2 = B * nb, 2 * nb
+        if use_graph is None:
+            use_graph = dev.type == "cuda" and getattr(ops, "name", "") == "cuda"
+        # every beam of a batch item attends to the same memory (HF expands encoder outputs num_beams times)
+        mem_x = memory.view(B, E, d).repeat_interleave(nb, 0).reshape(Bn * E, d).contiguous()
+        mask_x = mem_mask.repeat_interleave(nb, 0).contiguous()
+        kvmem = []
+        for sa, ca, ff in self.dec_blocks:
+            kv = self._e(Bn * E, 2 * inner, dtype=bf)
+            ops.gemm(mem_x, self.pb(ca.kv_w, 2 * inner), kv)
+            kvmem.append(kv)
+        nl = len(self.dec_blocks)
+        caches = [[torch.zeros(Bn, S, 2 * inner, dtype=bf, device=dev) for _ in range(nl)] for _ in range(2)]
+        bias_d = self._e(H, 2 * S - 1)
+        ops.bias_expand(self.p(self.dec_bias_name), self.lut(S, S, False), bias_d)
+        pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        ids = torch.zeros(Bn, dtype=torch.int64, device=dev)            # decoder_start_token_id = 0
+        beam_scores = torch.zeros(Bn, dtype=torch.float32, device=dev)
+        beam_idx = torch.zeros(Bn, dtype=torch.int32, device=dev)
+        top_s = torch.zeros(B, K2, dtype=torch.float32, device=dev)
+        top_t = torch.zeros(B, K2, dtype=torch.int32, device=dev)
+        top_b = torch.zeros(B, K2, dtype=torch.int32, device=dev)
+        Vp = (self.V + 7) // 8 * 8
+        x = self._e(Bn, d)
+        h = self._e(Bn, d, dtype=bf)
+        q = self._e(Bn, inner, dtype=bf)
+        kvn = self._e(Bn, 2 * inner, dtype=bf)
+        ctxb = self._e(Bn, inner, dtype=bf)
+        act = self._e(Bn, self.dff, dtype=bf)
+        logits = self._e(Bn, Vp)[:, :self.V]
+
+        def step(par):
+            cs = caches[par]
+            ops.embed_fwd(ids, self.p("t5_model.shared.weight"), x)
+            for li, (sa, ca, ff) in enumerate(self.dec_blocks):
+                ops.norm_fwd(0, x, self.pv(sa.norm_w), None, out_bf16=h, eps=1e-6)
+                ops.gemm(h, self.pb(sa.qkv_w), q)
+                k_name = sa.qkv_w.replace(".q.weight", ".k.weight")
+                ops.gemm(h, self.pb(k_name, 2 * inner), kvn)
+                ops.kv_append(kvn, cs[li], pos)
+                c2 = cs[li].view(Bn * S, 2 * inner)
+                ops.attn_fwd(q, c2, c2, q_col=0, k_col=0, v_col=inner, B=Bn, H=H, Lq=1, Lk=S, out=ctxb, lse2=None,
+                             bias_rel=bias_d, kmask=None, causal=True, scale=1.0, q_offset_dev=pos, kv_batch_rows=S,
+                             bias_zero=S - 1, bias_len=2 * S - 1)
+                ops.gemm(ctxb, self.pb(sa.o_w), x, residual=x)
+                ops.norm_fwd(0, x, self.pv(ca.norm_w), None, out_bf16=h, eps=1e-6)
+                ops.gemm(h, self.pb(ca.q_w), q)
+                ops.attn_fwd(q, kvmem[li], kvmem[li], q_col=0, k_col=0, v_col=inner, B=Bn, H=H, Lq=1, Lk=E, out=ctxb,
+                             lse2=None, bias_rel=None, kmask=mask_x, causal=False, scale=1.0)
+                ops.gemm(ctxb, self.pb(ca.o_w), x, residual=x)
+                ops.norm_fwd(0, x, self.pv(ff.norm_w), None, out_bf16=h, eps=1e-6)
+                ops.gemm(h, self.pb(ff.w1), act, act=ACT_RELU)
+                ops.gemm(act, self.pb(ff.w2), x, residual=x)
+            ops.norm_fwd(0, x, self.pv("t5_model.decoder.final_layer_norm.weight"), None, out_bf16=h, eps=1e-6,
+                         out_scale=d ** -0.5)
+            ops.gemm(h, self.pb("t5_model.shared.weight"), logits)
+            ops.beam_topk(logits, beam_scores, nb, top_s, top_t, top_b)
+            ops.step_advance(pos)
+
+        def rewind():
+            pos.zero_(); ids.zero_()
+            init = torch.zeros(B, nb)
+            init[:, 1:] = -1e9                      # HF: only beam 0 of every batch item is alive at the start
+            beam_scores.copy_(init.view(-1))
+            for par in range(2):
+                for c in caches[par]:
+                    c.zero_()
+
+        graphs = [None, None]
+        if use_graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step(0)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            for par in range(2):
+                rewind()
+                graphs[par] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graphs[par]):
+                    step(par)
+        rewind()
+
+        # ---- host-side n-best bookkeeping (HF-4.28 BeamSearchScorer.process / finalize, early_stopping=False)
+        hyps = [[] for _ in range(B)]          # per batch item: list of (score, token list)
+        worst = [1e9] * B
+        done = [False] * B
+        seqs = [[0] for _ in range(Bn)]        # tokens of every live beam (start token included)
+        max_length = 1 + S
+        par = 0
+
+        def add_hyp(b, tokens, sum_logprobs):
+            score = sum_logprobs / (len(tokens) ** length_penalty)    # length BEFORE the eos token, as HF
+            if len(hyps[b]) < nb or score > worst[b]:
+                hyps[b].append((score, list(tokens)))
+                if len(hyps[b]) > nb:
+                    srt = sorted((sc, i) for i, (sc, _) in enumerate(hyps[b]))
+                    del hyps[b][srt[0][1]]
+                    worst[b] = srt[1][0]
+                else:
+                    worst[b] = min(score, worst[b])
+
+        while True:
+            if graphs[par] is not None:
+                graphs[par].replay()
+            else:
+                step(par)
+            ts, tt, tb = top_s.cpu(), top_t.cpu(), top_b.cpu()      # one small D2H + sync per step
+            cur_len = len(seqs[0])
+            n_scores = [0.0] * Bn
+            n_tokens = [pad_id] * Bn
+            n_index = [0] * Bn
+            for b in range(B):
+                if done[b]:
+                    continue                   # finished items: scores 0, pad tokens, beam index 0 (as HF)
+                k = 0
+                for rank in range(K2):
+                    tok, sc, bi = int(tt[b, rank]), float(ts[b, rank]), b * nb + int(tb[b, rank])
+                    if tok == eos_id:
+                        if rank >= nb:
+                            continue
+                        add_hyp(b, seqs[bi], sc)
+                    else:
+                        n_scores[b * nb + k], n_tokens[b * nb + k], n_index[b * nb + k] = sc, tok, bi
+                        k += 1
+                    if k == nb:
+                        break
+                if not done[b] and len(hyps[b]) >= nb:
+                    done[b] = worst[b] >= float(ts[b].max()) / cur_len ** length_penalty
+            seqs = [seqs[n_index[j]] + [n_tokens[j]] for j in range(Bn)]
+            if all(done) or len(seqs[0]) >= max_length:
+                break
+            ids.copy_(torch.tensor(n_tokens, dtype=torch.int64), non_blocking=False)
+            beam_scores.copy_(torch.tensor(n_scores, dtype=torch.float32))
+            beam_idx.copy_(torch.tensor(n_index, dtype=torch.int32))
+            n_rows = cur_len                   # cache rows written so far: positions 0 .. cur_len-1
+            for li in range(nl):
+                ops.kv_reorder(caches[par][li], caches[1 - par][li], beam_idx, n_rows)
+            par ^= 1
+        final_scores = n_scores
+        best = []
+        for b in range(B):
+            if not done[b]:
+                for j in range(nb):
+                    add_hyp(b, seqs[b * nb + j], final_scores[b * nb + j])
+            best.append(sorted(hyps[b], key=lambda t: t[0])[-1][1])
+        sent_max = min(max(len(t) for t in best) + 1, max_length)
+        out = torch.full((B, sent_max), pad_id, dtype=torch.int64)
+        for b, t in enumerate(best):
+            out[b, :len(t)] = torch.tensor(t, dtype=torch.int64)
+            if len(t) < sent_max:
+                out[b, len(t)] = eos_id
+        return out.to(dev)
+
     # ------------------------------------------------------------------ optimiser tail (dvc.py:114-126)
     def zero_grad(self):
         self.flat_g.zero_()

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvidchap.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class GemmArgs(C.Structure):
@@ -89,6 +89,8 @@ SIGNATURES = {
     "vc_kv_append": [P, I64, P, I, I, I, P, P],
     "vc_greedy_next": [P, I64, I, P, P, P, I, P, I64, I64, I, P],
     "vc_step_advance": [P, P],
+    "vc_beam_topk": [P, I64, I, P, I, I, P, P, P, P],
+    "vc_kv_reorder": [P, P, P, I, I, I, I, P],
     "vc_set_dropout_salt": [P],
     "vc_version": [],
     "vc_last_error": [],

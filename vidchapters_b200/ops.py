@@ -265,6 +265,28 @@ class CudaOps:
                                            seq.shape[1], _ptr(pos_dev), eos_id, pad_id, B, self._stream()))
         self.launches += 1
 
+    def beam_topk(self, logits, beam_scores, num_beams, out_scores, out_tokens, out_beams):
+        """Top 2*num_beams of log_softmax(logits) + beam_scores per batch item (HF-4.28 beam_search candidate step)."""
+        _chk_cuda(logits, beam_scores, out_scores, out_tokens, out_beams)
+        Bn, V = logits.shape
+        B = Bn // num_beams
+        assert logits.dtype == torch.float32 and logits.stride(1) == 1 and beam_scores.dtype == torch.float32
+        assert out_scores.shape == (B, 2 * num_beams) and out_scores.is_contiguous() and out_scores.dtype == torch.float32
+        assert out_tokens.dtype == torch.int32 and out_beams.dtype == torch.int32
+        assert out_tokens.is_contiguous() and out_beams.is_contiguous() and beam_scores.is_contiguous()
+        _lib.check(self.lib.vc_beam_topk(_ptr(logits), logits.stride(0), V, _ptr(beam_scores), num_beams, B, _ptr(out_scores),
+                                         _ptr(out_tokens), _ptr(out_beams), self._stream()))
+        self.launches += 1
+
+    def kv_reorder(self, src, dst, beam_idx, n):
+        """dst[b, :n] = src[beam_idx[b], :n] for bf16 caches [Bn, cap, C] (HF _reorder_cache)."""
+        _chk_cuda(src, dst, beam_idx)
+        Bn, cap, C = src.shape
+        assert src.dtype == torch.bfloat16 and dst.shape == src.shape and src.is_contiguous() and dst.is_contiguous()
+        assert beam_idx.dtype == torch.int32 and beam_idx.numel() == Bn
+        _lib.check(self.lib.vc_kv_reorder(_ptr(src), _ptr(dst), _ptr(beam_idx), Bn, cap, C, int(n), self._stream()))
+        self.launches += 1
+
     def step_advance(self, pos_dev):
         _chk_cuda(pos_dev)
         _lib.check(self.lib.vc_step_advance(_ptr(pos_dev), self._stream()))

@@ -221,18 +221,24 @@ class Vid2Seq(nn.Module):
     @torch.no_grad()
     def generate(self, video, input_tokenized, use_nucleus_sampling=False, num_beams=4, max_length=256, min_length=1,
                  top_p=0.9, repetition_penalty=1.0, length_penalty=1.0, num_captions=1, temperature=1):
-        """Greedy decoding (num_beams=1, no sampling) runs on the B200 path with a KV cache and a CUDA-graphed step.
-        Beam search / nucleus sampling (HF-4.28 `generate`, third-party code the reference delegates to) are not
-        built yet and raise."""
-        if use_nucleus_sampling or num_beams != 1 or num_captions != 1 or repetition_penalty != 1.0:
-            raise NotImplementedError("vidchapters_b200.Vid2Seq.generate implements greedy decoding only "
-                                      "(num_beams=1, use_nucleus_sampling=False); beam search is SURVEY §8(f) N1")
+        """Greedy (num_beams=1) and beam-search (num_beams 2..8, the reference default is 4) decoding run on the B200
+        path with a KV cache and a CUDA-graphed decode step; the n-best bookkeeping follows HF-4.28's BeamSearchScorer
+        (early_stopping=False).  Nucleus sampling, repetition penalties and several returned captions (HF-4.28
+        `generate` features, third-party code the reference delegates to) are not built and raise."""
+        if use_nucleus_sampling or num_beams < 1 or num_beams > 8 or num_captions != 1 or repetition_penalty != 1.0 \
+                or min_length > 1:
+            raise NotImplementedError("vidchapters_b200.Vid2Seq.generate implements greedy and beam-search decoding "
+                                      "(1 <= num_beams <= 8, repetition_penalty 1.0, min_length 1, one caption)")
         self._refresh_shadow()
         eng = self.engine
         ids = input_tokenized["input_ids"] if self.use_speech else None
         mask = input_tokenized["attention_mask"] if self.use_speech else None
         memory, mem_mask, B, E = eng.encode(video, ids, mask)
-        seq = eng.generate_greedy(memory, mem_mask, B, E, max_new_tokens=max_length)
+        if num_beams == 1:
+            seq = eng.generate_greedy(memory, mem_mask, B, E, max_new_tokens=max_length)
+        else:
+            seq = eng.generate_beam(memory, mem_mask, B, E, num_beams=num_beams, max_new_tokens=max_length,
+                                    length_penalty=length_penalty)
         self.last_generated_ids = seq
         return self.t5_tokenizer.batch_decode(seq, skip_special_tokens=True)
 
