@@ -110,7 +110,8 @@ def t5_config(d_model=768, d_kv=64, d_ff=3072, num_layers=12, num_heads=12, voca
     )
 
 
-def build_reference_vid2seq(cfg: dict, *, vis_drop=0.0, enc_drop=0.0, dec_drop=0.0, label_smoothing=0.1, seed=0):
+def build_reference_vid2seq(cfg: dict, *, vis_drop=0.0, enc_drop=0.0, dec_drop=0.0, label_smoothing=0.1, seed=0,
+                            use_video=True, use_speech=True):
     """Builds the reference Vid2Seq (vid2seq.py:20-56) with seeded random init at `cfg` shapes.
 
     cfg keys: d_model,d_kv,d_ff,num_layers,num_heads,base_vocab,num_bins,num_features,
@@ -155,7 +156,7 @@ def build_reference_vid2seq(cfg: dict, *, vis_drop=0.0, enc_drop=0.0, dec_drop=0
         model = ref.vid2seq.Vid2Seq(
             "t5-base", num_features=cfg["num_features"], embed_dim=cfg["embed_dim"], depth=cfg["depth"],
             heads=cfg["heads"], mlp_dim=cfg["mlp_dim"], vis_drop=vis_drop, tokenizer=tok, enc_drop=enc_drop,
-            dec_drop=dec_drop, use_speech=True, use_video=True, num_bins=cfg["num_bins"],
+            dec_drop=dec_drop, use_speech=use_speech, use_video=use_video, num_bins=cfg["num_bins"],
             label_smoothing=label_smoothing)
     finally:
         T5.resize_token_embeddings = orig_resize

@@ -239,24 +239,35 @@ def t5_decoder(sd, cfg, dec_ids, dec_mask, enc_h, enc_mask, ar: Arith, pfx="t5_m
 
 
 def vid2seq_forward(sd, cfg, video, input_ids, input_mask, output_ids, output_mask, *, emulate_bf16=False,
-                    label_smoothing=0.1, video_is_cached=False, flash_rounding=False, drop_plan=None):
+                    label_smoothing=0.1, video_is_cached=False, flash_rounding=False, drop_plan=None, use_video=True,
+                    use_speech=True):
     """model/vid2seq.py:58-98 (+ modeling_t5.py:1587-1738).  Dropout-free (p=0 / eval) restatement.
+    use_video / use_speech = the reference's --no_video / --no_speech variants (vid2seq.py:59-84): the decoder's memory
+    is the visual tokens, the text-encoder states, or their concatenation.
 
     Returns dict(loss, logits (B,S,V), video (B,T,d), memory (B,T+L,d)).
     """
     ar = Arith(emulate_bf16, flash_rounding, drop_plan)
     d = cfg["d_model"]
-    if video_is_cached:
-        vid = video
+    vid = None
+    if use_video:
+        if video_is_cached:
+            vid = video
+        else:
+            vid = vit_forward(sd, cfg, video, ar)
+            if d != 768:  # vid2seq.py:54-56,64-65
+                vid = ar.linear(vid, sd["proj_v2t.weight"], sd["proj_v2t.bias"])
+        atts_vis = torch.ones(vid.shape[:2], dtype=torch.long, device=vid.device)
+    if use_speech:
+        text = sd["t5_model.shared.weight"][input_ids]  # vid2seq.py:71
+        enc = t5_encoder(sd, cfg, text, input_mask, ar)
+    if use_video and use_speech:
+        memory = torch.cat([vid, enc], dim=1)  # vid2seq.py:78
+        mem_mask = torch.cat([atts_vis, input_mask.to(torch.long)], dim=1)
+    elif use_video:
+        memory, mem_mask = vid, atts_vis       # vid2seq.py:80-82
     else:
-        vid = vit_forward(sd, cfg, video, ar)
-        if d != 768:  # vid2seq.py:54-56,64-65
-            vid = ar.linear(vid, sd["proj_v2t.weight"], sd["proj_v2t.bias"])
-    atts_vis = torch.ones(vid.shape[:2], dtype=torch.long, device=vid.device)
-    text = sd["t5_model.shared.weight"][input_ids]  # vid2seq.py:71
-    enc = t5_encoder(sd, cfg, text, input_mask, ar)
-    memory = torch.cat([vid, enc], dim=1)  # vid2seq.py:78
-    mem_mask = torch.cat([atts_vis, input_mask.to(torch.long)], dim=1)
+        memory, mem_mask = enc, input_mask.to(torch.long)   # vid2seq.py:83-84
     targets = output_ids.masked_fill(output_ids == 0, -100)  # vid2seq.py:86-88
     dec_in = shift_right(targets)
     seq = t5_decoder(sd, cfg, dec_in, output_mask, memory, mem_mask, ar)

@@ -352,3 +352,35 @@ def test_full_size_properties_config2():
     # P3
     l3, g3 = run(video, inp, out, scale=2.0)
     assert rel(g3, 2.0 * g0) < max(1e-2, 3 * floor)
+
+
+@pytest.mark.parametrize("use_video,use_speech", [(True, False), (False, True)], ids=["no_speech", "no_video"])
+def test_modality_variants_cuda(use_video, use_speech):
+    """--no_speech / --no_video (vid2seq.py:59-84) through the drop-in module on the GPU vs the oracle."""
+    from oracle import vid2seq_oracle as O
+    from vidchapters_b200 import Vid2Seq
+    fx = torch.load(os.path.join(GOLD, "tiny.pt"), weights_only=False)
+    cfg = fx["cfg"]
+    tok = Tok(cfg["base_vocab"] + cfg["num_bins"])
+    m = Vid2Seq("t5-base", num_features=cfg["num_features"], embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                heads=cfg["heads"], mlp_dim=cfg["mlp_dim"], vis_drop=0.0, tokenizer=tok, enc_drop=0.0, dec_drop=0.0,
+                num_bins=cfg["num_bins"], t5_config=cfg, seed=0, use_video=use_video, use_speech=use_speech).to("cuda")
+    m.train()
+    video, inp, out = fx["video"].cuda(), fx["input_ids"].cuda(), fx["output_ids"].cuda()
+    ld, vd = m(video, {"input_ids": inp, "attention_mask": inp != 0}, {"input_ids": out, "attention_mask": out != 0})
+    ld["loss"].backward()
+    assert (vd is None) == (not use_video)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m._params.items()}
+    o = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True,
+                          use_video=use_video, use_speech=use_speech)
+    o["loss"].backward()
+    assert abs(ld["loss"].item() - o["loss"].item()) < 1e-3 * abs(o["loss"].item())
+    errs = []
+    for n, p in m._params.items():
+        if sd[n].grad is None:
+            assert p.grad is None or float(p.grad.abs().sum()) == 0.0, n
+        else:
+            errs.append((rel(p.grad, sd[n].grad), n))
+    errs.sort(reverse=True)
+    print(f"[variant video={use_video} speech={use_speech}] loss {ld['loss'].item():.5f} vs oracle {o['loss'].item():.5f}; worst grad rel {errs[0]}")
+    assert errs[0][0] < 1.2e-1 and errs[len(errs) // 2][0] < 4e-2

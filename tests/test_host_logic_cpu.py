@@ -89,6 +89,32 @@ def test_phased_backward_equals_single_backward(cfg):
     assert grads[0][hi:].abs().sum() > 0   # the visual encoder region exists and is written by phase 3
 
 
+@pytest.mark.parametrize("use_video,use_speech", [(True, False), (False, True)], ids=["no_speech", "no_video"])
+def test_engine_modality_variants_match_oracle(use_video, use_speech):
+    """--no_speech / --no_video train steps: engine (torch op table) vs the oracle, forward and backward."""
+    cfg = dict(TINY, num_features=10)
+    sd = init_state_dict(cfg, 0)
+    eng = Vid2SeqEngine(cfg, TorchOps(), "cpu", use_video=use_video, use_speech=use_speech)
+    for n, t in sd.items():
+        eng.p(n).copy_(t)
+    eng.sync_bf16()
+    video, inp, out = batch(cfg)
+    loss, ctx = eng.forward(video, inp, inp != 0, out, out != 0, want_logits=True)
+    eng.zero_grad()
+    eng.backward(ctx)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True,
+                          use_video=use_video, use_speech=use_speech)
+    o["loss"].backward()
+    assert abs(loss.item() - o["loss"].item()) < 1e-4 * abs(o["loss"].item())
+    assert rel(ctx["logits"].reshape(o["logits"].shape), o["logits"]) < 1e-3
+    for n in sd:
+        if sdg[n].grad is None:
+            assert float(eng.g(n).abs().sum()) == 0.0, n      # the unused tower receives no gradient
+        else:
+            assert rel(eng.g(n), sdg[n].grad) < 2e-2, n
+
+
 def test_beam_search_host_logic_matches_oracle():
     """engine.generate_beam (KV cache, cache reorder, n-best bookkeeping) driven by the torch op table vs the uncached
     oracle restatement of HF-4.28 beam search, on a half-trained and on a memorised tiny model; num_beams=1 == greedy."""

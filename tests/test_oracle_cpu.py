@@ -87,3 +87,34 @@ def test_oracle_matches_live_reference():
         done = (cur[:, 1:] == 1).cumsum(1) - (cur[:, 1:] == 1).long() > 0
         ref_ids = torch.cat([cur[:, :1], cur[:, 1:].masked_fill(done, 0)], 1)
         assert torch.equal(ids, ref_ids[:, :ids.shape[1]])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("use_video,use_speech", [(True, False), (False, True)], ids=["no_speech", "no_video"])
+def test_oracle_matches_live_reference_modality_variants(use_video, use_speech):
+    """--no_speech / --no_video (vid2seq.py:59-84): the decoder's memory is one modality only."""
+    from vidchapters_b200.config import TINY
+    cfg = dict(TINY, num_features=10)
+    m = ref_shim.build_reference_vid2seq(cfg, use_video=use_video, use_speech=use_speech)
+    sd = init_state_dict(cfg, 4)
+    full = dict(sd)
+    for k in ("t5_model.encoder.embed_tokens.weight", "t5_model.decoder.embed_tokens.weight", "t5_model.lm_head.weight"):
+        full[k] = sd["t5_model.shared.weight"]
+    m.load_state_dict(full, strict=False)        # the reference drops the unused tower (vid2seq.py:41-56)
+    g = torch.Generator().manual_seed(10)
+    B, T, L, S = 2, 10, 23, 11
+    video = torch.randn(B, T, 768, generator=g)
+    inp = torch.randint(2, 1100, (B, L), generator=g); inp[1, -5:] = 0
+    out = torch.randint(2, 1100, (B, S), generator=g); out[0, -3:] = 0
+    ld, vd = m(video, {"input_ids": inp, "attention_mask": inp != 0}, {"input_ids": out, "attention_mask": out != 0})
+    ld["loss"].backward()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, use_video=use_video, use_speech=use_speech)
+    o["loss"].backward()
+    assert abs(o["loss"].item() - ld["loss"].item()) < 1e-5
+    assert (vd is None) == (not use_video)
+    for n, p in m.named_parameters():
+        if p.grad is None:
+            assert sdg[n].grad is None or float(sdg[n].grad.abs().sum()) == 0.0, n
+        else:
+            assert rel(sdg[n].grad, p.grad) < 1e-2, n
