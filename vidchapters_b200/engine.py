@@ -695,6 +695,45 @@ class Vid2SeqEngine:
         return memory, torch.cat(parts, dim=1).contiguous(), B, E
 
     @torch.no_grad()
+    def _decode_buffers(self, Bn):
+        """Per-step activations of the incremental decoder for Bn sequences."""
+        bf, d, inner = torch.bfloat16, self.d, self.inner
+        Vp = (self.V + 7) // 8 * 8
+        return dict(x=self._e(Bn, d), h=self._e(Bn, d, dtype=bf), q=self._e(Bn, inner, dtype=bf),
+                    kvn=self._e(Bn, 2 * inner, dtype=bf), ctxb=self._e(Bn, inner, dtype=bf),
+                    act=self._e(Bn, self.dff, dtype=bf), logits=self._e(Bn, Vp)[:, :self.V])
+
+    def _decode_step_logits(self, ids, buf, caches, kvmem, mem_mask, bias_d, pos, Bn, S, E):
+        """One incremental decoder step for Bn sequences (modeling_t5.py:484-525,551-556 with past_key_values): embeds
+        `ids`, appends this position's K/V to `caches`, attends to positions <= *pos and to the encoder memory, and
+        leaves the next-token logits in buf["logits"].  A fixed launch sequence (the position is a device scalar)."""
+        ops, d, H, inner = self.ops, self.d, self.H, self.inner
+        x, h, q, kvn, ctxb, act, logits = (buf[k] for k in ("x", "h", "q", "kvn", "ctxb", "act", "logits"))
+        ops.embed_fwd(ids, self.p("t5_model.shared.weight"), x)
+        for li, (sa, ca, ff) in enumerate(self.dec_blocks):
+            ops.norm_fwd(0, x, self.pv(sa.norm_w), None, out_bf16=h, eps=1e-6)
+            ops.gemm(h, self.pb(sa.qkv_w), q)                                   # q rows of the fused [q;k;v]
+            k_name = sa.qkv_w.replace(".q.weight", ".k.weight")
+            ops.gemm(h, self.pb(k_name, 2 * inner), kvn)                         # adjacent k,v weights
+            ops.kv_append(kvn, caches[li], pos)
+            c2 = caches[li].view(Bn * S, 2 * inner)
+            ops.attn_fwd(q, c2, c2, q_col=0, k_col=0, v_col=inner, B=Bn, H=H, Lq=1, Lk=S, out=ctxb, lse2=None,
+                         bias_rel=bias_d, kmask=None, causal=True, scale=1.0, q_offset_dev=pos, kv_batch_rows=S,
+                         bias_zero=S - 1, bias_len=2 * S - 1)
+            ops.gemm(ctxb, self.pb(sa.o_w), x, residual=x)
+            ops.norm_fwd(0, x, self.pv(ca.norm_w), None, out_bf16=h, eps=1e-6)
+            ops.gemm(h, self.pb(ca.q_w), q)
+            ops.attn_fwd(q, kvmem[li], kvmem[li], q_col=0, k_col=0, v_col=inner, B=Bn, H=H, Lq=1, Lk=E, out=ctxb,
+                         lse2=None, bias_rel=None, kmask=mem_mask, causal=False, scale=1.0)
+            ops.gemm(ctxb, self.pb(ca.o_w), x, residual=x)
+            ops.norm_fwd(0, x, self.pv(ff.norm_w), None, out_bf16=h, eps=1e-6)
+            ops.gemm(h, self.pb(ff.w1), act, act=ACT_RELU)
+            ops.gemm(act, self.pb(ff.w2), x, residual=x)
+        ops.norm_fwd(0, x, self.pv("t5_model.decoder.final_layer_norm.weight"), None, out_bf16=h, eps=1e-6,
+                     out_scale=d ** -0.5)
+        ops.gemm(h, self.pb("t5_model.shared.weight"), logits)
+        return logits
+
     def generate_greedy(self, memory, mem_mask, B, E, max_new_tokens=256, use_graph=None, check_every=16):
         """Greedy decoding with a KV cache (HF-4.28 greedy semantics: start id 0, argmax, sequences that emitted eos=1
         continue with pad=0, stop when all are done or after max_new_tokens).  Returns int64 [B, 1 + n] ids including
@@ -719,39 +758,10 @@ class Vid2SeqEngine:
         ids = torch.zeros(B, dtype=torch.int64, device=dev)            # decoder_start_token_id = 0
         seq = torch.zeros(B, S + 1, dtype=torch.int64, device=dev)
         done = torch.zeros(B, dtype=torch.uint8, device=dev)
-        Vp = (self.V + 7) // 8 * 8
-        x = self._e(B, d)
-        h = self._e(B, d, dtype=bf)
-        q = self._e(B, inner, dtype=bf)
-        kvn = self._e(B, 2 * inner, dtype=bf)
-        ctxb = self._e(B, inner, dtype=bf)
-        act = self._e(B, self.dff, dtype=bf)
-        logits = self._e(B, Vp)[:, :self.V]
+        buf = self._decode_buffers(B)
 
         def step():
-            ops.embed_fwd(ids, self.p("t5_model.shared.weight"), x)
-            for li, (sa, ca, ff) in enumerate(self.dec_blocks):
-                ops.norm_fwd(0, x, self.pv(sa.norm_w), None, out_bf16=h, eps=1e-6)
-                ops.gemm(h, self.pb(sa.qkv_w), q)                                   # q rows of the fused [q;k;v]
-                k_name = sa.qkv_w.replace(".q.weight", ".k.weight")
-                ops.gemm(h, self.pb(k_name, 2 * inner), kvn)                         # adjacent k,v weights
-                ops.kv_append(kvn, caches[li], pos)
-                c2 = caches[li].view(B * S, 2 * inner)
-                ops.attn_fwd(q, c2, c2, q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=1, Lk=S, out=ctxb, lse2=None,
-                             bias_rel=bias_d, kmask=None, causal=True, scale=1.0, q_offset_dev=pos, kv_batch_rows=S,
-                             bias_zero=S - 1, bias_len=2 * S - 1)
-                ops.gemm(ctxb, self.pb(sa.o_w), x, residual=x)
-                ops.norm_fwd(0, x, self.pv(ca.norm_w), None, out_bf16=h, eps=1e-6)
-                ops.gemm(h, self.pb(ca.q_w), q)
-                ops.attn_fwd(q, kvmem[li], kvmem[li], q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=1, Lk=E, out=ctxb,
-                             lse2=None, bias_rel=None, kmask=mem_mask, causal=False, scale=1.0)
-                ops.gemm(ctxb, self.pb(ca.o_w), x, residual=x)
-                ops.norm_fwd(0, x, self.pv(ff.norm_w), None, out_bf16=h, eps=1e-6)
-                ops.gemm(h, self.pb(ff.w1), act, act=ACT_RELU)
-                ops.gemm(act, self.pb(ff.w2), x, residual=x)
-            ops.norm_fwd(0, x, self.pv("t5_model.decoder.final_layer_norm.weight"), None, out_bf16=h, eps=1e-6,
-                         out_scale=d ** -0.5)
-            ops.gemm(h, self.pb("t5_model.shared.weight"), logits)
+            logits = self._decode_step_logits(ids, buf, caches, kvmem, mem_mask, bias_d, pos, B, S, E)
             ops.greedy_next(logits, done, ids, seq, pos, 1, 0)
             ops.step_advance(pos)
 
@@ -817,40 +827,10 @@ class Vid2SeqEngine:
         top_s = torch.zeros(B, K2, dtype=torch.float32, device=dev)
         top_t = torch.zeros(B, K2, dtype=torch.int32, device=dev)
         top_b = torch.zeros(B, K2, dtype=torch.int32, device=dev)
-        Vp = (self.V + 7) // 8 * 8
-        x = self._e(Bn, d)
-        h = self._e(Bn, d, dtype=bf)
-        q = self._e(Bn, inner, dtype=bf)
-        kvn = self._e(Bn, 2 * inner, dtype=bf)
-        ctxb = self._e(Bn, inner, dtype=bf)
-        act = self._e(Bn, self.dff, dtype=bf)
-        logits = self._e(Bn, Vp)[:, :self.V]
+        buf = self._decode_buffers(Bn)
 
         def step(par):
-            cs = caches[par]
-            ops.embed_fwd(ids, self.p("t5_model.shared.weight"), x)
-            for li, (sa, ca, ff) in enumerate(self.dec_blocks):
-                ops.norm_fwd(0, x, self.pv(sa.norm_w), None, out_bf16=h, eps=1e-6)
-                ops.gemm(h, self.pb(sa.qkv_w), q)
-                k_name = sa.qkv_w.replace(".q.weight", ".k.weight")
-                ops.gemm(h, self.pb(k_name, 2 * inner), kvn)
-                ops.kv_append(kvn, cs[li], pos)
-                c2 = cs[li].view(Bn * S, 2 * inner)
-                ops.attn_fwd(q, c2, c2, q_col=0, k_col=0, v_col=inner, B=Bn, H=H, Lq=1, Lk=S, out=ctxb, lse2=None,
-                             bias_rel=bias_d, kmask=None, causal=True, scale=1.0, q_offset_dev=pos, kv_batch_rows=S,
-                             bias_zero=S - 1, bias_len=2 * S - 1)
-                ops.gemm(ctxb, self.pb(sa.o_w), x, residual=x)
-                ops.norm_fwd(0, x, self.pv(ca.norm_w), None, out_bf16=h, eps=1e-6)
-                ops.gemm(h, self.pb(ca.q_w), q)
-                ops.attn_fwd(q, kvmem[li], kvmem[li], q_col=0, k_col=0, v_col=inner, B=Bn, H=H, Lq=1, Lk=E, out=ctxb,
-                             lse2=None, bias_rel=None, kmask=mask_x, causal=False, scale=1.0)
-                ops.gemm(ctxb, self.pb(ca.o_w), x, residual=x)
-                ops.norm_fwd(0, x, self.pv(ff.norm_w), None, out_bf16=h, eps=1e-6)
-                ops.gemm(h, self.pb(ff.w1), act, act=ACT_RELU)
-                ops.gemm(act, self.pb(ff.w2), x, residual=x)
-            ops.norm_fwd(0, x, self.pv("t5_model.decoder.final_layer_norm.weight"), None, out_bf16=h, eps=1e-6,
-                         out_scale=d ** -0.5)
-            ops.gemm(h, self.pb("t5_model.shared.weight"), logits)
+            logits = self._decode_step_logits(ids, buf, caches[par], kvmem, mask_x, bias_d, pos, Bn, S, E)
             ops.beam_topk(logits, beam_scores, nb, top_s, top_t, top_b)
             ops.step_advance(pos)
 
