@@ -286,7 +286,10 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   }
 
   // CTA-pair kernel (256 x BN tiles) whenever the problem still fills the machine with pairs
-  if (pair_mode() && a->tile_n >= 0 && a->M >= 256) {
+  // VIDCHAP_GEMM_PAIR_MIN_M: smallest M that takes the CTA-pair kernel (A/B switch; smaller problems are launch /
+  // prologue bound and the pair's cluster launch and two cluster barriers are pure overhead there)
+  static const int pair_min_m = [] { const char* e = getenv("VIDCHAP_GEMM_PAIR_MIN_M"); return e ? atoi(e) : 256; }();
+  if (pair_mode() && a->tile_n >= 0 && a->M >= pair_min_m) {
     const int mb2 = (a->M + 255) / 256;
     int BN2 = 0;
     for (int cand = 256; cand >= 128; cand >>= 1) {
