@@ -66,3 +66,31 @@ def write_dataset(root, n_videos=12, seed=0, features_dim=768):
     with open(os.path.join(root, "subs.pkl"), "wb") as f:
         pickle.dump(subs, f)
     return os.path.join(root, "ann.json"), os.path.join(root, "feats"), os.path.join(root, "subs.pkl")
+
+
+def write_yt_dataset(root, n_videos=10, seed=1, features_dim=768):
+    """Pretraining-set layout of dataset/yt_dataset.py: root/{list.csv, feats/<path>.npy, subs/<id>.pkl}; covers subtitles
+    with and without a stored duration, out-of-range subtitles, a video whose subtitles are all dropped, long transcripts."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    os.makedirs(os.path.join(root, "feats"), exist_ok=True)
+    os.makedirs(os.path.join(root, "subs"), exist_ok=True)
+    rows = []
+    for v in range(n_videos):
+        vid = f"ytv{v:08d}"
+        n_frames = [100, 60, 333, 7][v % 4] if v < 4 else int(rng.integers(5, 400))
+        np.save(os.path.join(root, "feats", vid + ".npy"), rng.standard_normal((n_frames, features_dim)).astype(np.float32))
+        n_sub = 260 if v == 1 else int(rng.integers(1, 50))
+        horizon = float(n_frames + 1)
+        st = np.sort(rng.uniform(-3 if v == 2 else 0, horizon, size=n_sub))
+        ed = st + rng.uniform(0.5, 6, size=n_sub)
+        if v == 3:
+            st, ed = st + 10 * horizon, ed + 10 * horizon       # nothing survives the duration filter
+        sub = {"start": [float(x) for x in st], "end": [float(x) for x in ed], "text": [_sentence(rng, 1, 12) for _ in range(n_sub)]}
+        if v % 3 == 0:
+            sub["duration"] = float(n_frames) * 1.5
+        with open(os.path.join(root, "subs", vid + ".pkl"), "wb") as f:
+            pickle.dump(sub, f)
+        rows.append({"video_id": vid, "video_path": vid + ".npy"})
+    pd.DataFrame(rows).to_csv(os.path.join(root, "list.csv"), index=False)
+    return os.path.join(root, "list.csv"), os.path.join(root, "feats"), os.path.join(root, "subs")

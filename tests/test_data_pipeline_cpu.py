@@ -103,3 +103,41 @@ def test_fixed_shape_and_pinned_batches():
     assert torch.equal(x["video"], y["video"]) and all(torch.equal(x[k], y[k]) for k in TOKEN_KEYS)
     z = pb.fill(samples[:4])                                   # buffers are reused: stale rows must be cleared
     assert all(torch.equal(z[k], b[k]) for k in TOKEN_KEYS)
+
+
+def test_yt_pretraining_pipeline_matches_reference_golden_and_live():
+    """dataset/yt_dataset.py (pretraining): golden minted from the reference, plus the live reference where present."""
+    from data_fixture import write_yt_dataset
+    fx = torch.load(os.path.join(os.path.dirname(GOLD), "yt_pipeline.pt"), weights_only=False)
+    keys = ("output_tokens", "denoising_input_tokens", "denoising_output_tokens")
+
+    def mine(seed, bs):
+        with tempfile.TemporaryDirectory() as d:
+            csv, feats, subs = write_yt_dataset(d)
+            ds = D.YTDataset(csv, feats, subs, tokenizer=HFStubTokenizer())
+            np.random.seed(seed)
+            samples = [ds[i] for i in range(len(ds))]
+        return samples, [D.collate_dvc(samples[i:i + bs]) for i in range(0, len(samples), bs)]
+
+    samples, batches = mine(fx["seed"], fx["batch_size"])
+    assert len(samples) == len(fx["samples"]) == 10
+    for s, r in zip(samples, fx["samples"]):
+        assert s["video_id"] == r["video_id"] and s["duration"] == r["duration"] and "input_tokens" not in s
+        assert s["video"].double().sum().item() == r["video_sum"]
+        for k in keys:
+            assert torch.equal(s[k], r[k]), (s["video_id"], k)
+    for b, r in zip(batches, fx["batches"]):
+        assert tuple(b["video"].shape) == r["video_shape"] and set(b) == set(r) - {"video_shape"} | {"video"}
+        for k in keys:
+            assert torch.equal(b[k], r[k]), k
+    assert max(len(s["output_tokens"]) for s in samples) == 1000 and min(len(s["output_tokens"]) for s in samples) == 1
+    if os.path.isdir("/root/reference/dataset"):
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle"))
+        import make_golden_data as G
+        with tempfile.TemporaryDirectory() as d:
+            ref_s, ref_b = G.reference_yt_outputs(d, seed=11, batch_size=3)
+        my_s, my_b = mine(11, 3)
+        for s, r in zip(my_s, ref_s):
+            assert torch.equal(s["video"], r["video"]) and all(torch.equal(s[k], r[k]) for k in keys)
+        for b, r in zip(my_b, ref_b):
+            assert torch.equal(b["video"], r["video"]) and all(torch.equal(b[k], r[k]) for k in keys)

@@ -6,6 +6,7 @@ Replaces, with the same inputs, outputs and random-number consumption:
   dataset/dvc_dataset.py:86-89    time_tokenize       -> time_tokenize
   dataset/dvc_dataset.py:91-165   __getitem__         -> DenseVideoCaptioningDataset.__getitem__
   dataset/dvc_dataset.py:168-208  collate             -> collate_dvc / PinnedBatcher
+  dataset/yt_dataset.py:10-165    pretraining dataset -> YTDataset (+ collate_dvc, which also covers yt_collate_fn)
   util/t5.py:3-94                 span corruption     -> random_spans_noise_mask / span_corrupt
 Integer work throughout: parity with the reference is bit-exact (tests/test_data_pipeline_cpu.py, golden minted from
 the reference by oracle/make_golden_data.py).  The tokenizer (sentencepiece T5Tokenizer, third-party) stays an injected
@@ -186,6 +187,46 @@ class DenseVideoCaptioningDataset(torch.utils.data.Dataset):
                 "denoising_input_tokens": f(den_in), "denoising_output_tokens": f(den_out)}
 
 
+class YTDataset(torch.utils.data.Dataset):
+    """Drop-in for dataset/yt_dataset.py::YT_Dataset, the pretraining set (HowTo100M / VidChapters ASR): the "output" of
+    the generative pass is the timed transcript itself, plus its span-corrupted pair (yt_dataset.py:84-131)."""
+
+    def __init__(self, csv_path, features_path, subtitles_path, max_feats=100, features_dim=768, tokenizer=None, num_bins=100,
+                 max_input_tokens=1000, max_output_tokens=1000, noise_density=0.25, mean_noise_span_length=5):
+        import pandas as pd
+        self.data = pd.read_csv(csv_path)
+        self.features_path, self.subtitles_path = features_path, subtitles_path
+        self.max_feats, self.features_dim, self.tokenizer = max_feats, features_dim, tokenizer
+        self.num_bins = num_bins
+        self.max_input_tokens, self.max_output_tokens = max_input_tokens, max_output_tokens
+        self.num_text_tokens = len(tokenizer) - num_bins
+        self.noise_density, self.mean_noise_span_length = noise_density, mean_noise_span_length
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        video_id = self.data["video_id"][idx]
+        with open(os.path.join(self.subtitles_path, video_id + ".pkl"), "rb") as f:
+            sub = pickle.load(f)
+        raw = np.load(os.path.join(self.features_path, self.data["video_path"][idx]))
+        duration = sub["duration"] if "duration" in sub else len(raw) + 1          # yt_dataset.py:53-55
+        keep = [i for i, (x, y) in enumerate(zip(sub["start"], sub["end"])) if x >= 0 and y <= duration]
+        video = subsample_pad_features(raw, self.max_feats, self.features_dim)
+        tok, eos = self.tokenizer, self.tokenizer.eos_token_id
+        if keep:
+            seq = timed_token_sequence([max(sub["start"][i], 0) for i in keep], [min(sub["end"][i], duration) for i in keep],
+                                       [_clean_text(sub["text"][i]) for i in keep], duration, tok, self.num_bins,
+                                       self.num_text_tokens, self.max_input_tokens)
+            den_in, den_out = span_corrupt(seq, len(tok), self.num_bins, eos, self.noise_density, self.mean_noise_span_length)
+        else:
+            seq = np.array([eos], dtype=np.int64)
+            den_in, den_out = np.array([0], dtype=np.int64), seq
+        f = torch.from_numpy
+        return {"video_id": video_id, "duration": duration, "video": video, "output_tokens": f(seq),
+                "denoising_input_tokens": f(den_in), "denoising_output_tokens": f(den_out)}
+
+
 _TOKEN_KEYS = ("input_tokens", "output_tokens", "denoising_input_tokens", "denoising_output_tokens")
 
 
@@ -198,6 +239,8 @@ def collate_dvc(batch: List[dict], pad_to: Optional[Dict[str, int]] = None, pin_
     video = torch.stack([b["video"] for b in batch])
     out["video"] = video.pin_memory() if pin_memory else video
     for key in _TOKEN_KEYS:
+        if key not in batch[0]:
+            continue                 # yt_collate_fn (yt_dataset.py:134-165): the pretraining samples carry no "input_tokens"
         rows = [b[key] for b in batch]
         width = max(len(r) for r in rows)
         if pad_to and key in pad_to:
