@@ -63,6 +63,26 @@ def _worker(rank, world, port, outdir):
     ld["loss"].backward()
     opt.step()
     torch.save({n: p.detach().clone() for n, p in m._params.items()}, os.path.join(outdir, f"rank{rank}.pt"))
+    # the graphed step's schedule without the graphs: three backward phases, each finished region of the flat gradient
+    # buffer all-reduced asynchronously while the next phase runs (vidchapters_b200/graphed.py)
+    m2 = _make(_cfg())
+    opt2 = Vid2SeqAdam(m2, lr=3e-4, clip_max_norm=0.1)
+    eng = m2.engine
+    m2._refresh_shadow()          # bf16 shadow of the freshly initialised fp32 parameters (the module's forward does this)
+    loss, ectx = eng.forward(v, it["input_ids"], it["attention_mask"], ot["input_ids"], ot["attention_mask"], training=True)
+    eng.zero_grad()
+    lo, hi = eng.decoder_grad_range()
+    eng.backward(ectx, phase=1)
+    w1 = torch.distributed.all_reduce(eng.flat_g[lo:hi], async_op=True)
+    eng.backward(ectx, phase=2)
+    w2 = torch.distributed.all_reduce(eng.flat_g[:lo], async_op=True)
+    eng.backward(ectx, phase=3)
+    w3 = torch.distributed.all_reduce(eng.flat_g[hi:], async_op=True)
+    for w in (w1, w2, w3):
+        w.wait()
+    m2._end_backward()
+    opt2.step(grads_already_reduced=True)
+    torch.save({n: p.detach().clone() for n, p in m2._params.items()}, os.path.join(outdir, f"rank{rank}_phased.pt"))
     torch.distributed.destroy_process_group()
 
 
@@ -71,8 +91,12 @@ def test_two_rank_step_equals_averaged_gradient_step(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0 = torch.load(tmp_path / "rank0.pt")
     r1 = torch.load(tmp_path / "rank1.pt")
+    p0 = torch.load(tmp_path / "rank0_phased.pt")
+    p1 = torch.load(tmp_path / "rank1_phased.pt")
     for n in r0:
         assert torch.equal(r0[n], r1[n]), n      # replicas stay identical after the all-reduced step
+        assert torch.equal(p0[n], p1[n]), n
+        assert torch.equal(p0[n], r0[n]), n      # region-wise overlapped all-reduce == one flat all-reduce, bit for bit
     # single process: average of the two shard gradients, then the same tail
     from vidchapters_b200 import Vid2SeqAdam
     torch.set_num_threads(2)  # same thread count as the workers: identical CPU matmul blocking, hence identical
