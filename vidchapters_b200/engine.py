@@ -117,6 +117,12 @@ class Vid2SeqEngine:
         self.drop_rates = dict(vis=0.0, enc=0.0, dec=0.0)   # vis_drop / enc_drop / dec_drop of the reference ctor
         self.drop_seed = 0x5EED                             # user seed; every forward call derives its own stream
         self._drop_calls = 0
+        # VIDCHAP_DUAL_STREAM=1 (experimental, default off): the visual encoder (small 1600-row kernels that cannot fill the
+        # GPU) runs on a second stream next to the text encoder, forward and backward; joined before the decoder / at the
+        # end of the backward.  Works inside CUDA-graph capture (fork/join become graph dependencies).
+        import os
+        self.dual_stream = os.environ.get("VIDCHAP_DUAL_STREAM") == "1" and self.device.type == "cuda"
+        self._side_stream = None
         self._build_specs()
 
     # ------------------------------------------------------------------ parameter views
@@ -203,6 +209,17 @@ class Vid2SeqEngine:
             return NO_DROP
         self._drop_site += 1
         return drop_spec(self.drop_rates[which], (self._drop_base + self._drop_site * 0x632BE5AB) & 0xFFFFFFFF)
+
+    # ------------------------------------------------------------------ second stream (VIDCHAP_DUAL_STREAM)
+    def _fork(self):
+        """Returns (main, side) with `side` ordered after everything enqueued on the current stream, or (None, None)."""
+        if not self.dual_stream:
+            return None, None
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        self._side_stream.wait_stream(main)
+        return main, self._side_stream
 
     # ------------------------------------------------------------------ allocation helpers
     def _e(self, *shape, dtype=torch.float32):
@@ -418,6 +435,9 @@ class Vid2SeqEngine:
         ctx.update(B=B, T=T, L=L, S=S, E=E, video_cached=video_cached)
         memory = self._e(B * E, d, dtype=bf)
         vid_f32 = None
+        main_s, side_s = self._fork() if (self.use_video and self.use_speech and not video_cached) else (None, None)
+        if side_s is not None:
+            torch.cuda.set_stream(side_s)
         # ---------------- visual encoder (vit.py:117-133)
         if self.use_video:
             if video_cached:
@@ -456,6 +476,8 @@ class Vid2SeqEngine:
                     ops.copy_rows_bf16(tmp, memory, B, T, d, E, 0)
                 ctx.update(vit_x=xv, vit_rstd=rstd, vit_mean=mean, vit_vn=vn)
         ctx["n_vit_tape"] = len(tape)
+        if side_s is not None:
+            torch.cuda.set_stream(main_s)      # the text encoder is enqueued on the main stream, concurrently
         # ---------------- text encoder (modeling_t5.py:930-1138)
         if self.use_speech:
             ids = input_ids.contiguous()
@@ -475,6 +497,8 @@ class Vid2SeqEngine:
                          eps=1e-6, rows_per_batch=L, out_batch_stride=E, out_row_offset=T, drop=d_fin_e)
             ctx.update(enc_x=x, enc_rstd=rstd_e, enc_ids=ids, lut_e=lut_e, d_emb_e=d_emb_e, d_fin_e=d_fin_e)
         ctx["n_enc_tape"] = len(tape)
+        if side_s is not None:
+            main_s.wait_stream(side_s)         # join: the decoder's cross-attention reads both halves of `memory`
         parts = []
         if self.use_video:
             parts.append(torch.ones(B, T, dtype=torch.uint8, device=self.device))
@@ -591,6 +615,14 @@ class Vid2SeqEngine:
             return tape[j]["d_out"] if j >= 0 else NO_DROP
         if grad_video is not None and self.use_video and part in (None, 2):
             dmem.view(B, E, d)[:, :T].add_(grad_video.reshape(B, T, d).to(dmem.dtype))
+        main_s, side_s = (None, None)
+        if part is None and self.use_video and self.use_speech and not ctx["video_cached"]:
+            main_s, side_s = self._fork()      # forked HERE: the side stream must not wait for the text-encoder backward
+            if side_s is not None:             # the two chains run concurrently: the visual one gets its own scratch
+                Mv, Cv = B * T, self.C
+                ws_v = dict(dact=self._e(Mv * self.mlp, dtype=bf), dh=self._e(Mv * max(d, Cv)),
+                            dhb=self._e(Mv * max(d, Cv), dtype=bf), dctx=self._e(Mv * Cv, dtype=bf),
+                            dqkv=self._e(Mv * 3 * Cv, dtype=bf), dq_acc=self._e(Mv * Cv), delta=self._e(B * self.Hv * T))
         # ---- text encoder
         if self.use_speech and do_enc:
             dx = self._e(B * L, d)
@@ -613,6 +645,9 @@ class Vid2SeqEngine:
             return None
         # ---- visual encoder
         dvideo_out = None
+        if side_s is not None:
+            torch.cuda.set_stream(side_s)
+            ws = ws_v
         if self.use_video:
             if ctx["video_cached"]:
                 dvideo_out = dmem.view(B, E, d)[:, :T].contiguous()
@@ -643,6 +678,9 @@ class Vid2SeqEngine:
                     i -= 2
                 ops.add_pos_bwd(dxv, self.g("visual_encoder.pos_embed"), B, T, C, self.cfg["num_features"],
                                 drop=ctx["d_pos"])
+        if side_s is not None:
+            torch.cuda.set_stream(main_s)
+            main_s.wait_stream(side_s)
         assert i == 0, i
         return dvideo_out
 
