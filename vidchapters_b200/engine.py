@@ -117,11 +117,11 @@ class Vid2SeqEngine:
         self.drop_rates = dict(vis=0.0, enc=0.0, dec=0.0)   # vis_drop / enc_drop / dec_drop of the reference ctor
         self.drop_seed = 0x5EED                             # user seed; every forward call derives its own stream
         self._drop_calls = 0
-        # VIDCHAP_DUAL_STREAM=1 (experimental, default off): the visual encoder (small 1600-row kernels that cannot fill the
-        # GPU) runs on a second stream next to the text encoder, forward and backward; joined before the decoder / at the
-        # end of the backward.  Works inside CUDA-graph capture (fork/join become graph dependencies).
+        # The visual encoder (small 1600-row kernels that cannot fill the GPU) runs on a second stream next to the text
+        # encoder, forward and backward; joined before the decoder / at the end of the backward.  Inside CUDA-graph capture
+        # the fork/join become graph dependencies.  -3.7 % step time (profiles/README.md); VIDCHAP_DUAL_STREAM=0 disables.
         import os
-        self.dual_stream = os.environ.get("VIDCHAP_DUAL_STREAM") == "1" and self.device.type == "cuda"
+        self.dual_stream = os.environ.get("VIDCHAP_DUAL_STREAM", "1") != "0" and self.device.type == "cuda"
         self._side_stream = None
         self._build_specs()
 
