@@ -24,6 +24,11 @@ class Tok:
         return self.n
 
 
+# t5-large's per-layer shapes (BASELINE configs[3]) at 1+1 layers and a small vocabulary
+T5_LARGE_SHALLOW = dict(name="t5-large-shallow", d_model=1024, d_kv=64, d_ff=4096, num_layers=1, num_heads=16, base_vocab=600,
+                        num_bins=100, num_features=10, embed_dim=768, depth=1, heads=12, mlp_dim=2048)
+
+
 def batch(cfg, B=2, T=10, L=24, S=12, seed=1):
     g = torch.Generator().manual_seed(seed)
     V = cfg["base_vocab"] + cfg["num_bins"]
@@ -60,6 +65,35 @@ def test_engine_matches_oracle(cfg):
         assert rel(eng.g(n), sdg[n].grad) < 2e-2, n
     o32 = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=False)
     assert rel(ctx["logits"].reshape(o32["logits"].shape), o32["logits"]) < 1.2e-2   # tier B: below the reference's own bf16 error
+
+
+def test_engine_t5_large_shapes_and_ragged_lengths():
+    """Per-layer shapes of BASELINE configs[3] (t5-large: d_model 1024, 16 heads, d_ff 4096; proj_v2t 768 -> 1024) at
+    reduced depth, with the odd, `padding="longest"`-style lengths vc.py produces (vc.py:26-86): T not equal to
+    num_features (interpolated time embedding), lengths that are no multiple of any tile size, fully padded tails."""
+    cfg = dict(T5_LARGE_SHALLOW)
+    sd = init_state_dict(cfg, 0)
+    eng = Vid2SeqEngine(cfg, TorchOps(), "cpu")
+    for n, t in sd.items():
+        eng.p(n).copy_(t)
+    eng.sync_bf16()
+    g = torch.Generator().manual_seed(2)
+    B, T, L, S = 3, 7, 37, 13
+    V = cfg["base_vocab"] + cfg["num_bins"]
+    video = torch.randn(B, T, 768, generator=g)
+    inp = torch.randint(2, V, (B, L), generator=g); inp[0, 20:] = 0; inp[2, 1:] = 0
+    out = torch.randint(2, V, (B, S), generator=g); out[1, 5:] = 0
+    loss, ctx = eng.forward(video, inp, inp != 0, out, out != 0, want_logits=True)
+    eng.zero_grad()
+    eng.backward(ctx)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True)
+    o["loss"].backward()
+    assert abs(loss.item() - o["loss"].item()) < 1e-4 * abs(o["loss"].item())
+    assert rel(ctx["logits"].reshape(o["logits"].shape), o["logits"]) < 1e-3
+    for n in sd:
+        assert rel(eng.g(n), sdg[n].grad) < 2e-2, n
+    assert "proj_v2t.weight" in sd and sd["t5_model.encoder.block.0.layer.0.SelfAttention.q.weight"].shape == (1024, 1024)
 
 
 @pytest.mark.parametrize("cfg", [dict(TINY, num_features=10), dict(TINY_PROJ)], ids=["tiny", "tiny-proj"])
