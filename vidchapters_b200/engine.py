@@ -123,6 +123,13 @@ class Vid2SeqEngine:
         import os
         self.dual_stream = os.environ.get("VIDCHAP_DUAL_STREAM", "1") != "0" and self.device.type == "cuda"
         self._side_stream = None
+        # VIDCHAP_WGRAD_STREAM=1 (experimental, default off, not yet measured): weight-gradient GEMMs are off the critical
+        # path of the backward (nothing reads dW before the optimiser), so they are enqueued on their own stream; events
+        # order them after the producer of dY and before the next writer of the scratch buffer that holds dY.
+        self.wgrad_stream = os.environ.get("VIDCHAP_WGRAD_STREAM") == "1" and self.device.type == "cuda"
+        self._wg_stream = None
+        self._wg_main = None
+        self._wg_pending: Dict[str, "torch.cuda.Event"] = {}
         self._build_specs()
 
     # ------------------------------------------------------------------ parameter views
@@ -332,11 +339,41 @@ class Vid2SeqEngine:
         return x2
 
     # ------------------------------------------------------------------ sub-layers: backward
-    def _wgrad(self, dy, x, gname, rows=None):
-        """g[N,K] += dy[M,N]^T @ x[M,K]  (reduction over the token dimension, split-K with fp32 atomics)."""
+    def _wgrad(self, dy, x, gname, rows=None, tag=None):
+        """g[N,K] += dy[M,N]^T @ x[M,K]  (reduction over the token dimension, split-K with fp32 atomics).
+        tag names the scratch buffer dy lives in; with VIDCHAP_WGRAD_STREAM the GEMM then runs on the weight-gradient
+        stream and `_wg_wait(tag)` must precede the next write to that buffer."""
         out = self.g2(gname, rows)
-        self.ops.gemm(dy, x, out, a_mn=True, b_mn=True, atomic=True,
-                      splits=self._splits(out.shape[0], out.shape[1], dy.shape[0]))
+        splits = self._splits(out.shape[0], out.shape[1], dy.shape[0])
+        if self.wgrad_stream and tag is not None and self._wg_main is not None \
+                and torch.cuda.current_stream(self.device) == self._wg_main:
+            if self._wg_stream is None:
+                self._wg_stream = torch.cuda.Stream(device=self.device)
+            produced = torch.cuda.Event()
+            produced.record(self._wg_main)
+            self._wg_stream.wait_event(produced)
+            prev = self._wg_pending.get(tag)
+            with torch.cuda.stream(self._wg_stream):
+                self.ops.gemm(dy, x, out, a_mn=True, b_mn=True, atomic=True, splits=splits)
+                done = torch.cuda.Event()
+                done.record(self._wg_stream)
+            self._wg_pending[tag] = done        # (the stream is in order: a later event also covers `prev`)
+            del prev
+            return
+        self.ops.gemm(dy, x, out, a_mn=True, b_mn=True, atomic=True, splits=splits)
+
+    def _wg_wait(self, *tags):
+        """The current stream waits until the weight-gradient GEMMs reading the named scratch buffers are done."""
+        for tag in tags:
+            ev = self._wg_pending.pop(tag, None)
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def _wg_join(self):
+        if self._wg_stream is not None and self._wg_main is not None:
+            self._wg_main.wait_stream(self._wg_stream)
+        self._wg_pending.clear()
+        self._wg_main = None
 
     def _ff_bwd(self, r, dx, dxb, ws, next_drop=NO_DROP):
         """dxb arrives already masked by this sub-layer's output dropout (r["d_out"]); the norm backward at the end
@@ -346,17 +383,19 @@ class Vid2SeqEngine:
         dff = r["act"].shape[1]
         if sp.b2:
             ops.colsum_bf16(dxb, self.gv(sp.b2))
-        self._wgrad(dxb, r["act"], sp.w2)
+        self._wgrad(dxb, r["act"], sp.w2, tag="dxb")
         dact = ws["dact"][:M * dff].view(M, dff)
+        self._wg_wait("dact")
         if sp.act == ACT_GELU:
             ops.gemm(dxb, self.pb(sp.w2), dact, b_mn=True, act=ACT_GELU_BWD, aux=r["pre"], drop=r["d_act"])
         else:
             ops.gemm(dxb, self.pb(sp.w2), dact, b_mn=True, act=ACT_RELU_BWD, aux=r["act"], drop=r["d_act"])
         if sp.b1:
             ops.colsum_bf16(dact, self.gv(sp.b1))
-        self._wgrad(dact, r["h"], sp.w1)
+        self._wgrad(dact, r["h"], sp.w1, tag="dact")
         dh = ws["dhb"][:M * D].view(M, D)
         ops.gemm(dact, self.pb(sp.w1), dh, b_mn=True)
+        self._wg_wait("dxb")
         ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
                      accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b), dxb_drop=next_drop)
 
@@ -367,13 +406,14 @@ class Vid2SeqEngine:
         inner = H * 64
         if sp.o_b:
             ops.colsum_bf16(dxb, self.gv(sp.o_b))
-        self._wgrad(dxb, r["ctx"], sp.o_w)
+        self._wgrad(dxb, r["ctx"], sp.o_w, tag="dxb")
         dctx = ws["dctx"][:M * inner].view(M, inner)
         ops.gemm(dxb, self.pb(sp.o_w), dctx, b_mn=True)
         dqkv = ws["dqkv"][:M * 3 * inner].view(M, 3 * inner)
         dq_acc = ws["dq_acc"][:M * inner].view(M, inner)   # cleared inside attn_bwd
         delta = ws["delta"][:B * H * L].view(B, H, L)
         qkv = r["qkv"]
+        self._wg_wait("dqkv")
         ops.attn_bwd(qkv, qkv, qkv, q_col=0, k_col=inner, v_col=2 * inner, B=B, H=H, Lq=L, Lk=L, out=r["ctx"],
                      lse2=r["lse"], bias_rel=r["bias_rel"], kmask=r["kmask"], causal=r["causal"], scale=sp.scale,
                      dout=dctx, do_col=0, delta=delta, dq_acc=dq_acc, dk=dqkv, dk_col=inner, dv=dqkv, dv_col=2 * inner,
@@ -381,9 +421,10 @@ class Vid2SeqEngine:
         ops.cast_f32_bf16(dq_acc, dqkv[:, :inner])
         if sp.qkv_b:
             ops.colsum_bf16(dqkv, self.gv(sp.qkv_b))
-        self._wgrad(dqkv, r["h"], sp.qkv_w, rows=3 * inner)
+        self._wgrad(dqkv, r["h"], sp.qkv_w, rows=3 * inner, tag="dqkv")
         dh = ws["dhb"][:M * D].view(M, D)
         ops.gemm(dqkv, self.pb(sp.qkv_w, 3 * inner), dh, b_mn=True)
+        self._wg_wait("dxb")
         ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
                      accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b), dxb_drop=next_drop)
 
@@ -392,24 +433,26 @@ class Vid2SeqEngine:
         M, D = dx.shape
         B, S, E, H = r["B"], r["S"], r["E"], sp.H
         inner = H * 64
-        self._wgrad(dxb, r["ctx"], sp.o_w)
+        self._wgrad(dxb, r["ctx"], sp.o_w, tag="dxb")
         dctx = ws["dctx"][:M * inner].view(M, inner)
         ops.gemm(dxb, self.pb(sp.o_w), dctx, b_mn=True)
         dq_acc = ws["dq_acc"][:M * inner].view(M, inner)   # cleared inside attn_bwd
         dq = ws["dqkv"][:M * inner].view(M, inner)
         dkv = ws["dkv"][:B * E * 2 * inner].view(B * E, 2 * inner)
         delta = ws["delta"][:B * H * S].view(B, H, S)
+        self._wg_wait("dqkv", "dkv")
         ops.attn_bwd(r["qc"], r["kv"], r["kv"], q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=S, Lk=E, out=r["ctx"],
                      lse2=r["lse"], bias_rel=None, kmask=r["mem_mask"], causal=False, scale=1.0, dout=dctx, do_col=0,
                      delta=delta, dq_acc=dq_acc, dk=dkv, dk_col=0, dv=dkv, dv_col=inner, dbias_rel=None, bucket_lut=None,
                      drop=r["d_attn"])
         ops.cast_f32_bf16(dq_acc, dq)
-        self._wgrad(dq, r["h"], sp.q_w)
+        self._wgrad(dq, r["h"], sp.q_w, tag="dqkv")
         dh = ws["dhb"][:M * D].view(M, D)
         ops.gemm(dq, self.pb(sp.q_w), dh, b_mn=True)
+        self._wg_wait("dxb")
         ops.norm_bwd(0, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], None, dx=dx, dx_bf16=dxb, accumulate_dx=True,
                      dw=self.gv(sp.norm_w), dxb_drop=next_drop)
-        self._wgrad(dkv, memory, sp.kv_w, rows=2 * inner)
+        self._wgrad(dkv, memory, sp.kv_w, rows=2 * inner, tag="dkv")
         ops.gemm(dkv, self.pb(sp.kv_w, 2 * inner), dmem, b_mn=True, residual=dmem)  # dmem += dkv @ Wkv
 
     # ------------------------------------------------------------------ forward
@@ -558,6 +601,8 @@ class Vid2SeqEngine:
         the encoder are final), phase=3 the visual encoder."""
         if phase in (2, 3):
             return self._backward_phase2(ctx, grad_video, part=phase)
+        if self.wgrad_stream:
+            self._wg_main = torch.cuda.current_stream(self.device)
         ops, d = self.ops, self.d
         bf = torch.bfloat16
         tape = ctx["tape"]
@@ -599,6 +644,7 @@ class Vid2SeqEngine:
         ops.embed_bwd(ctx["dec_in"].view(-1), dy, self.g("t5_model.shared.weight"), drop=ctx["d_emb_d"])
         ctx["_bwd_state"] = (dmem, i, ws)
         if phase == 1:
+            self._wg_join()
             return None
         return self._backward_phase2(ctx, grad_video)
 
@@ -610,6 +656,8 @@ class Vid2SeqEngine:
         B, T, L, S, E = ctx["B"], ctx["T"], ctx["L"], ctx["S"], ctx["E"]
         dmem, i, ws = ctx["_bwd_state"] if part == 2 else ctx.pop("_bwd_state")
         do_enc = part in (None, 2)
+        if self.wgrad_stream and self._wg_main is None:
+            self._wg_main = torch.cuda.current_stream(self.device)
 
         def out_drop(j):
             return tape[j]["d_out"] if j >= 0 else NO_DROP
@@ -642,6 +690,7 @@ class Vid2SeqEngine:
             ops.embed_bwd(ctx["enc_ids"].view(-1), dx, self.g("t5_model.shared.weight"), drop=ctx["d_emb_e"])
         if part == 2:   # the saved tape index already points past the text-encoder entries
             ctx["_bwd_state"] = (dmem, i, ws)
+            self._wg_join()
             return None
         # ---- visual encoder
         dvideo_out = None
@@ -681,6 +730,7 @@ class Vid2SeqEngine:
         if side_s is not None:
             torch.cuda.set_stream(main_s)
             main_s.wait_stream(side_s)
+        self._wg_join()
         assert i == 0, i
         return dvideo_out
 
