@@ -4,7 +4,9 @@ A dvc.py step at fixed (B, T, L, S) is ~1000 kernel launches; issued one by one 
 B200 busy (measured: 75 ms/step of which the GPU works ~45 ms).  `GraphedTrainStep` captures forward + backward
 (zeroing of the flat gradient buffer included) once into a `torch.cuda.CUDAGraph` and replays it per step; the
 optimiser tail (gradient all-reduce for N>1, clip + Adam + renorm: 5 launches) stays eager so NCCL is never captured
-and the learning rate / Adam step count remain plain host values.
+and the learning rate / Adam step count remain plain host values.  The engine's second stream (visual encoder next to
+the text encoder) is forked and joined inside the capture, i.e. becomes parallel branches of the graph.  For N>1 the
+backward is captured as three graphs and the all-reduce of each finished gradient region overlaps the next one.
 
 The semantics are exactly `loss_dict, _ = model(...); optimizer.zero_grad(); loss.backward(); optimizer.step()`
 (dvc.py:70-116) on the batch copied into the static input buffers.
@@ -45,8 +47,8 @@ class GraphedTrainStep:
         self.world = getattr(optimizer, "world_size", 1)
         self.graph2 = None
         if self.world > 1:
-            # data parallel: two graphs, so the decoder's gradients (final after phase 1) are all-reduced by NCCL while
-            # the encoder / visual-encoder backward (phase 2) still runs
+            # data parallel: three graphs (forward + head/decoder backward | text-encoder backward | visual-encoder
+            # backward), so that NCCL all-reduces each finished region of the gradient buffer while the next phase runs
             with torch.cuda.graph(self.graph):
                 self.loss = self._fwd_bwd(phase=1)
             self.graph2 = torch.cuda.CUDAGraph()
@@ -78,7 +80,7 @@ class GraphedTrainStep:
         eng.zero_grad()
         eng.backward(ectx, phase=phase)
         if phase == 1:
-            self._ectx = ectx      # phase 2 is captured into the second graph
+            self._ectx = ectx      # phases 2 and 3 are captured into their own graphs
         else:
             m._end_backward()      # host-side: make every Parameter's .grad a view of the flat gradient buffer
         return loss.view(())
