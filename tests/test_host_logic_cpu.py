@@ -343,3 +343,32 @@ def test_greedy_generate_matches_oracle():
     assert rel(memory.float().view(B, E, -1), O._r(o["memory"])) < 2e-3
     ref = O.greedy_decode(sd, cfg, O._r(o["memory"]), mem_mask.long(), max_new_tokens=6, emulate_bf16=True)
     assert torch.equal(seq[:, :ref.shape[1]], ref), (seq, ref)
+
+
+def test_fused_cross_kv_matches_oracle_and_default_path():
+    """engine.fuse_cross_kv (one K/V projection GEMM for all decoder layers, one weight-/memory-gradient GEMM in the
+    backward; default off until measured on the GPU) computes the same step as the per-layer path and as the oracle."""
+    cfg = dict(TINY, num_features=10)
+    sd = init_state_dict(cfg, 0)
+    video, inp, out = batch(cfg)
+    res = []
+    for fuse in (False, True):
+        eng = Vid2SeqEngine(cfg, TorchOps(), "cpu", fuse_cross_kv=fuse)
+        for n, t in sd.items():
+            eng.p(n).copy_(t)
+        eng.sync_bf16()
+        loss, ctx = eng.forward(video, inp, inp != 0, out, out != 0, want_logits=True)
+        eng.zero_grad()
+        eng.backward(ctx)
+        res.append((loss.item(), ctx["logits"].clone(), {n: eng.g(n).clone() for n in sd}))
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])        # the forward is the same arithmetic
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True)
+    o["loss"].backward()
+    for n in sd:
+        assert rel(res[1][2][n], sdg[n].grad) < 2e-2, n
+        assert rel(res[1][2][n], res[0][2][n]) < 2e-2, n
+    # the layout keeps every decoder parameter in one contiguous range (the data-parallel regions rely on it)
+    lo, hi = eng.decoder_grad_range()
+    for n, (o_, _, cnt) in eng.layout.items():
+        assert n.startswith("t5_model.decoder.") == (lo <= o_ < hi), n

@@ -64,3 +64,21 @@ def param_shapes(cfg: dict):
     if d != 768:
         out += [("proj_v2t.weight", (d, 768)), ("proj_v2t.bias", (d,))]
     return out
+
+
+def layout_order(cfg: dict):
+    """param_shapes(cfg) in the order the engine lays parameters out in its flat buffers: identical, except that the
+    decoder's cross-attention k,v weights of ALL layers form one contiguous group (right before the decoder's final norm),
+    so that a single [num_layers * 2 * inner, d] matrix view exists — the K/V projections of every layer read the same
+    encoder memory and can run as ONE GEMM (engine.fuse_cross_kv).  Initialisation keeps following param_shapes' order."""
+    shapes = param_shapes(cfg)
+    is_ckv = lambda n: ".layer.1.EncDecAttention.k.weight" in n or ".layer.1.EncDecAttention.v.weight" in n
+    group = [e for e in shapes if is_ckv(e[0])]
+    out = []
+    for e in shapes:
+        if is_ckv(e[0]):
+            continue
+        if e[0] == "t5_model.decoder.final_layer_norm.weight":
+            out += group
+        out.append(e)
+    return out

@@ -26,7 +26,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .config import param_shapes, vocab_size
+from .config import layout_order, param_shapes, vocab_size
 from .ops import ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD, NO_DROP, drop_spec
 
 _ALIGN = 64  # elements; keeps every parameter 256 B (fp32) / 128 B (bf16) aligned for TMA
@@ -78,9 +78,18 @@ class _Sub:
 
 class Vid2SeqEngine:
     @staticmethod
-    def layout_of(cfg: dict):
+    def _fuse_cross_kv_default() -> bool:
+        import os
+        return os.environ.get("VIDCHAP_FUSE_CROSS_KV") == "1"
+
+    @staticmethod
+    def layout_of(cfg: dict, grouped_cross_kv: Optional[bool] = None):
+        """name -> (offset, shape, numel) in the flat buffers.  grouped_cross_kv (default: VIDCHAP_FUSE_CROSS_KV) selects
+        config.layout_order, which keeps the decoder's cross-attention k,v weights of all layers contiguous."""
+        if grouped_cross_kv is None:
+            grouped_cross_kv = Vid2SeqEngine._fuse_cross_kv_default()
         layout, off = {}, 0
-        for name, shape in param_shapes(cfg):
+        for name, shape in (layout_order(cfg) if grouped_cross_kv else param_shapes(cfg)):
             n = 1
             for s in shape:
                 n *= s
@@ -89,7 +98,7 @@ class Vid2SeqEngine:
         return layout, off
 
     def __init__(self, cfg: dict, ops, device, label_smoothing: float = 0.1, use_video=True, use_speech=True,
-                 flat_p: Optional[torch.Tensor] = None):
+                 flat_p: Optional[torch.Tensor] = None, fuse_cross_kv: Optional[bool] = None):
         self.cfg, self.ops, self.device = cfg, ops, torch.device(device)
         self.label_smoothing = label_smoothing
         self.use_video, self.use_speech = use_video, use_speech
@@ -99,7 +108,12 @@ class Vid2SeqEngine:
         self.C, self.Hv, self.mlp = cfg["embed_dim"], cfg["heads"], cfg["mlp_dim"]
         assert self.C // self.Hv == 64
         self.V = vocab_size(cfg)
-        self.layout, self.total = self.layout_of(cfg)
+        # VIDCHAP_FUSE_CROSS_KV=1 (experimental, default off, not yet measured on the GPU): the cross-attention K/V
+        # projections of all decoder layers (same input: the encoder memory) as ONE GEMM [B*E, d] x [d, layers*2*inner]
+        # in the forward, and one weight-gradient GEMM + one input-gradient GEMM (K = layers*2*inner) in the backward.
+        # Needs the grouped parameter layout, hence fixed at construction.
+        self.fuse_cross_kv = self._fuse_cross_kv_default() if fuse_cross_kv is None else bool(fuse_cross_kv)
+        self.layout, self.total = self.layout_of(cfg, self.fuse_cross_kv)
         dev = self.device
         if flat_p is not None:
             assert flat_p.numel() == self.total and flat_p.dtype == torch.float32 and flat_p.device == dev
@@ -299,7 +313,7 @@ class Vid2SeqEngine:
                          bias_rel=bias_rel, kmask=kmask, causal=causal, d_attn=d_attn, d_out=d_out))
         return x1
 
-    def _ca_fwd(self, y1, sp: _Sub, B, S, memory, E, mem_mask, tape):
+    def _ca_fwd(self, y1, sp: _Sub, B, S, memory, E, mem_mask, tape, kv=None):
         ops, M, D = self.ops, y1.shape[0], y1.shape[1]
         inner = sp.H * 64
         bf = torch.bfloat16
@@ -308,8 +322,9 @@ class Vid2SeqEngine:
         ops.norm_fwd(0, y1, self.pv(sp.norm_w), None, out_bf16=h, rstd=rstd, eps=sp.eps)
         qc = self._e(M, inner, dtype=bf)
         ops.gemm(h, self.pb(sp.q_w), qc)
-        kv = self._e(B * E, 2 * inner, dtype=bf)
-        ops.gemm(memory, self.pb(sp.kv_w, 2 * inner), kv)
+        if kv is None:
+            kv = self._e(B * E, 2 * inner, dtype=bf)
+            ops.gemm(memory, self.pb(sp.kv_w, 2 * inner), kv)
         ctx = self._e(M, inner, dtype=bf)
         lse = self._e(B, sp.H, S)
         d_attn, d_out = self._site("dec"), self._site("dec")
@@ -428,7 +443,9 @@ class Vid2SeqEngine:
         ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
                      accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b), dxb_drop=next_drop)
 
-    def _ca_bwd(self, r, dx, dxb, ws, memory, dmem, next_drop=NO_DROP):
+    def _ca_bwd(self, r, dx, dxb, ws, memory, dmem, next_drop=NO_DROP, dkv_out=None):
+        """dkv_out: (fuse_cross_kv) this layer's slice of the all-layer dK/dV matrix; the K/V weight and memory gradients
+        are then computed once for all layers by the caller."""
         ops, sp = self.ops, r["sp"]
         M, D = dx.shape
         B, S, E, H = r["B"], r["S"], r["E"], sp.H
@@ -438,7 +455,7 @@ class Vid2SeqEngine:
         ops.gemm(dxb, self.pb(sp.o_w), dctx, b_mn=True)
         dq_acc = ws["dq_acc"][:M * inner].view(M, inner)   # cleared inside attn_bwd
         dq = ws["dqkv"][:M * inner].view(M, inner)
-        dkv = ws["dkv"][:B * E * 2 * inner].view(B * E, 2 * inner)
+        dkv = dkv_out if dkv_out is not None else ws["dkv"][:B * E * 2 * inner].view(B * E, 2 * inner)
         delta = ws["delta"][:B * H * S].view(B, H, S)
         self._wg_wait("dqkv", "dkv")
         ops.attn_bwd(r["qc"], r["kv"], r["kv"], q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=S, Lk=E, out=r["ctx"],
@@ -452,6 +469,8 @@ class Vid2SeqEngine:
         self._wg_wait("dxb")
         ops.norm_bwd(0, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], None, dx=dx, dx_bf16=dxb, accumulate_dx=True,
                      dw=self.gv(sp.norm_w), dxb_drop=next_drop)
+        if dkv_out is not None:
+            return
         self._wgrad(dkv, memory, sp.kv_w, rows=2 * inner, tag="dkv")
         ops.gemm(dkv, self.pb(sp.kv_w, 2 * inner), dmem, b_mn=True, residual=dmem)  # dmem += dkv @ Wkv
 
@@ -560,9 +579,15 @@ class Vid2SeqEngine:
         bias_d = self._e(self.H, 2 * S - 1)
         ops.bias_expand(self.p(self.dec_bias_name), lut_d, bias_d)
         kmask_d = self._mask_u8(output_mask)
-        for sa, ca, ff in self.dec_blocks:
+        kv_all = None
+        if self.fuse_cross_kv:
+            nl2 = len(self.dec_blocks) * 2 * self.inner
+            kv_all = self._e(B * E, nl2, dtype=bf)
+            ops.gemm(memory, self.pb(self.dec_blocks[0][1].kv_w, nl2), kv_all)
+        for li, (sa, ca, ff) in enumerate(self.dec_blocks):
             y = self._sa_fwd(y, sa, B, S, bias_d, kmask_d, True, tape, dk="dec")
-            y = self._ca_fwd(y, ca, B, S, memory, E, mem_mask, tape)
+            kv_i = None if kv_all is None else kv_all[:, li * 2 * self.inner:(li + 1) * 2 * self.inner]
+            y = self._ca_fwd(y, ca, B, S, memory, E, mem_mask, tape, kv=kv_i)
             y = self._ff_fwd(y, ff, tape, dk="dec")
         # ---------------- head: final norm * d^-0.5 (tied), lm_head, label-smoothed CE (modeling_t5.py:1709-1721)
         seq = self._e(B * S, d, dtype=bf)
@@ -631,15 +656,23 @@ class Vid2SeqEngine:
                      dx=dy, dx_bf16=dyb, accumulate_dx=False, dw=self.gv("t5_model.decoder.final_layer_norm.weight"),
                      scale=d ** -0.5, g_drop=ctx["d_fin_d"], dxb_drop=out_drop(i - 1))
         # ---- decoder blocks (reverse)
-        dmem = self._z(B * E, d)
+        nl, inner2 = len(self.dec_blocks), 2 * self.inner
+        fuse = self.fuse_cross_kv
+        dmem = self._e(B * E, d) if fuse else self._z(B * E, d)      # fused: written once by the all-layer GEMM below
+        dkv_all = self._e(B * E, nl * inner2, dtype=bf) if fuse else None
         drel_d = self._z(self.H, 2 * S - 1)
         n_dec_end = ctx["n_enc_tape"]
-        for _ in range(len(self.dec_blocks)):
+        for li in reversed(range(nl)):
             self._ff_bwd(tape[i - 1], dy, dyb, ws, next_drop=out_drop(i - 2))
-            self._ca_bwd(tape[i - 2], dy, dyb, ws, ctx["memory"], dmem, next_drop=out_drop(i - 3))
+            self._ca_bwd(tape[i - 2], dy, dyb, ws, ctx["memory"], dmem, next_drop=out_drop(i - 3),
+                         dkv_out=dkv_all[:, li * inner2:(li + 1) * inner2] if fuse else None)
             self._sa_bwd(tape[i - 3], dy, dyb, ws, drel_d, ctx["lut_d"],
                          next_drop=out_drop(i - 4) if i - 4 >= n_dec_end else NO_DROP)
             i -= 3
+        if fuse:   # K/V projections of all layers at once: dW_kv = dKV^T . memory ; dmemory = dKV . W_kv
+            kv0 = self.dec_blocks[0][1].kv_w
+            self._wgrad(dkv_all, ctx["memory"], kv0, rows=nl * inner2)
+            ops.gemm(dkv_all, self.pb(kv0, nl * inner2), dmem, b_mn=True)
         ops.bias_fold(drel_d, ctx["lut_d"], self.g(self.dec_bias_name))
         ops.embed_bwd(ctx["dec_in"].view(-1), dy, self.g("t5_model.shared.weight"), drop=ctx["d_emb_d"])
         ctx["_bwd_state"] = (dmem, i, ws)
