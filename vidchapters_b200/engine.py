@@ -51,6 +51,33 @@ def relative_position_bucket(relative_position, bidirectional=True, num_buckets=
     return relative_buckets + torch.where(is_small, relative_position, if_large)
 
 
+def _restores_stream(fn):
+    """forward / backward switch torch's current stream to the side stream for the visual-encoder chain.  If anything
+    raises in between (a C-ABI status such as Lk > 1536, an out-of-memory error) the caller's stream is restored and
+    joined with the side stream, so later torch work is not left running unsynchronised on the wrong stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        if self.device.type != "cuda":
+            return fn(self, *a, **k)
+        entry = torch.cuda.current_stream(self.device)
+        try:
+            return fn(self, *a, **k)
+        except BaseException:
+            torch.cuda.set_stream(entry)
+            for side in (self._side_stream, self._wg_stream):
+                if side is not None:
+                    try:
+                        entry.wait_stream(side)
+                    except Exception:
+                        pass
+            self._wg_pending.clear()
+            self._wg_main = None
+            raise
+    return wrapper
+
+
 @dataclass
 class _Sub:
     """One residual sub-layer's parameter names and static attributes."""
@@ -81,6 +108,19 @@ class Vid2SeqEngine:
     def _fuse_cross_kv_default() -> bool:
         import os
         return os.environ.get("VIDCHAP_FUSE_CROSS_KV") == "1"
+
+    @staticmethod
+    def _default_drop_seed() -> int:
+        import os
+        rank = 0
+        try:
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                rank = torch.distributed.get_rank()
+            else:
+                rank = int(os.environ.get("RANK", "0"))
+        except Exception:
+            rank = 0
+        return (int(torch.initial_seed()) ^ (rank * 0x9E3779B1) ^ 0x5EED) & 0xFFFFFFFF
 
     @staticmethod
     def layout_of(cfg: dict, grouped_cross_kv: Optional[bool] = None):
@@ -129,7 +169,10 @@ class Vid2SeqEngine:
         self._luts: Dict[tuple, torch.Tensor] = {}
         self._one = torch.ones(1, dtype=torch.float32, device=dev)
         self.drop_rates = dict(vis=0.0, enc=0.0, dec=0.0)   # vis_drop / enc_drop / dec_drop of the reference ctor
-        self.drop_seed = 0x5EED                             # user seed; every forward call derives its own stream
+        # user seed of the dropout streams: torch's seed (dvc.py:255-258 seeds `args.seed + rank` before the model is
+        # built) mixed with the data-parallel rank, so that --seed changes the masks and replicas draw different ones;
+        # every forward call then derives its own stream from (drop_seed, call counter)
+        self.drop_seed = self._default_drop_seed()
         self._drop_calls = 0
         # The visual encoder (small 1600-row kernels that cannot fill the GPU) runs on a second stream next to the text
         # encoder, forward and backward; joined before the decoder / at the end of the backward.  Inside CUDA-graph capture
@@ -480,6 +523,7 @@ class Vid2SeqEngine:
         m = mask if mask.dtype == torch.bool else (mask != 0)
         return m.contiguous().view(torch.uint8)
 
+    @_restores_stream
     def forward(self, video, input_ids, input_mask, output_ids, output_mask, video_cached: bool = False,
                 want_logits: bool = False, training: bool = False):
         """One Vid2Seq forward (vid2seq.py:58-98).  Returns (loss[1] device tensor, ctx) — ctx feeds backward().
@@ -617,6 +661,7 @@ class Vid2SeqEngine:
         hi = max(self.layout[n][0] + self.layout[n][2] for n in names)
         return lo, hi
 
+    @_restores_stream
     def backward(self, ctx, grad_loss: Optional[torch.Tensor] = None, grad_video: Optional[torch.Tensor] = None,
                  phase: Optional[int] = None):
         """Accumulates d(loss)/d(params) * grad_loss into flat_g.  Returns d/d(cached video) when the forward consumed

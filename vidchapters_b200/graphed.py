@@ -18,6 +18,11 @@ import torch
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, video, input_ids, output_ids, warmup_steps: int = 2):
+        from .vid2seq import _dev_guard
+        with _dev_guard(model._flat.device):
+            self._init(model, optimizer, video, input_ids, output_ids, warmup_steps)
+
+    def _init(self, model, optimizer, video, input_ids, output_ids, warmup_steps):
         """`video` (B,T,768) float, `input_ids` (B,L), `output_ids` (B,S) int64: example batch (any device; shapes are
         frozen).  Masks are `ids != 0` as in dvc.py:44-53.  NOTE: the warm-up runs real optimiser steps on the example
         batch unless warmup_steps=0 (then the caller must have run at least one eager step at these shapes)."""
@@ -88,6 +93,11 @@ class GraphedTrainStep:
     def __call__(self, video=None, input_ids=None, output_ids=None):
         """Copies the batch (host pinned or device tensors) into the static buffers, replays forward+backward, runs the
         optimiser tail.  Returns the (static) 0-dim device loss tensor; `.item()` it to read the value."""
+        from .vid2seq import _dev_guard
+        with _dev_guard(self.model._flat.device):
+            return self._call(video, input_ids, output_ids)
+
+    def _call(self, video=None, input_ids=None, output_ids=None):
         if video is not None:
             self.video.copy_(video, non_blocking=True)
         if input_ids is not None:

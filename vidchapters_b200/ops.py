@@ -40,6 +40,9 @@ class CudaOps:
         if not torch.cuda.is_available():
             raise RuntimeError("vidchapters_b200 needs a CUDA device (B200, sm_100a); none is available")
         _lib.check(self.lib.vc_device_check())
+        # the device this table was built for: every launch goes to the CURRENT device's current stream, so callers
+        # (Vid2Seq / Vid2SeqAdam / GraphedTrainStep entry points) make this device current first and _stream() verifies it
+        self.device_index = torch.cuda.current_device()
         self.launches = 0  # kernels launched through this table (bench.py reports it as gpu_launches)
 
     def set_dropout_salt(self, salt):
@@ -47,8 +50,10 @@ class CudaOps:
         self._salt = salt
         _lib.check(self.lib.vc_set_dropout_salt(None if salt is None else C.c_void_p(salt.data_ptr())))
 
-    @staticmethod
-    def _stream():
+    def _stream(self):
+        if torch.cuda.current_device() != self.device_index:
+            raise RuntimeError(f"vidchapters_b200 ops built for cuda:{self.device_index} called while cuda:"
+                               f"{torch.cuda.current_device()} is current (wrap the call in torch.cuda.device(...))")
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------ GEMM

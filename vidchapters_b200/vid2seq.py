@@ -13,6 +13,9 @@ All parameters are views into ONE flat fp32 buffer (what the fused optimiser and
 """
 from __future__ import annotations
 
+import contextlib
+import os
+import warnings
 from typing import Optional
 
 import torch
@@ -33,6 +36,58 @@ def _get_tokenizer(tokenizer_path, num_bins=0):
     else:
         raise NotImplementedError(tokenizer_path)
     return tokenizer
+
+
+def _dev_guard(device):
+    """Every engine entry point runs with the MODEL's device current: the C ABI launches on the current device / its
+    current stream, and a model on cuda:1 driven while cuda:0 is current would otherwise launch on the wrong GPU."""
+    device = torch.device(device)
+    return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
+
+
+_HF_WEIGHT_FILES = ("model.safetensors", "pytorch_model.bin")
+
+
+def find_pretrained_t5(t5_path) -> Optional[str]:
+    """Weight file of an HF T5 checkpoint directory (what `T5ForConditionalGeneration.from_pretrained(t5_path,
+    local_files_only=True)` would read, model/vid2seq.py:37-38), or None."""
+    if t5_path is None or not os.path.isdir(str(t5_path)):
+        return None
+    for f in _HF_WEIGHT_FILES:
+        if os.path.isfile(os.path.join(str(t5_path), f)):
+            return os.path.join(str(t5_path), f)
+    return None
+
+
+def load_hf_t5_state_dict(path: str) -> dict:
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path)
+    return torch.load(path, map_location="cpu", weights_only=True)
+
+
+def t5_state_to_vid2seq(hf_sd: dict, cfg: dict, generator: Optional[torch.Generator] = None) -> dict:
+    """HF `T5ForConditionalGeneration` state dict -> this module's key space, with the reference's vocabulary surgery
+    (model/vid2seq.py:37-40): `from_pretrained` (32128 rows for the released T5s) -> `resize_token_embeddings(len(tok) -
+    num_bins)` crops to the tokenizer's 32100 rows -> `resize_token_embeddings(len(tok))` appends num_bins rows, which
+    HF-4.28 leaves at nn.Embedding's default N(0,1) init (T5's `_init_weights` has no Embedding branch) ->
+    lm_head re-tied to `shared`.  Keys: `shared.weight`, `{encoder,decoder}.block.*`, `*.final_layer_norm.weight` get the
+    `t5_model.` prefix; `lm_head.weight` / `*.embed_tokens.weight` are aliases of `shared` (tied) and are dropped, as is
+    the cross-attention relative bias some old checkpoints carry."""
+    d, V0, nb = cfg["d_model"], cfg["base_vocab"], cfg["num_bins"]
+    shared = hf_sd["shared.weight"].float()
+    if shared.shape[1] != d:
+        raise ValueError(f"checkpoint d_model {shared.shape[1]} != configured {d}")
+    if shared.shape[0] < V0:
+        raise ValueError(f"checkpoint vocabulary {shared.shape[0]} smaller than the tokenizer's {V0}")
+    new_rows = torch.randn(nb, d, generator=generator)            # nn.Embedding default init of the appended rows
+    out = {"t5_model.shared.weight": torch.cat([shared[:V0], new_rows], 0)}
+    for k, v in hf_sd.items():
+        if k.startswith(("encoder.block.", "decoder.block.")) or k.endswith("final_layer_norm.weight"):
+            if "EncDecAttention.relative_attention_bias" in k:
+                continue
+            out["t5_model." + k] = v.float()
+    return out
 
 
 class _Node(nn.Module):
@@ -64,24 +119,43 @@ class _Vid2SeqFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, grad_vid):
         module = ctx.module
-        module._begin_backward()
-        if grad_loss is None:
-            grad_loss = torch.zeros(1, device=module._flat.device)
-        dvideo = module.engine.backward(ctx.ectx, grad_loss, grad_vid)
-        ctx.ectx = None
-        module._end_backward()
+        with _dev_guard(module._flat.device):
+            module._begin_backward()
+            if grad_loss is None:
+                grad_loss = torch.zeros(1, device=module._flat.device)
+            dvideo = module.engine.backward(ctx.ectx, grad_loss, grad_vid)
+            ctx.ectx = None
+            module._end_backward()
         return None, None, dvideo, None, None, None, None, None
 
 
 class Vid2Seq(nn.Module):
     def __init__(self, t5_path, num_features=100, embed_dim=768, depth=12, heads=12, mlp_dim=2048, vis_drop=0.0,
                  tokenizer=None, enc_drop=0.0, dec_drop=0.1, use_speech=True, use_video=True, num_bins=100,
-                 label_smoothing=0.1, *, t5_config: Optional[dict] = None, seed: int = 0, ops=None):
-        """`t5_path` selects the T5 shape ("t5-base" / "t5-large" in the path, like the reference's from_pretrained
-        directory name).  Weights are seeded-random in the reference's init scheme unless a checkpoint is loaded with
-        `load_state_dict` (offline image: no pretrained files).  `t5_config`, `seed`, `ops` are extensions: an explicit
-        shape dict, the init seed, and an injected op table (tests inject the torch oracle table on CPU)."""
+                 label_smoothing=0.1, *, t5_config: Optional[dict] = None, seed: int = 0, ops=None,
+                 pretrained: Optional[bool] = None):
+        """`t5_path`: as in the reference (model/vid2seq.py:37-38) the directory of an HF T5 checkpoint
+        (`$TRANSFORMERS_CACHE/t5-base`, dvc.py:480).  If it holds `model.safetensors` / `pytorch_model.bin` the T5 weights
+        are loaded from it with the reference's vocabulary surgery (32128 -> 32100 -> +num_bins rows ~ N(0,1)); the
+        visual encoder is seeded-random in the reference's init scheme, like the reference's.  "t5-base" / "t5-large"
+        in the path selects the shape.  `pretrained`: None = load if the files exist, otherwise WARN that the T5 is
+        randomly initialised (the reference would raise: no silent random T5); True = raise if they are missing; False =
+        seeded random init without a warning (benchmarks, tests).  `t5_config` (explicit shape dict; implies
+        pretrained=False unless files exist), `seed`, `ops` (injected op table: tests use the torch oracle table on CPU)
+        are extensions."""
         super().__init__()
+        if "v1_1" in str(t5_path):
+            raise NotImplementedError("gated-activation T5 v1.1 checkpoints (is_gated_act, model/vid2seq.py:38) are not "
+                                      "supported by the B200 path: t5-base / t5-large use ReLU feed-forward layers")
+        weight_file = find_pretrained_t5(t5_path)
+        if weight_file is None:
+            if pretrained:
+                raise OSError(f"no T5 checkpoint (model.safetensors / pytorch_model.bin) under {t5_path!r}")
+            if pretrained is None and t5_config is None:
+                warnings.warn(f"vidchapters_b200.Vid2Seq: no T5 checkpoint found under {t5_path!r}; the T5 weights are "
+                              "RANDOMLY INITIALISED (the reference loads pretrained weights here, model/vid2seq.py:37). "
+                              "Load a checkpoint with load_state_dict / --load, or pass pretrained=False to silence.",
+                              RuntimeWarning, stacklevel=2)
         if t5_config is None:
             key = "t5-large" if "large" in str(t5_path) else "t5-base"
             t5_config = dict(CONFIGS[key])
@@ -104,6 +178,19 @@ class Vid2Seq(nn.Module):
         self._layout, total = probe
         self._flat = torch.zeros(total, dtype=torch.float32)
         sd = init_state_dict(cfg, seed)
+        self.pretrained_from = None
+        if weight_file is not None and pretrained is not False:
+            g = torch.Generator().manual_seed(seed)
+            loaded = t5_state_to_vid2seq(load_hf_t5_state_dict(weight_file), cfg, g)
+            missing = [n for n, _ in param_shapes(cfg) if n.startswith("t5_model.") and n not in loaded]
+            if missing:
+                raise KeyError(f"T5 checkpoint {weight_file} lacks {missing[:4]} ... ({len(missing)} tensors)")
+            for n, t in loaded.items():
+                if n in sd:
+                    if tuple(t.shape) != tuple(sd[n].shape):
+                        raise ValueError(f"{n}: checkpoint shape {tuple(t.shape)} != model shape {tuple(sd[n].shape)}")
+                    sd[n] = t
+            self.pretrained_from = weight_file
         self._params = {}
         for name, shape in param_shapes(cfg):
             o, shp, n = self._layout[name]
@@ -190,6 +277,10 @@ class Vid2Seq(nn.Module):
 
     # ------------------------------------------------------------------ reference surface
     def forward(self, video, input_tokenized, output_tokenized):
+        with _dev_guard(self._flat.device):
+            return self._forward(video, input_tokenized, output_tokenized)
+
+    def _forward(self, video, input_tokenized, output_tokenized):
         self._refresh_shadow()
         cached = isinstance(video, dict)
         if self.use_video:
@@ -211,12 +302,13 @@ class Vid2Seq(nn.Module):
     @torch.no_grad()
     def forward_logits(self, video, input_tokenized, output_tokenized):
         """Debug path: materialises (B,S,V) logits like `model.t5_model(...).logits` in the reference."""
-        self._refresh_shadow()
-        eng = self.engine
-        loss, ectx = eng.forward(video, input_tokenized["input_ids"], input_tokenized["attention_mask"],
-                                 output_tokenized["input_ids"], output_tokenized["attention_mask"], want_logits=True)
-        B, S = ectx["B"], ectx["S"]
-        return loss.view(()), ectx["logits"].reshape(B, S, -1)
+        with _dev_guard(self._flat.device):
+            self._refresh_shadow()
+            eng = self.engine
+            loss, ectx = eng.forward(video, input_tokenized["input_ids"], input_tokenized["attention_mask"],
+                                     output_tokenized["input_ids"], output_tokenized["attention_mask"], want_logits=True)
+            B, S = ectx["B"], ectx["S"]
+            return loss.view(()), ectx["logits"].reshape(B, S, -1)
 
     @torch.no_grad()
     def generate(self, video, input_tokenized, use_nucleus_sampling=False, num_beams=4, max_length=256, min_length=1,
@@ -229,16 +321,17 @@ class Vid2Seq(nn.Module):
                 or min_length > 1:
             raise NotImplementedError("vidchapters_b200.Vid2Seq.generate implements greedy and beam-search decoding "
                                       "(1 <= num_beams <= 8, repetition_penalty 1.0, min_length 1, one caption)")
-        self._refresh_shadow()
-        eng = self.engine
-        ids = input_tokenized["input_ids"] if self.use_speech else None
-        mask = input_tokenized["attention_mask"] if self.use_speech else None
-        memory, mem_mask, B, E = eng.encode(video, ids, mask)
-        if num_beams == 1:
-            seq = eng.generate_greedy(memory, mem_mask, B, E, max_new_tokens=max_length)
-        else:
-            seq = eng.generate_beam(memory, mem_mask, B, E, num_beams=num_beams, max_new_tokens=max_length,
-                                    length_penalty=length_penalty)
+        with _dev_guard(self._flat.device):
+            self._refresh_shadow()
+            eng = self.engine
+            ids = input_tokenized["input_ids"] if self.use_speech else None
+            mask = input_tokenized["attention_mask"] if self.use_speech else None
+            memory, mem_mask, B, E = eng.encode(video, ids, mask)
+            if num_beams == 1:
+                seq = eng.generate_greedy(memory, mem_mask, B, E, max_new_tokens=max_length)
+            else:
+                seq = eng.generate_beam(memory, mem_mask, B, E, num_beams=num_beams, max_new_tokens=max_length,
+                                        length_penalty=length_penalty)
         self.last_generated_ids = seq
         return self.t5_tokenizer.batch_decode(seq, skip_special_tokens=True)
 
