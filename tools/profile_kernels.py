@@ -26,10 +26,24 @@ if which in ("all", "attn"):
     db = torch.zeros(H, 2 * L - 1, device=dev)
     drop = (0xC0FFEE, 6554) if os.environ.get("PROFILE_DROPOUT", "1") == "1" else (0, 0)   # reference default p = 0.1
     kw["drop"] = drop
+    kw["q_like_k"] = os.environ.get("PROFILE_QLK", "1") == "1"     # as the train step calls the text encoder's attention
     for _ in range(3):
         ops.attn_fwd(qkv, qkv, qkv, out=out, lse2=lse, **kw)
         ops.attn_bwd(qkv, qkv, qkv, out=out, lse2=lse, dout=dout, do_col=0, delta=delta, dq_acc=dq, dk=dqkv, dk_col=inner,
                      dv=dqkv, dv_col=2 * inner, dbias_rel=db, bucket_lut=lut, **kw)
+    if os.environ.get("PROFILE_TIME", "0") == "1":
+        for name, fn in (("attn_fwd", lambda: ops.attn_fwd(qkv, qkv, qkv, out=out, lse2=lse, **kw)),
+                         ("attn_bwd", lambda: ops.attn_bwd(qkv, qkv, qkv, out=out, lse2=lse, dout=dout, do_col=0, delta=delta,
+                                                           dq_acc=dq, dk=dqkv, dk_col=inner, dv=dqkv, dv_col=2 * inner,
+                                                           dbias_rel=db, bucket_lut=lut, **kw))):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            print(f"{name}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per call (encoder shape B=16 H=12 L=1000, q_like_k={kw['q_like_k']})")
 if which in ("all", "gemm"):
     M, N, K = 16000, 3072, 768
     A = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()

@@ -45,11 +45,20 @@ struct AttnBwdParams {
   float* dbias_rel;       // fp32 [H][Lq+Lk-1] (atomicAdd) or null
   uint32_t drop_seed, drop_p16;
   const uint32_t* drop_salt;
+  int q_like_k;           // self-attention over a padded sequence: query tiles past the last attended key are skipped
+  long long* trace;       // debug (vc_debug_set_trace): clock64 timeline of CTA (0,0,0), warp 2 lane 0 and the MMA thread
 };
+
+#define VC_TRACE(slot, ev)                                                                                   \
+  do {                                                                                                       \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (slot) < 2048)                    \
+      p.trace[(slot)] = ((long long)(ev) << 48) | (clock64() & 0xFFFFFFFFFFFFLL);                             \
+  } while (0)
 
 constexpr int kBwdSmemTiles = 16384 * 2 /*K,V*/ + 2 * 16384 /*Q ring*/ + 2 * 16384 /*dO ring*/ + 32768 /*P*/ + 32768 /*dS*/;
 constexpr int kBwdRelMax = 2304;  // floats per relative-position window: ceil(Lq/128)*128 + 128 <= 2304 (Lq <= 2176)
-constexpr int kAttnBwdSmem = kBwdSmemTiles + 32768 + 2 * kBwdRelMax * 4 + 512 + 512;  // + dQ staging + d(bias)/bias windows + key ceilings
+constexpr int kBwdTsum = 16 * 24 * 4;   // per compute warp x query tile: d(bias) total of a one-bucket tile
+constexpr int kAttnBwdSmem = kBwdSmemTiles + 32768 + 2 * kBwdRelMax * 4 + 512 + 512 + kBwdTsum;  // + dQ staging + d(bias)/bias windows + key ceilings
 
 template <int NCW>   // compute warps: 8 (two 32-column chunks of the tile per thread) or 16 (one chunk per thread)
 __global__ void __launch_bounds__(64 + NCW * 32, 1)
@@ -82,6 +91,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   int* s_anypen = s_nonuni_b + 24;                        // [1] some key of this tile is masked / out of range
   int* s_tile_att = s_anypen + 1;                         // [1] some key of this tile attends
   int* s_row_att = s_anypen + 2;                          // [1] some key of this batch row attends (causal: key 0 does)
+  int* s_last_key = s_anypen + 3;                         // [1] last attended key of this batch row (q_like_k), -1: none
+  float* s_tsum = reinterpret_cast<float*>(bars + 64);    // [16 warps][24 query tiles]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -95,18 +106,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(s_full, 1);
     mbar_init(pds_full, NCW);   // one arrival per compute warp
     mbar_init(dq_full, 1);
-    mbar_init(dq_read, 8);      // one arrival per staging warp (warps 2..9)
+    mbar_init(dq_read, NCW == 16 ? 16 : 8);   // one arrival per dQ-staging warp
     fence_barrier_init();
   }
   const int nqt_all = (p.Lq + kBT - 1) / kBT;
   if (threadIdx.x < 51) s_nonuni_v[threadIdx.x] = 0;   // (all flag arrays)
+  if (threadIdx.x == 51) *s_last_key = -1;
   __syncthreads();
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is read from here on
   pdl_trigger();
   const int n_rel = p.Lq + kBT;  // relative positions touched by this CTA: (k - q + Lq - 1) - rel_base in [0, Lq+127)
   const int rel_base = k0;       // slot = (k - k0) + (Lq - 1 - q)
-  if (p.dbias_rel)
+  if (p.dbias_rel) {
     for (int i = threadIdx.x; i < kBwdRelMax; i += blockDim.x) s_rel[i] = 0.f;
+    for (int i = threadIdx.x; i < 16 * 24; i += blockDim.x) s_tsum[i] = 0.f;
+  }
   {  // always filled + padded so the per-element loop below is branch-free (see attn_fwd.cu)
     const float* brow_g = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) : nullptr;
     const int n_pad = ((p.Lq + kBT - 1) / kBT) * kBT + kBT;  // covers slot (k-k0) + (Lq-1-q) for every q of every tile
@@ -124,8 +138,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     } else if (p.causal) {
       if (threadIdx.x == 0 && p.kmask[(long long)b * p.Lk] != 0) *s_row_att = 1;
     } else {
+      int last = -1;
       for (int i = threadIdx.x; i < p.Lk; i += blockDim.x)
-        if (p.kmask[(long long)b * p.Lk + i] != 0) *s_row_att = 1;
+        if (p.kmask[(long long)b * p.Lk + i] != 0) last = i;
+      last = __reduce_max_sync(0xffffffffu, last);
+      if (lane == 0 && last >= 0) { *s_row_att = 1; atomicMax(s_last_key, last); }
     }
   }
   __syncthreads();
@@ -163,7 +180,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
 
   const int qt0 = p.causal ? min(kt, nqt_all) : 0;  // causal: query tiles before the key tile see nothing of it
-  const int nqt = nqt_all - qt0;
+  // q_like_k: query rows past the sequence's last token are padding whose upstream gradient is exactly zero (nothing
+  // downstream can observe them), so their tiles add nothing to dK / dV / d(bias) and their dQ stays zero: skip them
+  const int nqt_end = (p.q_like_k && *s_last_key >= 0) ? min(nqt_all, *s_last_key / kBT + 1) : nqt_all;
+  const int nqt = max(nqt_end - qt0, 0);
 
   if (warp == 0 && lane == 0) {
     mbar_arrive_expect_tx(kv_full, 32768);
@@ -183,7 +203,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(kv_full, 0);
     const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK), 0, 1024);
     const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 0, 1024);
-    for (int i = 0; i < nqt; ++i) {
+    // Software pipeline: S/dP of tile i+1 are issued BEFORE dV/dK/dQ of tile i (the score buffers are free as soon as the
+    // compute warps have written P/dS(i), i.e. at pds_full(i)), so the compute warps run the register math of tile i+1
+    // underneath the 768 cycles of dV/dK/dQ(i) instead of waiting for them.
+    auto issue_scores = [&](int i) {
       const int st = i & 1;
       mbar_wait(&qd_full[st], (i >> 1) & 1);
       tc_fence_after();
@@ -194,9 +217,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < 4; ++k) tc_mma_bf16(tDP, dodesc + (uint64_t)(k * 2), vdesc + (uint64_t)(k * 2), id_s, k > 0);
       tc_commit(s_full);
-      mbar_wait(pds_full, i & 1);
-      if (i > 0) mbar_wait(dq_read, (i - 1) & 1);
+    };
+    if (nqt > 0) issue_scores(0);
+    for (int i = 0; i < nqt; ++i) {
+      const int st = i & 1;
+      const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + st * 16384), 0, 1024);
+      const uint64_t dodesc = make_smem_desc_sw128(smem_u32(sDO + st * 16384), 0, 1024);
+      VC_TRACE(1024 + i * 8 + 0, 100);
+      mbar_wait(pds_full, i & 1);          // P/dS(i) in shared memory; S(i), dP(i) consumed
       tc_fence_after();
+      VC_TRACE(1024 + i * 8 + 1, 101);
+      if (i + 1 < nqt) issue_scores(i + 1);
+      VC_TRACE(1024 + i * 8 + 2, 102);
+      if (i > 0) mbar_wait(dq_read, (i - 1) & 1);   // dQ(i-1) has left tensor memory
+      tc_fence_after();
+      VC_TRACE(1024 + i * 8 + 3, 103);
       // MN-major A over the [q rows][kv cols] tiles: 2 atoms of 64 kv (LBO = 16384), 8-row groups 1024 B, +2048 B per 16 q.
       const uint64_t pT = make_smem_desc_sw128(smem_u32(sP), 16384, 1024);
       const uint64_t dsT = make_smem_desc_sw128(smem_u32(sDS), 16384, 1024);
@@ -211,6 +246,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       tc_commit(&qd_empty[st]);
       tc_commit(dq_full);
+      VC_TRACE(1024 + i * 8 + 4, 104);
     }
   } else if (warp >= 2) {
     // ===================== compute: 8 warps = 2 per TMEM lane quarter, each taking 2 of the 4 column chunks ==========
@@ -223,13 +259,83 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int ct = (warp - 2) * 32 + lane;   // 0..255: index among the compute threads
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float drop_sc = p.drop_p16 ? drop_scale(p.drop_p16) : 1.0f;
+    static_assert(NCW == 16 || NCW == 8, "compute warps");
+    // dQ_i: TMEM -> swizzled smem staging -> ONE TMA reduce-add per 32-column half (whole 128-byte lines into the fp32
+    // dQ accumulator) instead of 2048 scattered 16-byte atomics per tile.  Called by warps 2..9 for tile t once
+    // dq_full(t) has been observed.
+    auto stage_dq = [&](int t) {
+      const int q0s = (qt0 + t) * kBT;
+      if constexpr (NCW == 16) {
+        // Warp-local: every compute warp moves ITS 32 rows x 16 columns of dQ: TMEM -> 2 KB private staging block
+        // (SWIZZLE_64B) -> one TMA reduce-add (box 16 x 32 fp32) into the fp32 dQ accumulator.  No CTA-wide barrier: with
+        // two bar.syncs over a shared 128-row box the staging cost ~1500 cycles per tile, all of it waiting for the
+        // slowest warp (r02 timeline, profiles/r02_attn_bwd_timeline.txt).
+        float v[16];
+        tmem_ld16(tDQ + lane_off + part * 16, v);
+        if (lane == 0) bulk_wait_read0();           // this warp's previous reduce has finished reading its block
+        __syncwarp();
+        tmem_ld_wait();
+        if (warp == 2 && lane == 0) VC_TRACE(512 + t * 4 + 0, 8);
+        uint8_t* blk = sDQ + (warp - 2) * 2048;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<float4*>(blk + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+              make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (warp == 2 && lane == 0) VC_TRACE(512 + t * 4 + 1, 9);
+        if (lane == 0) {   // rows past Lq carry zeros (p = 0 there); rows past the tensor are clipped by TMA
+          tma_reduce_add_2d(&tmDQ, blk, h * kBD + part * 16, b * p.Lq + q0s + quarter * 32);
+          bulk_commit();
+        }
+        if (warp == 2 && lane == 0) VC_TRACE(512 + t * 4 + 2, 10);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_read);
+        return;
+      } else {
+        float v[32];
+        tmem_ld32(tDQ + lane_off + half * 32, v);
+        if (ct == 0) bulk_wait_read0();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        tmem_ld_wait();
+        uint8_t* drow_q = sDQ + half * 16384 + r * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(drow_q + ((g ^ (r & 7)) << 4)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+      if (ct == 0) {   // rows past Lq carry zeros (p = 0 there); rows past the tensor are clipped by TMA
+        tma_reduce_add_2d(&tmDQ, sDQ, h * kBD, b * p.Lq + q0s);
+        tma_reduce_add_2d(&tmDQ, sDQ + 16384, h * kBD + 32, b * p.Lq + q0s);
+        bulk_commit();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_read);
+    };
+    // per-row statistics of the next query tile are fetched one tile ahead (their L2 latency was 14 % of the kernel's
+    // stall samples when loaded at the top of the tile, profiles/r02_attn_source_counters.md)
+    float lse2_n = INFINITY, delta_n = 0.f;
+    if (nqt > 0) {
+      const int qn = qt0 * kBT + r;
+      const long long si = ((long long)b * p.H + h) * p.Lq + (qn < p.Lq ? qn : 0);
+      lse2_n = qn < p.Lq ? p.lse2[si] : INFINITY;
+      delta_n = p.delta[si];
+    }
     for (int i = 0; i < nqt; ++i) {
       const int q0 = (qt0 + i) * kBT;
       const int q = q0 + r;
       const bool q_ok = q < p.Lq;
-      const long long stat_idx = ((long long)b * p.H + h) * p.Lq + (q_ok ? q : 0);
-      const float lse2 = q_ok ? p.lse2[stat_idx] : INFINITY;   // rows past Lq: p = exp2(-inf) = 0
-      const float delta = p.delta[stat_idx];
+      const float lse2 = lse2_n;          // rows past Lq: p = exp2(-inf) = 0
+      const float delta = delta_n;
+      if (i + 1 < nqt) {
+        const int qn = q + kBT;
+        const long long si = ((long long)b * p.H + h) * p.Lq + (qn < p.Lq ? qn : 0);
+        lse2_n = qn < p.Lq ? p.lse2[si] : INFINITY;
+        delta_n = p.delta[si];
+      }
       // indexed by k - k0; rows past Lq (zero-filled Q/dO, p forced to 0) clamp to slot 0 to stay inside the window
       const float* brow = s_bias + (q_ok ? (p.Lq - 1 - q) : 0);
       const bool causal_tile = p.causal && (k0 + kBT - 1 > q0);
@@ -240,8 +346,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float nds = -delta * p.scale;          // -delta * scale
       const float sc_s = drop_sc * p.scale;        // dropout 1/(1-p) * scale
       float ds_sum = 0.f;
+      if (warp == 2 && lane == 0) VC_TRACE(i * 8 + 0, 1);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) VC_TRACE(i * 8 + 1, 2);
 #pragma unroll 1
       for (int cc = 0; cc < CPT; ++cc) {
         const int c = part * CPT + cc;
@@ -311,58 +419,51 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (slot >= 0 && a_pos != 0.f) atomicAdd(&s_rel[slot], a_pos * p.inv_scale);   // d(bias) wants the unscaled ds
           if (slot >= 32 && a_neg != 0.f) atomicAdd(&s_rel[slot - 32], a_neg * p.inv_scale);
         }
+        // pack first: while this tile's math ran, the MMAs of the PREVIOUS tile (dV, dK, dQ) may still have been
+        // reading the P / dS tiles; only the stores below have to wait for them
+        uint32_t pk[16], dk_[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { pk[j] = pack_bf16x2(sv[2 * j], sv[2 * j + 1]); dk_[j] = pack_bf16x2(dp[2 * j], dp[2 * j + 1]); }
+        if (warp == 2 && lane == 0) VC_TRACE(i * 8 + 2, 3);
+        if (cc == 0 && i > 0) {
+          mbar_wait(dq_full, (i - 1) & 1);
+          tc_fence_after();
+        }
+        if (warp == 2 && lane == 0) VC_TRACE(i * 8 + 3, 4);
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
         uint8_t* drow = sDS + (c >> 1) * 16384 + r * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int ch = (((c & 1) * 4 + g) ^ (r & 7)) * 16;
-          *reinterpret_cast<uint4*>(prow + ch) =
-              make_uint4(pack_bf16x2(sv[g * 8 + 0], sv[g * 8 + 1]), pack_bf16x2(sv[g * 8 + 2], sv[g * 8 + 3]),
-                         pack_bf16x2(sv[g * 8 + 4], sv[g * 8 + 5]), pack_bf16x2(sv[g * 8 + 6], sv[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(drow + ch) =
-              make_uint4(pack_bf16x2(dp[g * 8 + 0], dp[g * 8 + 1]), pack_bf16x2(dp[g * 8 + 2], dp[g * 8 + 3]),
-                         pack_bf16x2(dp[g * 8 + 4], dp[g * 8 + 5]), pack_bf16x2(dp[g * 8 + 6], dp[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(prow + ch) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+          *reinterpret_cast<uint4*>(drow + ch) = make_uint4(dk_[g * 4], dk_[g * 4 + 1], dk_[g * 4 + 2], dk_[g * 4 + 3]);
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (warp == 2 && lane == 0) VC_TRACE(i * 8 + 4, 5);
       if (tile_sum) {
         // one bucket for the whole tile: deposit the tile's total at one of its relative positions (k = k0, q = q0)
+        // (a plain store into this warp's slot: 16 warps hitting one shared-memory word with float atomics — CAS
+        //  loops — cost ~500 cycles per tile in the r02 timeline; the slots are folded into s_rel at the end)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ds_sum += __shfl_xor_sync(0xffffffffu, ds_sum, o);
-        if (lane == 0) atomicAdd(&s_rel[p.Lq - 1 - q0], ds_sum * p.inv_scale);
+        if (lane == 0) s_tsum[(warp - 2) * 24 + (qt0 + i)] = ds_sum * p.inv_scale;
       }
-      // ---- dQ_i: TMEM -> swizzled smem staging -> ONE TMA reduce-add per 32-column half (whole 128-byte lines into the
-      // fp32 dQ accumulator) instead of 2048 scattered 16-byte atomics per tile.
-      if (io_warp) {
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      {
-        float v[32];
-        tmem_ld32(tDQ + lane_off + half * 32, v);
-        if (ct == 0) bulk_wait_read0();               // the previous tile's reduce has finished reading the staging
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        tmem_ld_wait();
-        uint8_t* drow_q = sDQ + half * 16384 + r * 128;
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<float4*>(drow_q + ((g ^ (r & 7)) << 4)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        fence_proxy_async_smem();
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (ct == 0) {   // rows past Lq carry zeros (p = 0 there); rows past the tensor are clipped by TMA
-          tma_reduce_add_2d(&tmDQ, sDQ, h * kBD, b * p.Lq + q0);
-          tma_reduce_add_2d(&tmDQ, sDQ + 16384, h * kBD + 32, b * p.Lq + q0);
-          bulk_commit();
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_read);
-      }
+      // dQ of the PREVIOUS tile (complete: dq_full(i-1) was observed above) leaves while the tensor pipe computes the
+      // scores of tile i+1
+      if (warp == 2 && lane == 0) VC_TRACE(i * 8 + 6, 7);
+      if ((io_warp || NCW == 16) && i > 0) stage_dq(i - 1);
+      if (warp == 2 && lane == 0) VC_TRACE(i * 8 + 5, 6);
     }
-    if (ct == 0) bulk_wait_all();
+    if ((io_warp || NCW == 16) && nqt > 0) {
+      mbar_wait(dq_full, (nqt - 1) & 1);     // also covers the final dV / dK MMAs
+      tc_fence_after();
+      stage_dq(nqt - 1);
+    }
+    if (NCW == 16 ? lane == 0 : ct == 0) bulk_wait_all();
     // ---- dV, dK: rows = keys of this tile, stored by warps 2..9.  (Their last dq_full wait also covers the final dV/dK MMAs.)
     const int kk = k0 + r;
     if (!io_warp) {
@@ -399,6 +500,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 
   tc_fence_before();
+  __syncthreads();
+  if (p.dbias_rel && threadIdx.x < nqt_all) {   // one-bucket tiles: total of the 16 warps -> the tile's slot (k = k0, q = q0)
+    float t = 0.f;
+    for (int w = 0; w < 16; ++w) t += s_tsum[w * 24 + threadIdx.x];
+    if (t != 0.f) s_rel[p.Lq - 1 - threadIdx.x * kBT] += t;
+  }
   __syncthreads();
   if (p.dbias_rel) {
     float* dst = p.dbias_rel + (long long)h * (p.Lq + p.Lk - 1) + rel_base;
@@ -471,7 +578,11 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
   int s;
   VC_CHECK(((uintptr_t)a->dq_acc & 15) == 0, "vc_attn_bwd: dq_acc must be 16-byte aligned");
-  if ((s = make_tmap_2d_ex(&tmDQ, a->dq_acc, 4, (uint64_t)f->H * 64, (uint64_t)f->B * f->Lq, a->ld_dq, 32, 128, 128)) != VC_OK) return s;
+  static const int ncw = [] { const char* e = getenv("VIDCHAP_ATTN_BWD_WARPS"); return e && atoi(e) == 8 ? 8 : 16; }();
+  // dQ reduce-add boxes: 16 warps -> one [32 rows x 16 cols] fp32 box per warp (SWIZZLE_64B); 8 warps -> [128 x 32] (128B)
+  if (ncw == 16) s = make_tmap_2d_ex(&tmDQ, a->dq_acc, 4, (uint64_t)f->H * 64, (uint64_t)f->B * f->Lq, a->ld_dq, 16, 32, 64);
+  else s = make_tmap_2d_ex(&tmDQ, a->dq_acc, 4, (uint64_t)f->H * 64, (uint64_t)f->B * f->Lq, a->ld_dq, 32, 128, 128);
+  if (s != VC_OK) return s;
   if ((s = make_tmap_3d(&tmQ, f->q, f->ldq, f->Lq, f->B, f->ldq, (uint64_t)f->Lq * f->ldq, 64, kBT)) != VC_OK) return s;
   if ((s = make_tmap_3d(&tmK, f->k, f->ldk, f->Lk, f->B, f->ldk, (uint64_t)f->Lk * f->ldk, 64, kBT)) != VC_OK) return s;
   if ((s = make_tmap_3d(&tmV, f->v, f->ldv, f->Lk, f->B, f->ldv, (uint64_t)f->Lk * f->ldv, 64, kBT)) != VC_OK) return s;
@@ -486,6 +597,9 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   p.dv = (__nv_bfloat16*)a->dv; p.ld_dv = a->ld_dv; p.dv_col = a->dv_col;
   p.dbias_rel = a->dbias_rel;
   p.drop_seed = f->drop_seed; p.drop_p16 = f->drop_p16; p.drop_salt = drop_salt_ptr();
+  p.q_like_k = f->q_like_k;
+  p.trace = debug_trace_ptr();
+  VC_CHECK(!f->q_like_k || (f->Lq == f->Lk && f->kmask && !f->causal), "vc_attn_bwd: q_like_k needs non-causal self-attention with a key mask");
   static bool attr = false;
   if (!attr) {
     VC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
@@ -493,7 +607,6 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
     attr = true;
   }
   dim3 grid((f->Lk + kBT - 1) / kBT, f->H, f->B);
-  static const int ncw = [] { const char* e = getenv("VIDCHAP_ATTN_BWD_WARPS"); return e && atoi(e) == 8 ? 8 : 16; }();
   if (ncw == 8) VC_CUDA(launch_kernel(attn_bwd_kernel<8>, grid, dim3(320), (size_t)kAttnBwdSmem, st, tmQ, tmK, tmV, tmDO, tmDQ, p));
   else VC_CUDA(launch_kernel(attn_bwd_kernel<16>, grid, dim3(576), (size_t)kAttnBwdSmem, st, tmQ, tmK, tmV, tmDO, tmDQ, p));
   VC_CUDA(cudaGetLastError());

@@ -16,6 +16,7 @@
 // columns past Lk are excluded exactly.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -352,6 +353,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 using namespace vc;
 
+namespace vc {
+int launch_attn_fwd_pair(const vc_attn_args* a, cudaStream_t st);   // attn_fwd2.cu
+}
+
 extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   VC_CHECK(a != nullptr, "vc_attn_fwd: null args");
   VC_CHECK(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "vc_attn_fwd: bad dims");
@@ -359,6 +364,12 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   VC_CHECK(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "vc_attn_fwd: strides must be x8");
   VC_CHECK(a->q_col % 8 == 0 && a->k_col % 8 == 0 && a->v_col % 8 == 0, "vc_attn_fwd: column offsets must be x8");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VC_CHECK(a->scale > 0.f, "vc_attn_fwd: scale must be positive");
+  VC_CHECK(!a->q_like_k || (a->Lq == a->Lk && a->kmask), "vc_attn_fwd: q_like_k needs self-attention with a key mask");
+  // training shapes: two query tiles per CTA sharing one K/V stream (attn_fwd2.cu); VIDCHAP_ATTN_FWD_PAIR=0 = A/B switch
+  static const bool pair_on = [] { const char* e = getenv("VIDCHAP_ATTN_FWD_PAIR"); return !(e && e[0] == '0'); }();
+  if (pair_on && a->Lq > 128 && a->q_offset == 0 && a->q_offset_dev == nullptr && a->kv_batch_rows == 0 && a->bias_len == 0)
+    return launch_attn_fwd_pair(a, st);
   CUtensorMap tmQ, tmK, tmV;
   int s;
   const uint64_t kv_rows = a->kv_batch_rows > 0 ? a->kv_batch_rows : a->Lk;  // rows between batches of K/V in memory

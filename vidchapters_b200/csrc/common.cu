@@ -118,13 +118,20 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t d1
 static const uint32_t* g_drop_salt = nullptr;
 const uint32_t* drop_salt_ptr() { return g_drop_salt; }
 
+static long long* g_trace = nullptr;
+long long* debug_trace_ptr() { return g_trace; }
+
 }  // namespace vc
 
+extern "C" int vc_debug_set_trace(void* dev_ptr) {
+  vc::g_trace = reinterpret_cast<long long*>(dev_ptr);
+  return VC_OK;
+}
 extern "C" int vc_set_dropout_salt(const uint32_t* dev_ptr) {
   vc::g_drop_salt = dev_ptr;
   return VC_OK;
 }
-extern "C" int vc_version(void) { return 6; }
+extern "C" int vc_version(void) { return 7; }
 extern "C" const char* vc_last_error(void) { return vc::g_err; }
 extern "C" int vc_device_check(void) {
   int dev = 0;

@@ -61,5 +61,8 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
 // Device pointer to a 32-bit salt XORed into every dropout seed (vc_set_dropout_salt); lets a captured CUDA graph draw
 // fresh masks on every replay.  nullptr = no salt.
 const uint32_t* drop_salt_ptr();
+// Debug only (vc_debug_set_trace): device buffer of >= 2048 int64 that the attention kernels fill with a clock64
+// timeline of one CTA; nullptr (default) = off.
+long long* debug_trace_ptr();
 
 }  // namespace vc

@@ -50,10 +50,13 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  // Each try_wait suspends the warp in hardware for a bounded time (~100 cycles observed), so the loop body must be
+  // tiny: ncu's source counters showed the previous clock64()-based watchdog spending 30 % of the attention kernels'
+  // issued instructions in here (profiles/r02_attn_source_counters.md).  Watchdog: an iteration count (~1-2 s) that
+  // traps (sticky launch error) instead of hanging the GPU on a protocol bug.
+  uint32_t spins = 0;
   while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-    // Watchdog: ~2 s at 2 GHz means a protocol bug; trap (sticky launch error) instead of hanging the GPU.
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 

@@ -66,14 +66,11 @@ def _restores_stream(fn):
             return fn(self, *a, **k)
         except BaseException:
             torch.cuda.set_stream(entry)
-            for side in (self._side_stream, self._wg_stream):
-                if side is not None:
-                    try:
-                        entry.wait_stream(side)
-                    except Exception:
-                        pass
-            self._wg_pending.clear()
-            self._wg_main = None
+            if self._side_stream is not None:
+                try:
+                    entry.wait_stream(self._side_stream)
+                except Exception:
+                    pass
             raise
     return wrapper
 
@@ -106,8 +103,10 @@ class _Sub:
 class Vid2SeqEngine:
     @staticmethod
     def _fuse_cross_kv_default() -> bool:
+        """Cross-attention K/V projections of all decoder layers as one GEMM (measured on B200, config 2: 31.10 ->
+        30.59 ms/step, profiles/README.md round 2); VIDCHAP_FUSE_CROSS_KV=0 restores one GEMM pair per layer."""
         import os
-        return os.environ.get("VIDCHAP_FUSE_CROSS_KV") == "1"
+        return os.environ.get("VIDCHAP_FUSE_CROSS_KV", "1") != "0"
 
     @staticmethod
     def _default_drop_seed() -> int:
@@ -148,10 +147,10 @@ class Vid2SeqEngine:
         self.C, self.Hv, self.mlp = cfg["embed_dim"], cfg["heads"], cfg["mlp_dim"]
         assert self.C // self.Hv == 64
         self.V = vocab_size(cfg)
-        # VIDCHAP_FUSE_CROSS_KV=1 (experimental, default off, not yet measured on the GPU): the cross-attention K/V
-        # projections of all decoder layers (same input: the encoder memory) as ONE GEMM [B*E, d] x [d, layers*2*inner]
-        # in the forward, and one weight-gradient GEMM + one input-gradient GEMM (K = layers*2*inner) in the backward.
-        # Needs the grouped parameter layout, hence fixed at construction.
+        # fuse_cross_kv (default on; VIDCHAP_FUSE_CROSS_KV=0 disables): the cross-attention K/V projections of all decoder
+        # layers (same input: the encoder memory) as ONE GEMM [B*E, d] x [d, layers*2*inner] in the forward, and one
+        # weight-gradient GEMM + one input-gradient GEMM (K = layers*2*inner) in the backward.  Needs the grouped
+        # parameter layout, hence fixed at construction.
         self.fuse_cross_kv = self._fuse_cross_kv_default() if fuse_cross_kv is None else bool(fuse_cross_kv)
         self.layout, self.total = self.layout_of(cfg, self.fuse_cross_kv)
         dev = self.device
@@ -180,13 +179,6 @@ class Vid2SeqEngine:
         import os
         self.dual_stream = os.environ.get("VIDCHAP_DUAL_STREAM", "1") != "0" and self.device.type == "cuda"
         self._side_stream = None
-        # VIDCHAP_WGRAD_STREAM=1 (experimental, default off, not yet measured): weight-gradient GEMMs are off the critical
-        # path of the backward (nothing reads dW before the optimiser), so they are enqueued on their own stream; events
-        # order them after the producer of dY and before the next writer of the scratch buffer that holds dY.
-        self.wgrad_stream = os.environ.get("VIDCHAP_WGRAD_STREAM") == "1" and self.device.type == "cuda"
-        self._wg_stream = None
-        self._wg_main = None
-        self._wg_pending: Dict[str, "torch.cuda.Event"] = {}
         self._build_specs()
 
     # ------------------------------------------------------------------ parameter views
@@ -348,12 +340,15 @@ class Vid2SeqEngine:
         ctx = self._e(M, inner, dtype=bf)
         lse = self._e(B, sp.H, L)
         d_attn, d_out = self._site(dk), self._site(dk)
+        # text encoder: rows past a sequence's last token are padding that no consumer can observe (masked keys get an
+        # exactly-zero probability in every later attention) — whole query tiles of them are skipped, forward and backward
+        qlk = dk == "enc" and kmask is not None
         ops.attn_fwd(qkv, qkv, qkv, q_col=0, k_col=inner, v_col=2 * inner, B=B, H=sp.H, Lq=L, Lk=L, out=ctx, lse2=lse,
-                     bias_rel=bias_rel, kmask=kmask, causal=causal, scale=sp.scale, drop=d_attn)
+                     bias_rel=bias_rel, kmask=kmask, causal=causal, scale=sp.scale, drop=d_attn, q_like_k=qlk)
         x1 = self._e(M, D)
         ops.gemm(ctx, self.pb(sp.o_w), x1, bias=self.pv(sp.o_b), residual=x0, drop=d_out)
         tape.append(dict(t="sa", sp=sp, x0=x0, h=h, rstd=rstd, mean=mean, qkv=qkv, ctx=ctx, lse=lse, B=B, L=L,
-                         bias_rel=bias_rel, kmask=kmask, causal=causal, d_attn=d_attn, d_out=d_out))
+                         bias_rel=bias_rel, kmask=kmask, causal=causal, d_attn=d_attn, d_out=d_out, qlk=qlk))
         return x1
 
     def _ca_fwd(self, y1, sp: _Sub, B, S, memory, E, mem_mask, tape, kv=None):
@@ -399,39 +394,11 @@ class Vid2SeqEngine:
     # ------------------------------------------------------------------ sub-layers: backward
     def _wgrad(self, dy, x, gname, rows=None, tag=None):
         """g[N,K] += dy[M,N]^T @ x[M,K]  (reduction over the token dimension, split-K with fp32 atomics).
-        tag names the scratch buffer dy lives in; with VIDCHAP_WGRAD_STREAM the GEMM then runs on the weight-gradient
-        stream and `_wg_wait(tag)` must precede the next write to that buffer."""
+        (A variant that ran these GEMMs on their own stream, event-ordered against the scratch buffers, measured no gain
+        on B200 — 31.35 vs 31.10 ms/step — and was removed; profiles/README.md round 2.)"""
         out = self.g2(gname, rows)
         splits = self._splits(out.shape[0], out.shape[1], dy.shape[0])
-        if self.wgrad_stream and tag is not None and self._wg_main is not None \
-                and torch.cuda.current_stream(self.device) == self._wg_main:
-            if self._wg_stream is None:
-                self._wg_stream = torch.cuda.Stream(device=self.device)
-            produced = torch.cuda.Event()
-            produced.record(self._wg_main)
-            self._wg_stream.wait_event(produced)
-            prev = self._wg_pending.get(tag)
-            with torch.cuda.stream(self._wg_stream):
-                self.ops.gemm(dy, x, out, a_mn=True, b_mn=True, atomic=True, splits=splits)
-                done = torch.cuda.Event()
-                done.record(self._wg_stream)
-            self._wg_pending[tag] = done        # (the stream is in order: a later event also covers `prev`)
-            del prev
-            return
         self.ops.gemm(dy, x, out, a_mn=True, b_mn=True, atomic=True, splits=splits)
-
-    def _wg_wait(self, *tags):
-        """The current stream waits until the weight-gradient GEMMs reading the named scratch buffers are done."""
-        for tag in tags:
-            ev = self._wg_pending.pop(tag, None)
-            if ev is not None:
-                torch.cuda.current_stream(self.device).wait_event(ev)
-
-    def _wg_join(self):
-        if self._wg_stream is not None and self._wg_main is not None:
-            self._wg_main.wait_stream(self._wg_stream)
-        self._wg_pending.clear()
-        self._wg_main = None
 
     def _ff_bwd(self, r, dx, dxb, ws, next_drop=NO_DROP):
         """dxb arrives already masked by this sub-layer's output dropout (r["d_out"]); the norm backward at the end
@@ -443,7 +410,6 @@ class Vid2SeqEngine:
             ops.colsum_bf16(dxb, self.gv(sp.b2))
         self._wgrad(dxb, r["act"], sp.w2, tag="dxb")
         dact = ws["dact"][:M * dff].view(M, dff)
-        self._wg_wait("dact")
         if sp.act == ACT_GELU:
             ops.gemm(dxb, self.pb(sp.w2), dact, b_mn=True, act=ACT_GELU_BWD, aux=r["pre"], drop=r["d_act"])
         else:
@@ -453,7 +419,6 @@ class Vid2SeqEngine:
         self._wgrad(dact, r["h"], sp.w1, tag="dact")
         dh = ws["dhb"][:M * D].view(M, D)
         ops.gemm(dact, self.pb(sp.w1), dh, b_mn=True)
-        self._wg_wait("dxb")
         ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
                      accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b), dxb_drop=next_drop)
 
@@ -471,18 +436,16 @@ class Vid2SeqEngine:
         dq_acc = ws["dq_acc"][:M * inner].view(M, inner)   # cleared inside attn_bwd
         delta = ws["delta"][:B * H * L].view(B, H, L)
         qkv = r["qkv"]
-        self._wg_wait("dqkv")
         ops.attn_bwd(qkv, qkv, qkv, q_col=0, k_col=inner, v_col=2 * inner, B=B, H=H, Lq=L, Lk=L, out=r["ctx"],
                      lse2=r["lse"], bias_rel=r["bias_rel"], kmask=r["kmask"], causal=r["causal"], scale=sp.scale,
                      dout=dctx, do_col=0, delta=delta, dq_acc=dq_acc, dk=dqkv, dk_col=inner, dv=dqkv, dv_col=2 * inner,
-                     dbias_rel=dbias_rel, bucket_lut=lut, drop=r["d_attn"])
+                     dbias_rel=dbias_rel, bucket_lut=lut, drop=r["d_attn"], q_like_k=r["qlk"])
         ops.cast_f32_bf16(dq_acc, dqkv[:, :inner])
         if sp.qkv_b:
             ops.colsum_bf16(dqkv, self.gv(sp.qkv_b))
         self._wgrad(dqkv, r["h"], sp.qkv_w, rows=3 * inner, tag="dqkv")
         dh = ws["dhb"][:M * D].view(M, D)
         ops.gemm(dqkv, self.pb(sp.qkv_w, 3 * inner), dh, b_mn=True)
-        self._wg_wait("dxb")
         ops.norm_bwd(sp.kind, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], r["mean"], dx=dx, dx_bf16=dxb,
                      accumulate_dx=True, dw=self.gv(sp.norm_w), db=self.gv(sp.norm_b), dxb_drop=next_drop)
 
@@ -500,7 +463,6 @@ class Vid2SeqEngine:
         dq = ws["dqkv"][:M * inner].view(M, inner)
         dkv = dkv_out if dkv_out is not None else ws["dkv"][:B * E * 2 * inner].view(B * E, 2 * inner)
         delta = ws["delta"][:B * H * S].view(B, H, S)
-        self._wg_wait("dqkv", "dkv")
         ops.attn_bwd(r["qc"], r["kv"], r["kv"], q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=S, Lk=E, out=r["ctx"],
                      lse2=r["lse"], bias_rel=None, kmask=r["mem_mask"], causal=False, scale=1.0, dout=dctx, do_col=0,
                      delta=delta, dq_acc=dq_acc, dk=dkv, dk_col=0, dv=dkv, dv_col=inner, dbias_rel=None, bucket_lut=None,
@@ -509,7 +471,6 @@ class Vid2SeqEngine:
         self._wgrad(dq, r["h"], sp.q_w, tag="dqkv")
         dh = ws["dhb"][:M * D].view(M, D)
         ops.gemm(dq, self.pb(sp.q_w), dh, b_mn=True)
-        self._wg_wait("dxb")
         ops.norm_bwd(0, dh, r["x0"], self.pv(sp.norm_w), r["rstd"], None, dx=dx, dx_bf16=dxb, accumulate_dx=True,
                      dw=self.gv(sp.norm_w), dxb_drop=next_drop)
         if dkv_out is not None:
@@ -671,8 +632,6 @@ class Vid2SeqEngine:
         the encoder are final), phase=3 the visual encoder."""
         if phase in (2, 3):
             return self._backward_phase2(ctx, grad_video, part=phase)
-        if self.wgrad_stream:
-            self._wg_main = torch.cuda.current_stream(self.device)
         ops, d = self.ops, self.d
         bf = torch.bfloat16
         tape = ctx["tape"]
@@ -722,7 +681,6 @@ class Vid2SeqEngine:
         ops.embed_bwd(ctx["dec_in"].view(-1), dy, self.g("t5_model.shared.weight"), drop=ctx["d_emb_d"])
         ctx["_bwd_state"] = (dmem, i, ws)
         if phase == 1:
-            self._wg_join()
             return None
         return self._backward_phase2(ctx, grad_video)
 
@@ -734,8 +692,6 @@ class Vid2SeqEngine:
         B, T, L, S, E = ctx["B"], ctx["T"], ctx["L"], ctx["S"], ctx["E"]
         dmem, i, ws = ctx["_bwd_state"] if part == 2 else ctx.pop("_bwd_state")
         do_enc = part in (None, 2)
-        if self.wgrad_stream and self._wg_main is None:
-            self._wg_main = torch.cuda.current_stream(self.device)
 
         def out_drop(j):
             return tape[j]["d_out"] if j >= 0 else NO_DROP
@@ -768,7 +724,6 @@ class Vid2SeqEngine:
             ops.embed_bwd(ctx["enc_ids"].view(-1), dx, self.g("t5_model.shared.weight"), drop=ctx["d_emb_e"])
         if part == 2:   # the saved tape index already points past the text-encoder entries
             ctx["_bwd_state"] = (dmem, i, ws)
-            self._wg_join()
             return None
         # ---- visual encoder
         dvideo_out = None
@@ -808,7 +763,6 @@ class Vid2SeqEngine:
         if side_s is not None:
             torch.cuda.set_stream(main_s)
             main_s.wait_stream(side_s)
-        self._wg_join()
         assert i == 0, i
         return dvideo_out
 

@@ -68,6 +68,18 @@ class GraphedTrainStep:
         self.launches_per_replay = ops.launches - n0   # libvidchap kernels inside the captured graph(s)
         self.replays = 0
 
+    def close(self):
+        """Detaches the dropout salt from the library (the captured graphs keep reading `self.salt`, so the object must
+        stay alive while it is replayed; after close() eager launches draw un-salted masks again)."""
+        try:
+            if getattr(self.model.engine.ops, "_salt", None) is self.salt:
+                self.model.engine.ops.set_dropout_salt(None)
+        except Exception:
+            pass
+
+    def __del__(self):
+        self.close()
+
     def _bwd_phase3(self):
         eng = self.model.engine
         eng.backward(self._ectx, phase=3)

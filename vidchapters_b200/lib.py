@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvidchap.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class GemmArgs(C.Structure):
@@ -48,6 +48,7 @@ class AttnArgs(C.Structure):
         ("drop_seed", C.c_uint32), ("drop_p16", C.c_uint32),
         ("q_offset", C.c_int32), ("q_offset_dev", C.c_void_p), ("kv_batch_rows", C.c_int32),
         ("bias_zero", C.c_int32), ("bias_len", C.c_int32),
+        ("q_like_k", C.c_int32),
     ]
 
 
@@ -92,6 +93,7 @@ SIGNATURES = {
     "vc_beam_topk": [P, I64, I, P, I, I, P, P, P, P],
     "vc_kv_reorder": [P, P, P, I, I, I, I, P],
     "vc_set_dropout_salt": [P],
+    "vc_debug_set_trace": [P],
     "vc_version": [],
     "vc_last_error": [],
     "vc_device_check": [],

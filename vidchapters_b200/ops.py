@@ -99,7 +99,7 @@ class CudaOps:
 
     # ------------------------------------------------------------------ attention
     def _attn_args(self, q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale,
-                   drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0, bias_len=0):
+                   drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0, bias_len=0, q_like_k=False):
         _chk_cuda(q, k, v, out, lse2, bias_rel, kmask)
         for t in (q, k, v, out):
             assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
@@ -124,24 +124,26 @@ class CudaOps:
         a.drop_seed, a.drop_p16 = drop
         a.q_offset, a.kv_batch_rows, a.bias_zero, a.bias_len = q_offset, kv_batch_rows, bias_zero, bias_len
         a.q_offset_dev = None if q_offset_dev is None else q_offset_dev.data_ptr()
+        assert not q_like_k or (Lq == Lk and kmask is not None)
+        a.q_like_k = int(bool(q_like_k))
         return a
 
     def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0,
-                 bias_len=0):
+                 bias_len=0, q_like_k=False):
         a = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale, drop,
-                            q_offset, q_offset_dev, kv_batch_rows, bias_zero, bias_len)
+                            q_offset, q_offset_dev, kv_batch_rows, bias_zero, bias_len, q_like_k)
         _lib.check(self.lib.vc_attn_fwd(C.byref(a), self._stream()))
         self.launches += 1
 
     def attn_bwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, dout, do_col=0, delta, dq_acc, dk, dk_col, dv, dv_col, dbias_rel=None,
-                 bucket_lut=None, drop=NO_DROP):
+                 bucket_lut=None, drop=NO_DROP, q_like_k=False):
         """dq_acc is cleared then accumulated (fp32 atomics); dk/dv are fully written; dbias_rel accumulates."""
         _chk_cuda(dout, delta, dq_acc, dk, dv, dbias_rel, bucket_lut)
         b = _lib.AttnBwdArgs()
         b.fwd = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale,
-                                drop)
+                                drop, q_like_k=q_like_k)
         assert dout.dtype == torch.bfloat16 and dq_acc.dtype == torch.float32 and delta.dtype == torch.float32
         assert dk.dtype == torch.bfloat16 and dv.dtype == torch.bfloat16
         b.dout, b.ld_do, b.do_col = dout.data_ptr(), dout.stride(0), do_col
