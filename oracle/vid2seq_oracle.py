@@ -85,9 +85,12 @@ class DropPlan:
 
 class Arith:
     def __init__(self, emulate_bf16: bool, flash_rounding: bool = False, drop_plan: "DropPlan" = None,
-                 acc64: bool = False, trace: Optional[list] = None):
+                 acc64: bool = False, trace: Optional[list] = None, torch_dropout: Optional[dict] = None):
         self.emu = emulate_bf16
         self.dp = drop_plan
+        # torch_dropout {"vis","enc","dec": p}: nn.Dropout / F.dropout at every reference site with torch's own random
+        # stream — what the reference itself runs in training mode (used by bench.py's CPU arm, not by parity tests)
+        self.tdrop = torch_dropout
         self.acc64 = acc64 and emulate_bf16
         # trace: list that receives (name, x_in, x_out) for every residual sub-layer (detached) — the teacher-forced
         # per-sub-layer parity test feeds x_in to the CUDA sub-layer and compares with x_out
@@ -101,6 +104,8 @@ class Arith:
     def dropout(self, which, x):
         """nn.Dropout / F.dropout site (training mode) with the replayed mask; identity without a plan."""
         if self.dp is None:
+            if self.tdrop and self.tdrop.get(which, 0.0) > 0:
+                return F.dropout(x, self.tdrop[which], training=True)
             return x
         m = self.dp.mask(which, x)
         return x if m is None else x * m
@@ -266,14 +271,14 @@ def t5_decoder(sd, cfg, dec_ids, dec_mask, enc_h, enc_mask, ar: Arith, pfx="t5_m
 
 def vid2seq_forward(sd, cfg, video, input_ids, input_mask, output_ids, output_mask, *, emulate_bf16=False,
                     label_smoothing=0.1, video_is_cached=False, flash_rounding=False, drop_plan=None, use_video=True,
-                    use_speech=True, acc64=False, trace=None):
+                    use_speech=True, acc64=False, trace=None, torch_dropout=None):
     """model/vid2seq.py:58-98 (+ modeling_t5.py:1587-1738).  Dropout-free (p=0 / eval) restatement.
     use_video / use_speech = the reference's --no_video / --no_speech variants (vid2seq.py:59-84): the decoder's memory
     is the visual tokens, the text-encoder states, or their concatenation.
 
     Returns dict(loss, logits (B,S,V), video (B,T,d), memory (B,T+L,d)).
     """
-    ar = Arith(emulate_bf16, flash_rounding, drop_plan, acc64=acc64, trace=trace)
+    ar = Arith(emulate_bf16, flash_rounding, drop_plan, acc64=acc64, trace=trace, torch_dropout=torch_dropout)
     d = cfg["d_model"]
     vid = None
     if use_video:
@@ -354,6 +359,64 @@ def greedy_decode(sd, cfg, memory, mem_mask, max_new_tokens=256, emulate_bf16=Fa
         ids = torch.cat([ids, nxt[:, None]], 1)
         done = done | (nxt == 1)
         if bool(done.all()):
+            break
+    return ids
+
+
+def greedy_decode_cached(sd, cfg, memory, mem_mask, max_new_tokens=256, emulate_bf16=False, stop_when_done=True):
+    """The same greedy loop with the reference's incremental-decoding contract (modeling_t5.py:484-525,551-556,
+    1740-1766): one new token per step, per-layer cache (self-K, self-V grown by concatenation; cross-K, cross-V computed
+    at step 0 and reused), relative bias of the last query row.  Same tokens as greedy_decode (tests/test_oracle_cpu.py);
+    this is the form whose cost matches what `generate(use_cache=True)` does, hence bench.py's CPU decode baseline."""
+    ar = Arith(emulate_bf16)
+    H, dkv, d, nl = cfg["num_heads"], cfg["d_kv"], cfg["d_model"], cfg["num_layers"]
+    B, E = memory.shape[0], memory.shape[1]
+    dev = memory.device
+    pfx = "t5_model.decoder."
+    table = sd[pfx + "block.0.layer.0.SelfAttention.relative_attention_bias.weight"]
+    cross_bias = (1.0 - mem_mask[:, None, None, :].to(torch.float32)) * NEG_MIN
+    split = lambda t, L: t.view(B, L, H, dkv).transpose(1, 2)
+    cross = []
+    for i in range(nl):
+        p = f"{pfx}block.{i}.layer.1.EncDecAttention."
+        cross.append((split(ar.linear(memory, sd[p + "k.weight"]), E), split(ar.linear(memory, sd[p + "v.weight"]), E)))
+    self_kv = [None] * nl
+    ids = torch.zeros(B, 1, dtype=torch.long, device=dev)
+    done = torch.zeros(B, dtype=torch.bool, device=dev)
+    cur = ids[:, 0]
+    for step in range(max_new_tokens):
+        x = sd["t5_model.shared.weight"][cur][:, None, :]                                   # (B,1,d)
+        klen = step + 1
+        # bias row of query position `step` over keys 0..step (modeling_t5.py:551-556: full bias, last row)
+        rel = torch.arange(klen, device=dev)[None, :] - step
+        bias = table[relative_position_bucket(rel, bidirectional=False)].permute(2, 0, 1).unsqueeze(0)   # (1,H,1,klen)
+        for i in range(nl):
+            p = f"{pfx}block.{i}."
+            h = t5_layer_norm(x, sd[p + "layer.0.layer_norm.weight"])
+            a = p + "layer.0.SelfAttention."
+            q = split(ar.linear(h, sd[a + "q.weight"]), 1)
+            k_new, v_new = split(ar.linear(h, sd[a + "k.weight"]), 1), split(ar.linear(h, sd[a + "v.weight"]), 1)
+            if self_kv[i] is None:
+                self_kv[i] = (k_new, v_new)
+            else:
+                self_kv[i] = (torch.cat([self_kv[i][0], k_new], 2), torch.cat([self_kv[i][1], v_new], 2))   # :511-515
+            sc = ar.matmul(q, self_kv[i][0].transpose(3, 2)) + bias
+            o = ar.softmax_pv(sc, self_kv[i][1]).transpose(1, 2).reshape(B, 1, H * dkv)
+            x = x + ar.linear(o, sd[a + "o.weight"])
+            h = t5_layer_norm(x, sd[p + "layer.1.layer_norm.weight"])
+            a = p + "layer.1.EncDecAttention."
+            q = split(ar.linear(h, sd[a + "q.weight"]), 1)
+            sc = ar.matmul(q, cross[i][0].transpose(3, 2)) + cross_bias
+            o = ar.softmax_pv(sc, cross[i][1]).transpose(1, 2).reshape(B, 1, H * dkv)
+            x = x + ar.linear(o, sd[a + "o.weight"])
+            x = t5_ff(sd, p + "layer.2.", x, ar)
+        seq = t5_layer_norm(x, sd[pfx + "final_layer_norm.weight"]) * (d ** -0.5)
+        nxt = ar.linear(seq, sd["t5_model.shared.weight"])[:, 0].argmax(-1)
+        nxt = torch.where(done, torch.zeros_like(nxt), nxt)
+        ids = torch.cat([ids, nxt[:, None]], 1)
+        done = done | (nxt == 1)
+        cur = nxt
+        if stop_when_done and bool(done.all()):
             break
     return ids
 

@@ -63,7 +63,7 @@ def _worker(rank, world, port, outdir):
     ld["loss"].backward()
     opt.step()
     torch.save({n: p.detach().clone() for n, p in m._params.items()}, os.path.join(outdir, f"rank{rank}.pt"))
-    # the graphed step's schedule without the graphs: three backward phases, each finished region of the flat gradient
+    # the graphed step's schedule without the graphs: the backward phases of engine.dp_phases(), each finished region of the flat gradient
     # buffer all-reduced asynchronously while the next phase runs (vidchapters_b200/graphed.py)
     m2 = _make(_cfg())
     opt2 = Vid2SeqAdam(m2, lr=3e-4, clip_max_norm=0.1)
@@ -71,14 +71,12 @@ def _worker(rank, world, port, outdir):
     m2._refresh_shadow()          # bf16 shadow of the freshly initialised fp32 parameters (the module's forward does this)
     loss, ectx = eng.forward(v, it["input_ids"], it["attention_mask"], ot["input_ids"], ot["attention_mask"], training=True)
     eng.zero_grad()
-    lo, hi = eng.decoder_grad_range()
-    eng.backward(ectx, phase=1)
-    w1 = torch.distributed.all_reduce(eng.flat_g[lo:hi], async_op=True)
-    eng.backward(ectx, phase=2)
-    w2 = torch.distributed.all_reduce(eng.flat_g[:lo], async_op=True)
-    eng.backward(ectx, phase=3)
-    w3 = torch.distributed.all_reduce(eng.flat_g[hi:], async_op=True)
-    for w in (w1, w2, w3):
+    works = []
+    for ph, regions in eng.dp_phases():
+        eng.backward(ectx, phase=ph)
+        for lo, hi in regions:
+            works.append(torch.distributed.all_reduce(eng.flat_g[lo:hi], async_op=True))
+    for w in works:
         w.wait()
     m2._end_backward()
     opt2.step(grads_already_reduced=True)

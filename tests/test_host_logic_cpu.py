@@ -98,29 +98,36 @@ def test_engine_t5_large_shapes_and_ragged_lengths():
 
 @pytest.mark.parametrize("cfg", [dict(TINY, num_features=10), dict(TINY_PROJ)], ids=["tiny", "tiny-proj"])
 def test_phased_backward_equals_single_backward(cfg):
-    """GraphedTrainStep (data parallel) runs the backward as three phases so that NCCL can all-reduce the regions of the
-    flat gradient buffer that are already final; the phases must add up to exactly the single-call backward."""
+    """GraphedTrainStep (data parallel) runs the backward as the phases of engine.dp_phases() so that NCCL can all-reduce
+    the regions of the flat gradient buffer that are already final; the phases must add up to exactly the single-call
+    backward, every region must be final when its phase says so, and the regions must tile the whole buffer."""
     sd = init_state_dict(cfg, 0)
     eng = Vid2SeqEngine(cfg, TorchOps(), "cpu")
     for n, t in sd.items():
         eng.p(n).copy_(t)
     eng.sync_bf16()
     video, inp, out = batch(cfg)
-    grads = []
-    for phases in ((None,), (1, 2, 3)):
-        loss, ctx = eng.forward(video, inp, inp != 0, out, out != 0)
-        eng.zero_grad()
-        for ph in phases:
-            eng.backward(ctx, phase=ph)
-            if ph == 1:   # the decoder region is final after phase 1 ...
-                lo, hi = eng.decoder_grad_range()
-                dec_after_1 = eng.flat_g[lo:hi].clone()
-            if ph == 2:   # ... and [shared | text encoder] after phase 2
-                head_after_2 = eng.flat_g[:lo].clone()
-        grads.append(eng.flat_g.clone())
-    assert torch.equal(grads[0], grads[1])
-    assert torch.equal(dec_after_1, grads[0][lo:hi]) and torch.equal(head_after_2, grads[0][:lo])
-    assert grads[0][hi:].abs().sum() > 0   # the visual encoder region exists and is written by phase 3
+    loss, ctx = eng.forward(video, inp, inp != 0, out, out != 0)
+    eng.zero_grad()
+    eng.backward(ctx)
+    ref = eng.flat_g.clone()
+    loss, ctx = eng.forward(video, inp, inp != 0, out, out != 0)
+    eng.zero_grad()
+    snaps, covered = [], torch.zeros(eng.total, dtype=torch.bool)
+    phases = eng.dp_phases()
+    assert len(phases) == 1 + min(3, cfg["num_layers"])
+    for ph, regions in phases:
+        eng.backward(ctx, phase=ph)
+        for lo, hi in regions:
+            snaps.append((lo, hi, eng.flat_g[lo:hi].clone()))
+            assert not covered[lo:hi].any()
+            covered[lo:hi] = True
+    assert covered.all() and "_bwd_state" not in ctx
+    assert torch.equal(eng.flat_g, ref)
+    for lo, hi, g in snaps:
+        assert torch.equal(g, ref[lo:hi]), (lo, hi)
+    lo, hi = phases[-1][1][-1]
+    assert lo == 0 and hi >= eng.layout["t5_model.shared.weight"][2]      # the last region starts at the loss slot's side
 
 
 @pytest.mark.parametrize("use_video,use_speech", [(True, False), (False, True)], ids=["no_speech", "no_video"])

@@ -119,3 +119,23 @@ def test_oracle_matches_live_reference_modality_variants(use_video, use_speech):
             assert sdg[n].grad is None or float(sdg[n].grad.abs().sum()) == 0.0, n
         else:
             assert rel(sdg[n].grad, p.grad) < 1e-2, n
+
+
+def test_cached_greedy_oracle_equals_uncached():
+    """oracle.greedy_decode_cached (the KV-cache form of modeling_t5.py:484-525, what bench.py's CPU decode baseline
+    times) emits the same tokens as the uncached loop that is pinned against the live reference above."""
+    from vidchapters_b200.config import TINY
+    cfg = dict(TINY, num_features=10)
+    for seed, std in ((3, 0.05), (4, 0.02)):     # small embeddings: the tied LM head does not just echo its input
+        sd = init_state_dict(cfg, seed, emb_std=std)
+        g = torch.Generator().manual_seed(seed)
+        for k in sd:
+            if "layer_norm" in k:
+                sd[k] = sd[k] * (1 + 0.5 * torch.randn(sd[k].shape, generator=g))
+        mem = torch.randn(3, 17, 768, generator=g)
+        mask = torch.ones(3, 17, dtype=torch.long)
+        mask[1, -5:] = 0
+        with torch.no_grad():
+            a = O.greedy_decode(sd, cfg, mem, mask, max_new_tokens=9)
+            b = O.greedy_decode_cached(sd, cfg, mem, mask, max_new_tokens=9)
+        assert torch.equal(a, b) and len(set(a[0].tolist())) > 3

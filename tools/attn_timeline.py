@@ -31,6 +31,29 @@ ops.attn_fwd(qkv, qkv, qkv, out=out, lse2=lse, **kw)
 bw = lambda: ops.attn_bwd(qkv, qkv, qkv, out=out, lse2=lse, dout=dout, do_col=0, delta=delta, dq_acc=dq, dk=dqkv, dk_col=inner,
                           dv=dqkv, dv_col=2 * inner, dbias_rel=db, bucket_lut=lut, **kw)
 bw(); bw()
+if len(sys.argv) > 1 and sys.argv[1] == "fwd":
+    ops.lib.vc_debug_set_trace(C.c_void_p(trace.data_ptr()))
+    ops.attn_fwd(qkv, qkv, qkv, out=out, lse2=lse, **kw)
+    torch.cuda.synchronize()
+    ops.lib.vc_debug_set_trace(None)
+    t = trace.cpu().tolist()
+    ev = [(v >> 48, v & 0xFFFFFFFFFFFF, i) for i, v in enumerate(t) if v]
+    t0 = min(e[1] for e in ev)
+    nm = {1: "top", 2: "s_full ok", 3: "pass1 done", 4: "max exchanged", 5: "pv_done(j-1) ok (+rescale)", 6: "pass2 done, p_full",
+          100: "mma: K ready", 101: "mma: s_free ok", 102: "mma: S(j+1) issued", 103: "mma: p_full ok", 104: "mma: PV issued"}
+    for grp, lo, hi in (("softmax group A (warp 2)", 1, 19), ("softmax group B (warp 10)", 21, 39)):
+        print(grp)
+        prev = None
+        for e, c, i in sorted([x for x in ev if lo <= x[0] <= hi], key=lambda x: x[1]):
+            print(f"  tile {(i % 512) // 8}  {nm[e - (lo - 1)]:28s} {c - t0:8d}  +{(c - prev) if prev else 0}")
+            prev = c
+    print("MMA thread (A = group 0, B = group 1)")
+    prev = None
+    for e, c, i in sorted([x for x in ev if x[0] >= 100], key=lambda x: x[1]):
+        gname = "B" if (e - 100) >= 10 else "A"
+        print(f"  tile {(i - 1024) // 16} {gname}  {nm[100 + (e - 100) % 10]:24s} {c - t0:8d}  +{(c - prev) if prev else 0}")
+        prev = c
+    sys.exit(0)
 ops.lib.vc_debug_set_trace(C.c_void_p(trace.data_ptr()))
 bw()
 torch.cuda.synchronize()

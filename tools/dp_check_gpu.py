@@ -33,10 +33,14 @@ m2 = build(cfg); m2.train()
 o2 = Vid2SeqAdam(m2, lr=3e-4, clip_max_norm=0.1)
 ld, _ = m2(video, it, ot); o2.zero_grad(); ld["loss"].backward(); o2.step()
 gs = GraphedTrainStep(m2, o2, video, inp, out, warmup_steps=0)
-assert gs.graph2 is not None
+assert gs.graphs, 'data-parallel schedule not active'
 for _ in range(3):
     loss = gs(video, inp, out)
 torch.cuda.synchronize()
+# the returned loss is the rank-mean (dvc.py:103) carried by the gradient all-reduce: compare with an explicit reduction
+own = gs.loss.detach().clone().reshape(1)
+dist.all_reduce(own)
+assert abs(loss.item() - own.item() / world) < 1e-6 * abs(loss.item()), (loss.item(), own.item() / world)
 p1, p2 = m1.engine.flat_p, m2.engine.flat_p
 err = ((p1 - p2).norm() / p1.norm()).item()
 # identical parameters on every rank

@@ -47,7 +47,14 @@ struct AttnFwd2Params {
   float scale_log2e;
   uint32_t drop_seed, drop_p16;
   const uint32_t* drop_salt;
+  long long* trace;        // debug (vc_debug_set_trace): clock64 timeline of CTA (0,0,0)
 };
+
+#define VC_TRACE2(slot, ev)                                                                                  \
+  do {                                                                                                       \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (slot) < 2048)                    \
+      p.trace[(slot)] = ((long long)(ev) << 48) | (clock64() & 0xFFFFFFFFFFFFLL);                             \
+  } while (0)
 
 constexpr int kP2Tiles = 2 * 16384 + kP2Stages * 16384 * 2 + 2 * 32768;                 // Q | K ring | V ring | P x2
 constexpr int kP2Tail = 512 /*barriers + flags*/ + 4096 /*sMx*/ + 2048 /*sL*/;
@@ -191,16 +198,20 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         bool k_ready = false, v_ready = false;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          if (j + 1 < nkt[g]) {            // S_g(j+1): the group holds S_g(j) in registers already
+          if (j + 1 < nkt[g]) {            // S_g(j+1): the group has read S_g(j) out of tensor memory
             if (!k_ready) { mbar_wait(&k_full[stn], phn); k_ready = true; }
+            VC_TRACE2(1024 + j * 16 + g * 8 + 0, 100 + g * 10);
             mbar_wait(&s_free[g], j & 1);
             tc_fence_after();
+            VC_TRACE2(1024 + j * 16 + g * 8 + 1, 101 + g * 10);
             issue_s(g, j + 1);
+            VC_TRACE2(1024 + j * 16 + g * 8 + 2, 102 + g * 10);
           }
           if (j < nkt[g]) {                // O_g += P_g(j).V(j)
             if (!v_ready) { mbar_wait(&v_full[st], ph); v_ready = true; }
             mbar_wait(&p_full[g], j & 1);
             tc_fence_after();
+            VC_TRACE2(1024 + j * 16 + g * 8 + 3, 103 + g * 10);
             const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + st * 16384), 0, 1024);
 #pragma unroll
             for (int k = 0; k < kP2TK / 16; ++k) {
@@ -208,6 +219,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               tc_mma_bf16(tmem_base + 256 + g * 64, pd, vdesc + (uint64_t)(k * 128), idesc_o, (j > 0 || k > 0));
             }
             tc_commit(&pv_done[g]);
+            VC_TRACE2(1024 + j * 16 + g * 8 + 4, 104 + g * 10);
           }
         }
         if (j + 1 < nkt_max) tc_commit(&k_empty[stn]);   // K(j+1) consumed by every S(j+1) issued above
@@ -246,8 +258,11 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int j = 0; j < n_g; ++j) {
         const int k0 = j * kP2TK;
         const int kh = k0 + hf * 64;
+        const bool tr = (wg == 0 && lane == 0);
+        if (tr) VC_TRACE2(g * 512 + j * 8 + 0, 1 + g * 20);
         mbar_wait(&s_full[g], j & 1);
         tc_fence_after();
+        if (tr) VC_TRACE2(g * 512 + j * 8 + 1, 2 + g * 20);
         // ---- pass 1: row max of s2 over the tile (TMEM reads are cheap: ~900 B/clk/SM measured, the tile is 64 KB)
         const bool causal_tile = p.causal && (k0 + kP2TK - 1 > q0);
         // uniform over the group: the tile's bias window is one value and every key attends
@@ -304,7 +319,9 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // exchange the half-row maxima (slots double-buffered by tile parity)
         float* mx = mxg + (j & 1) * 256;
         mx[hf * 128 + r] = m_loc;
+        if (tr) VC_TRACE2(g * 512 + j * 8 + 2, 3 + g * 20);
         asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        if (tr) VC_TRACE2(g * 512 + j * 8 + 3, 4 + g * 20);
         const float m_new = fmaxf(m_run, ceilf(fmaxf(m_loc, mx[(hf ^ 1) * 128 + r])));
         const float corr = fast_exp2(m_run - m_new);   // first tile: m_run = -inf -> 0
         if (j > 0) {
@@ -320,6 +337,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tmem_st_wait();
           }
         }
+        if (tr) VC_TRACE2(g * 512 + j * 8 + 4, 5 + g * 20);
         // ---- pass 2: p = exp2(s2 - m_new) -> bf16 P (swizzled K-major A operand), row sum.  Fast tiles still hold the
         // raw accumulator: one FMA folds scale, bias and the max.
         const float e_mul = fast ? p.scale_log2e : 1.0f;
@@ -358,6 +376,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
+        if (tr) VC_TRACE2(g * 512 + j * 8 + 5, 6 + g * 20);
         l_run = l_run * corr + l_tile;
         m_run = m_new;
       }
@@ -413,6 +432,7 @@ int launch_attn_fwd_pair(const vc_attn_args* a, cudaStream_t st) {
   p.q_like_k = a->q_like_k;
   p.scale_log2e = a->scale * kP2Log2e;
   p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16; p.drop_salt = drop_salt_ptr();
+  p.trace = debug_trace_ptr();
   VC_CHECK(a->Lk <= kP2MaxLk, "vc_attn_fwd: Lk=%d exceeds the %d keys the bias/mask staging supports", a->Lk, kP2MaxLk);
   const int lk_pad = ((a->Lk + kP2TK - 1) / kP2TK) * kP2TK;
   static bool attr = false;

@@ -160,7 +160,11 @@ class Vid2SeqEngine:
         else:
             self.flat_p = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.flat_pb = torch.zeros(self.total, dtype=torch.bfloat16, device=dev)
-        self.flat_g = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        # gradient buffer: 64 leading floats of slack in front of the parameters' gradients; the last of them carries the
+        # step's loss through the data-parallel all-reduce of the first region (dvc.py:103's loss reduction rides along)
+        self._g_store = torch.zeros(64 + self.total, dtype=torch.float32, device=dev)
+        self.flat_g = self._g_store[64:]
+        self.loss_slot = self._g_store[63:64]
         self.adam_m = None
         self.adam_v = None
         self.adam_step_count = 0
@@ -615,23 +619,57 @@ class Vid2SeqEngine:
 
     # ------------------------------------------------------------------ backward
     def decoder_grad_range(self):
-        """[lo, hi) of flat_g that is final once the head + decoder backward (phase 1) is done: every decoder
-        parameter.  (`shared` still receives the encoder's embedding gradient in phase 2.)"""
+        """[lo, hi) of flat_g that is final once the head + decoder backward is done: every decoder parameter.
+        (`shared` still receives the encoder's embedding gradient later.)"""
         names = [n for n in self.layout if n.startswith("t5_model.decoder.")]
         lo = min(self.layout[n][0] for n in names)
         hi = max(self.layout[n][0] + self.layout[n][2] for n in names)
         return lo, hi
+
+    def _enc_groups(self):
+        """Text-encoder layers in (up to) three groups, ascending; the backward walks them last to first."""
+        nl = len(self.enc_blocks)
+        k = min(3, nl)
+        bounds = [round(j * nl / k) for j in range(k + 1)]
+        return [list(range(bounds[j], bounds[j + 1])) for j in range(k)]
+
+    def dp_phases(self):
+        """Data-parallel schedule of the backward: [(phase, [(lo, hi), ...])].  `backward(ctx, phase=p)` for p = 0, 1, ...
+        in order is the whole backward; after phase p the listed ranges of `flat_g` are FINAL, so their all-reduce can
+        run while the later phases compute (graphed.py).  Phase 0 = LM head + decoder; phase 1 = visual encoder (second
+        stream) next to the last group of text-encoder layers; then the remaining groups; the last phase also folds the
+        relative-position bias and the embedding gradient, which completes `shared` + the first group.  The ranges are
+        ordered so that the LAST one to be reduced — the only one nothing overlaps — is as small as possible."""
+        order = sorted(self.layout.items(), key=lambda kv: kv[1][0])
+        first = lambda pred: next(off for n, (off, _, _) in order if pred(n))
+        lo_dec, hi_dec = self.decoder_grad_range()
+        enc_end = first(lambda n: n.startswith("t5_model.decoder."))
+        dec_end = first(lambda n: n.startswith("visual_encoder."))
+        assert enc_end == lo_dec and hi_dec <= dec_end
+        if not (self.use_video and self.use_speech):
+            return [(0, [(enc_end, dec_end)]), (1, [(0, enc_end), (dec_end, self.total)])]
+        groups = self._enc_groups()
+        start = [0] + [first(lambda n, g=g: n.startswith(f"t5_model.encoder.block.{g[0]}.")) for g in groups[1:]] + [enc_end]
+        phases = [(0, [(enc_end, dec_end)])]
+        for j in range(len(groups) - 1, -1, -1):
+            regions = [(start[j], start[j + 1])]
+            if j == len(groups) - 1:
+                regions = [(dec_end, self.total)] + regions
+            phases.append((len(groups) - j, regions))
+        return phases
 
     @_restores_stream
     def backward(self, ctx, grad_loss: Optional[torch.Tensor] = None, grad_video: Optional[torch.Tensor] = None,
                  phase: Optional[int] = None):
         """Accumulates d(loss)/d(params) * grad_loss into flat_g.  Returns d/d(cached video) when the forward consumed
         a cached visual-encoder output (so it can flow back to the pass that produced it), else None.
-        phase=None runs everything.  Data-parallel overlap (graphed.py): phase=1 runs head + decoder (the decoder's
-        gradients are then final and are all-reduced while the rest runs), phase=2 the text encoder (after it `shared` and
-        the encoder are final), phase=3 the visual encoder."""
-        if phase in (2, 3):
-            return self._backward_phase2(ctx, grad_video, part=phase)
+        phase=None runs everything; phase=p runs one phase of `dp_phases()` (data-parallel overlap, graphed.py)."""
+        if phase is not None and phase >= 1:
+            if not (self.use_video and self.use_speech):
+                return self._backward_rest(ctx, grad_video)
+            groups = self._enc_groups()
+            j = len(groups) - phase
+            return self._backward_rest(ctx, grad_video, enc_layers=groups[j], do_vit=(phase == 1))
         ops, d = self.ops, self.d
         bf = torch.bfloat16
         tape = ctx["tape"]
@@ -673,32 +711,43 @@ class Vid2SeqEngine:
             self._sa_bwd(tape[i - 3], dy, dyb, ws, drel_d, ctx["lut_d"],
                          next_drop=out_drop(i - 4) if i - 4 >= n_dec_end else NO_DROP)
             i -= 3
+        assert i == n_dec_end
         if fuse:   # K/V projections of all layers at once: dW_kv = dKV^T . memory ; dmemory = dKV . W_kv
             kv0 = self.dec_blocks[0][1].kv_w
             self._wgrad(dkv_all, ctx["memory"], kv0, rows=nl * inner2)
             ops.gemm(dkv_all, self.pb(kv0, nl * inner2), dmem, b_mn=True)
         ops.bias_fold(drel_d, ctx["lut_d"], self.g(self.dec_bias_name))
         ops.embed_bwd(ctx["dec_in"].view(-1), dy, self.g("t5_model.shared.weight"), drop=ctx["d_emb_d"])
-        ctx["_bwd_state"] = (dmem, i, ws)
-        if phase == 1:
+        ctx["_bwd_state"] = dict(dmem=dmem, ws=ws, dx=None, dxb=None, drel_e=None, vit_done=False, video_added=False,
+                                 dvideo_out=None)
+        if phase == 0:
             return None
-        return self._backward_phase2(ctx, grad_video)
+        return self._backward_rest(ctx, grad_video)
 
-    def _backward_phase2(self, ctx, grad_video, part=None):
-        """part None: text encoder + visual encoder; 2: text encoder only; 3: visual encoder only (after 2)."""
+    def _backward_rest(self, ctx, grad_video, enc_layers=None, do_vit=True):
+        """Text encoder (the block indices `enc_layers`, walked downwards; None = all of them) and, if `do_vit`, the
+        visual encoder — concurrently on the second stream when both run in this call."""
         ops, d = self.ops, self.d
         bf = torch.bfloat16
         tape = ctx["tape"]
         B, T, L, S, E = ctx["B"], ctx["T"], ctx["L"], ctx["S"], ctx["E"]
-        dmem, i, ws = ctx["_bwd_state"] if part == 2 else ctx.pop("_bwd_state")
-        do_enc = part in (None, 2)
+        st = ctx["_bwd_state"]
+        dmem, ws = st["dmem"], st["ws"]
+        n_vit, n_enc = ctx["n_vit_tape"], ctx["n_enc_tape"]
+        nle = len(self.enc_blocks)
+        if enc_layers is None:
+            enc_layers = list(range(nle))
+        enc_layers = sorted(enc_layers, reverse=True) if self.use_speech else []
+        do_vit = do_vit and self.use_video and not st["vit_done"]
 
         def out_drop(j):
             return tape[j]["d_out"] if j >= 0 else NO_DROP
-        if grad_video is not None and self.use_video and part in (None, 2):
+        if grad_video is not None and self.use_video and not st["video_added"]:
             dmem.view(B, E, d)[:, :T].add_(grad_video.reshape(B, T, d).to(dmem.dtype))
+            st["video_added"] = True
         main_s, side_s = (None, None)
-        if part is None and self.use_video and self.use_speech and not ctx["video_cached"]:
+        ws_v = ws
+        if do_vit and enc_layers and not ctx["video_cached"]:
             main_s, side_s = self._fork()      # forked HERE: the side stream must not wait for the text-encoder backward
             if side_s is not None:             # the two chains run concurrently: the visual one gets its own scratch
                 Mv, Cv = B * T, self.C
@@ -706,35 +755,35 @@ class Vid2SeqEngine:
                             dhb=self._e(Mv * max(d, Cv), dtype=bf), dctx=self._e(Mv * Cv, dtype=bf),
                             dqkv=self._e(Mv * 3 * Cv, dtype=bf), dq_acc=self._e(Mv * Cv), delta=self._e(B * self.Hv * T))
         # ---- text encoder
-        if self.use_speech and do_enc:
-            dx = self._e(B * L, d)
-            dxb = self._e(B * L, d, dtype=bf)
-            ops.norm_bwd(0, dmem, ctx["enc_x"], self.pv("t5_model.encoder.final_layer_norm.weight"), ctx["enc_rstd"], None,
-                         dx=dx, dx_bf16=dxb, accumulate_dx=False, dw=self.gv("t5_model.encoder.final_layer_norm.weight"),
-                         rows_per_batch=L, g_batch_stride=E, g_row_offset=T, g_drop=ctx["d_fin_e"],
-                         dxb_drop=out_drop(i - 1))
-            drel_e = self._z(self.H, 2 * L - 1)
-            n_enc_end = ctx["n_vit_tape"]
-            for _ in range(len(self.enc_blocks)):
-                self._ff_bwd(tape[i - 1], dx, dxb, ws, next_drop=out_drop(i - 2))
-                self._sa_bwd(tape[i - 2], dx, dxb, ws, drel_e, ctx["lut_e"],
-                             next_drop=out_drop(i - 3) if i - 3 >= n_enc_end else NO_DROP)
-                i -= 2
-            ops.bias_fold(drel_e, ctx["lut_e"], self.g(self.enc_bias_name))
-            ops.embed_bwd(ctx["enc_ids"].view(-1), dx, self.g("t5_model.shared.weight"), drop=ctx["d_emb_e"])
-        if part == 2:   # the saved tape index already points past the text-encoder entries
-            ctx["_bwd_state"] = (dmem, i, ws)
-            return None
+        if enc_layers:
+            if st["dx"] is None:
+                assert enc_layers[0] == nle - 1, "the text-encoder backward starts at its last layer"
+                st["dx"] = self._e(B * L, d)
+                st["dxb"] = self._e(B * L, d, dtype=bf)
+                ops.norm_bwd(0, dmem, ctx["enc_x"], self.pv("t5_model.encoder.final_layer_norm.weight"), ctx["enc_rstd"],
+                             None, dx=st["dx"], dx_bf16=st["dxb"], accumulate_dx=False,
+                             dw=self.gv("t5_model.encoder.final_layer_norm.weight"), rows_per_batch=L, g_batch_stride=E,
+                             g_row_offset=T, g_drop=ctx["d_fin_e"], dxb_drop=out_drop(n_enc - 1))
+                st["drel_e"] = self._z(self.H, 2 * L - 1)
+            dx, dxb, drel_e = st["dx"], st["dxb"], st["drel_e"]
+            for li in enc_layers:
+                i_sa, i_ff = n_vit + 2 * li, n_vit + 2 * li + 1
+                self._ff_bwd(tape[i_ff], dx, dxb, ws, next_drop=out_drop(i_sa))
+                self._sa_bwd(tape[i_sa], dx, dxb, ws, drel_e, ctx["lut_e"],
+                             next_drop=out_drop(i_sa - 1) if i_sa - 1 >= n_vit else NO_DROP)
+            if enc_layers[-1] == 0:
+                ops.bias_fold(drel_e, ctx["lut_e"], self.g(self.enc_bias_name))
+                ops.embed_bwd(ctx["enc_ids"].view(-1), dx, self.g("t5_model.shared.weight"), drop=ctx["d_emb_e"])
         # ---- visual encoder
-        dvideo_out = None
-        if side_s is not None:
-            torch.cuda.set_stream(side_s)
-            ws = ws_v
-        if self.use_video:
+        if do_vit:
+            if side_s is not None:
+                torch.cuda.set_stream(side_s)
+            wsv = ws_v
             if ctx["video_cached"]:
-                dvideo_out = dmem.view(B, E, d)[:, :T].contiguous()
+                st["dvideo_out"] = dmem.view(B, E, d)[:, :T].contiguous()
             else:
                 C = self.C
+                i = n_vit
                 dxv = self._e(B * T, C)
                 dxvb = self._e(B * T, C, dtype=bf)
                 if ctx["vit_vn"] is None:
@@ -748,23 +797,27 @@ class Vid2SeqEngine:
                     ops.cast_f32_bf16(dvid, dvb)
                     ops.colsum_bf16(dvb, self.gv("proj_v2t.bias"))
                     self._wgrad(dvb, ctx["vit_vn"], "proj_v2t.weight")
-                    dvn = ws["dh"][:B * T * C].view(B * T, C)
+                    dvn = wsv["dh"][:B * T * C].view(B * T, C)
                     ops.gemm(dvb, self.pb("proj_v2t.weight"), dvn, b_mn=True)
                     ops.norm_bwd(1, dvn, ctx["vit_x"], self.pv("visual_encoder.norm.weight"), ctx["vit_rstd"],
                                  ctx["vit_mean"], dx=dxv, dx_bf16=dxvb, accumulate_dx=False,
                                  dw=self.gv("visual_encoder.norm.weight"), db=self.gv("visual_encoder.norm.bias"),
                                  dxb_drop=out_drop(i - 1))
                 for _ in range(len(self.vit_blocks)):
-                    self._ff_bwd(tape[i - 1], dxv, dxvb, ws, next_drop=out_drop(i - 2))
-                    self._sa_bwd(tape[i - 2], dxv, dxvb, ws, None, None, next_drop=out_drop(i - 3))
+                    self._ff_bwd(tape[i - 1], dxv, dxvb, wsv, next_drop=out_drop(i - 2))
+                    self._sa_bwd(tape[i - 2], dxv, dxvb, wsv, None, None, next_drop=out_drop(i - 3))
                     i -= 2
+                assert i == 0, i
                 ops.add_pos_bwd(dxv, self.g("visual_encoder.pos_embed"), B, T, C, self.cfg["num_features"],
                                 drop=ctx["d_pos"])
-        if side_s is not None:
-            torch.cuda.set_stream(main_s)
-            main_s.wait_stream(side_s)
-        assert i == 0, i
-        return dvideo_out
+            st["vit_done"] = True
+            if side_s is not None:
+                torch.cuda.set_stream(main_s)
+                main_s.wait_stream(side_s)
+        finished = (st["vit_done"] or not self.use_video) and (not self.use_speech or (enc_layers and enc_layers[-1] == 0))
+        if finished:
+            ctx.pop("_bwd_state")
+        return st["dvideo_out"]
 
     # ------------------------------------------------------------------ inference: encode + greedy decode
     @torch.no_grad()
@@ -854,38 +907,42 @@ class Vid2SeqEngine:
         ops.gemm(h, self.pb("t5_model.shared.weight"), logits)
         return logits
 
-    def generate_greedy(self, memory, mem_mask, B, E, max_new_tokens=256, use_graph=None, check_every=16):
-        """Greedy decoding with a KV cache (HF-4.28 greedy semantics: start id 0, argmax, sequences that emitted eos=1
-        continue with pad=0, stop when all are done or after max_new_tokens).  Returns int64 [B, 1 + n] ids including
-        the start token, like `t5_model.generate` (model/vid2seq.py:150-162 with num_beams=1).
-        One decode step = a fixed launch sequence driven by a DEVICE step counter -> captured once as a CUDA graph."""
-        ops, d, H, inner = self.ops, self.d, self.H, self.inner
+    def _greedy_setup(self, memory, mem_mask, B, E, S, use_graph):
+        """Cross-attention K/V of every layer (modeling_t5.py:516-524), self-attention caches, the decode state and ONE
+        decode step captured as a CUDA graph (the step position is a device scalar, so the launch sequence is fixed)."""
+        ops, H, inner = self.ops, self.H, self.inner
         bf, dev = torch.bfloat16, self.device
-        S = int(max_new_tokens)
         nl = len(self.dec_blocks)
-        if use_graph is None:
-            use_graph = dev.type == "cuda" and getattr(ops, "name", "") == "cuda"
-        # cross-attention K/V of every layer once (modeling_t5.py:516-524), self-attention caches
-        kvmem = []
-        for sa, ca, ff in self.dec_blocks:
-            kv = self._e(B * E, 2 * inner, dtype=bf)
-            ops.gemm(memory, self.pb(ca.kv_w, 2 * inner), kv)
-            kvmem.append(kv)
+        if self.fuse_cross_kv:          # one GEMM for all layers (same input), per-layer column slices
+            kv_all = self._e(B * E, nl * 2 * inner, dtype=bf)
+            ops.gemm(memory, self.pb(self.dec_blocks[0][1].kv_w, nl * 2 * inner), kv_all)
+            kvmem = [kv_all[:, li * 2 * inner:(li + 1) * 2 * inner] for li in range(nl)]
+        else:
+            kvmem = []
+            for sa, ca, ff in self.dec_blocks:
+                kv = self._e(B * E, 2 * inner, dtype=bf)
+                ops.gemm(memory, self.pb(ca.kv_w, 2 * inner), kv)
+                kvmem.append(kv)
         caches = [torch.zeros(B, S, 2 * inner, dtype=bf, device=dev) for _ in range(nl)]
         bias_d = self._e(H, 2 * S - 1)
         ops.bias_expand(self.p(self.dec_bias_name), self.lut(S, S, False), bias_d)
-        pos = torch.zeros(1, dtype=torch.int32, device=dev)
-        ids = torch.zeros(B, dtype=torch.int64, device=dev)            # decoder_start_token_id = 0
-        seq = torch.zeros(B, S + 1, dtype=torch.int64, device=dev)
-        done = torch.zeros(B, dtype=torch.uint8, device=dev)
+        st = dict(pos=torch.zeros(1, dtype=torch.int32, device=dev),
+                  ids=torch.zeros(B, dtype=torch.int64, device=dev),            # decoder_start_token_id = 0
+                  seq=torch.zeros(B, S + 1, dtype=torch.int64, device=dev),
+                  done=torch.zeros(B, dtype=torch.uint8, device=dev), caches=caches, graph=None)
         buf = self._decode_buffers(B)
 
         def step():
-            logits = self._decode_step_logits(ids, buf, caches, kvmem, mem_mask, bias_d, pos, B, S, E)
-            ops.greedy_next(logits, done, ids, seq, pos, 1, 0)
-            ops.step_advance(pos)
+            logits = self._decode_step_logits(st["ids"], buf, caches, kvmem, mem_mask, bias_d, st["pos"], B, S, E)
+            ops.greedy_next(logits, st["done"], st["ids"], st["seq"], st["pos"], 1, 0)
+            ops.step_advance(st["pos"])
 
-        graph = None
+        def rewind():
+            st["pos"].zero_(); st["ids"].zero_(); st["seq"].zero_(); st["done"].zero_()
+            for c in caches:
+                c.zero_()
+
+        st["step"], st["rewind"] = step, rewind
         if use_graph:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -893,25 +950,50 @@ class Vid2SeqEngine:
                 step()                                  # warm-up (attribute setup, LUT uploads) ...
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
-            pos.zero_(); ids.zero_(); seq.zero_(); done.zero_()   # ... then rewind the state
-            for c in caches:
-                c.zero_()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            rewind()                                    # ... then rewind the state
+            st["graph"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st["graph"]):
                 step()
-            n = 1
-        else:
-            step()
-            n = 1
+            rewind()
+        return st
+
+    def generate_greedy(self, memory, mem_mask, B, E, max_new_tokens=256, use_graph=None, check_every=16):
+        """Greedy decoding with a KV cache (HF-4.28 greedy semantics: start id 0, argmax, sequences that emitted eos=1
+        continue with pad=0, stop when all are done or after max_new_tokens).  Returns int64 [B, 1 + n] ids including
+        the start token, like `t5_model.generate` (model/vid2seq.py:150-162 with num_beams=1).
+        One decode step = a fixed launch sequence driven by a DEVICE step counter -> captured once as a CUDA graph."""
+        S = int(max_new_tokens)
+        if use_graph is None:
+            use_graph = self.device.type == "cuda" and getattr(self.ops, "name", "") == "cuda"
+        st = self._greedy_setup(memory, mem_mask, B, E, S, use_graph)
+        n = 0
         while n < S:
-            if n % check_every == 0 and bool(done.all().item()):
+            if n and n % check_every == 0 and bool(st["done"].all().item()):
                 break
-            if graph is not None:
-                graph.replay()
+            if st["graph"] is not None:
+                st["graph"].replay()
             else:
-                step()
+                st["step"]()
             n += 1
-        return seq[:, :n + 1].clone()
+        return st["seq"][:, :n + 1].clone()
+
+    @torch.no_grad()
+    def time_greedy_loop(self, memory, mem_mask, B, E, max_new_tokens=256):
+        """Device time (ms, CUDA events) of `max_new_tokens` replays of the captured decode step — the decode loop alone,
+        without encoders, cross K/V projection and capture (bench.py's HBM roofline of BASELINE configs[4])."""
+        S = int(max_new_tokens)
+        st = self._greedy_setup(memory, mem_mask, B, E, S, True)
+        for _ in range(3):
+            st["graph"].replay()
+        st["rewind"]()
+        torch.cuda.synchronize(self.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(S):
+            st["graph"].replay()
+        e1.record()
+        torch.cuda.synchronize(self.device)
+        return e0.elapsed_time(e1)
 
     def generate_beam(self, memory, mem_mask, B, E, num_beams=4, max_new_tokens=256, length_penalty=1.0, use_graph=None,
                       eos_id=1, pad_id=0):

@@ -50,18 +50,26 @@ class GraphedTrainStep:
         ops = model.engine.ops
         n0 = ops.launches
         self.world = getattr(optimizer, "world_size", 1)
-        self.graph2 = None
+        self.graphs = []          # data parallel: one graph per backward phase after the first
+        self.phases = None
         if self.world > 1:
-            # data parallel: three graphs (forward + head/decoder backward | text-encoder backward | visual-encoder
-            # backward), so that NCCL all-reduces each finished region of the gradient buffer while the next phase runs
+            # data parallel: the backward is captured as the phases of engine.dp_phases() — forward + LM head + decoder |
+            # visual encoder next to the last third of the text encoder | middle third | first third + embeddings — and
+            # NCCL all-reduces each finished region of the gradient buffer while the following phases run
+            eng = model.engine
+            self.phases = eng.dp_phases()
             with torch.cuda.graph(self.graph):
-                self.loss = self._fwd_bwd(phase=1)
-            self.graph2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
-                self.model.engine.backward(self._ectx, phase=2)
-            self.graph3 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph3, pool=self.graph.pool()):
-                self._bwd_phase3()
+                self.loss = self._fwd_bwd(phase=0)
+            for k, (ph, _) in enumerate(self.phases[1:]):
+                g = torch.cuda.CUDAGraph()
+                last = k == len(self.phases) - 2
+                with torch.cuda.graph(g, pool=self.graph.pool()):
+                    eng.backward(self._ectx, phase=ph)
+                    if last:
+                        self._ectx = None
+                        self.model._end_backward()
+                self.graphs.append(g)
+            self.loss_avg = torch.zeros((), dtype=torch.float32, device=dev)
         else:
             with torch.cuda.graph(self.graph):
                 self.loss = self._fwd_bwd()
@@ -80,12 +88,6 @@ class GraphedTrainStep:
     def __del__(self):
         self.close()
 
-    def _bwd_phase3(self):
-        eng = self.model.engine
-        eng.backward(self._ectx, phase=3)
-        self._ectx = None
-        self.model._end_backward()
-
     def _fwd_bwd(self, phase=None):
         """Forward + backward through the engine directly (no autograd engine inside the capture: its cross-stream
         bookkeeping for leaf tensors is not capture-safe); gradients land in the flat buffer that `p.grad` views."""
@@ -96,8 +98,9 @@ class GraphedTrainStep:
         loss, ectx = eng.forward(self.video, ids, ids != 0, out, out != 0, training=m.training)
         eng.zero_grad()
         eng.backward(ectx, phase=phase)
-        if phase == 1:
-            self._ectx = ectx      # phases 2 and 3 are captured into their own graphs
+        if phase == 0:
+            eng.loss_slot.copy_(loss.view(1))   # rides through the all-reduce of the last gradient region (dvc.py:103)
+            self._ectx = ectx                   # the later phases are captured into their own graphs
         else:
             m._end_backward()      # host-side: make every Parameter's .grad a view of the flat gradient buffer
         return loss.view(())
@@ -122,20 +125,28 @@ class GraphedTrainStep:
         self.graph.replay()
         self.replays += 1
         self.model.engine.ops.launches += self.launches_per_replay
-        if self.graph2 is None:
+        if not self.graphs:
             self.optimizer.step()
             return self.loss
         eng = self.model.engine
-        lo, hi = eng.decoder_grad_range()
         pg = self.optimizer.pg
-        # flat_g = [shared | text encoder | decoder | visual encoder, proj]: each region is all-reduced by NCCL (its own
-        # stream) as soon as the phase that finishes it has been enqueued, overlapping the phases that follow
-        w1 = torch.distributed.all_reduce(eng.flat_g[lo:hi], group=pg, async_op=True)   # decoder, during phases 2-3
-        self.graph2.replay()
-        w2 = torch.distributed.all_reduce(eng.flat_g[:lo], group=pg, async_op=True)     # shared + text encoder, during 3
-        self.graph3.replay()
-        w3 = torch.distributed.all_reduce(eng.flat_g[hi:], group=pg, async_op=True)     # visual encoder (+ proj)
-        for w in (w1, w2, w3):
+        # each region of flat_g is all-reduced by NCCL (its own stream) as soon as the phase that finishes it has been
+        # enqueued, overlapping the phases that follow; the last region starts at the loss slot, so the rank-mean loss of
+        # dvc.py:103 (util/dist.py:89-113) costs no collective of its own
+        works = []
+        n_ph = len(self.phases)
+        for k, (ph, regions) in enumerate(self.phases):
+            if k > 0:
+                self.graphs[k - 1].replay()
+            for r, (lo, hi) in enumerate(regions):
+                if k == n_ph - 1 and r == len(regions) - 1:
+                    assert lo == 0
+                    buf = eng._g_store[60:64 + hi]          # [.., loss slot | shared | first encoder layers]
+                else:
+                    buf = eng.flat_g[lo:hi]
+                works.append(torch.distributed.all_reduce(buf, group=pg, async_op=True))
+        for w in works:
             w.wait()
         self.optimizer.step(grads_already_reduced=True)
-        return self.loss
+        torch.div(eng.loss_slot[0], float(self.world), out=self.loss_avg)
+        return self.loss_avg
