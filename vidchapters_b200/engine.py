@@ -627,11 +627,16 @@ class Vid2SeqEngine:
         return lo, hi
 
     def _enc_groups(self):
-        """Text-encoder layers in (up to) three groups, ascending; the backward walks them last to first."""
+        """Text-encoder layers in (up to) three groups, ascending; the backward walks them last to first.  Uneven on
+        purpose: the group walked FIRST is the upper half (the visual encoder's backward runs next to it on the second
+        stream and needs that long), the group walked LAST is as small as possible, because its gradient region — which
+        also holds `shared`, final only after the embedding backward — is the one all-reduce that nothing overlaps."""
         nl = len(self.enc_blocks)
-        k = min(3, nl)
-        bounds = [round(j * nl / k) for j in range(k + 1)]
-        return [list(range(bounds[j], bounds[j + 1])) for j in range(k)]
+        if nl < 3:
+            return [[i] for i in range(nl)]
+        first = max(1, nl // 12)
+        upper = nl // 2
+        return [list(range(0, first)), list(range(first, nl - upper)), list(range(nl - upper, nl))]
 
     def dp_phases(self):
         """Data-parallel schedule of the backward: [(phase, [(lo, hi), ...])].  `backward(ctx, phase=p)` for p = 0, 1, ...
