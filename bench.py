@@ -355,7 +355,7 @@ def run_train(args):
         s.record()
         r = orig_gemm(A, Bm, out, **kw)
         e.record()
-        rec.append((s, e, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), str(out.dtype).replace("torch.", ""),
+        rec.append((s, e, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), str(out.dtype).replace("torch.", "") if out is not None else "none",
                                             int(kw.get("act", 0)), int(kw.get("atomic", False)), int(kw.get("splits", 1)))))
         return r
 

@@ -35,7 +35,7 @@ int vc_debug_set_trace(void* dev_ptr);
  * Replaces nn.Linear forward (modeling_t5.py:305,310,528-536,581,1714; vit.py:17-20,41,53) and its autograd
  * dgrad/wgrad.  a_mn_major: A is stored [K][M] (lda = row stride) instead of [M][K]; b_mn_major: B is stored
  * [K][N] instead of [N][K].  Epilogue order: *alpha, +bias[N], (pre_out=copy), act, +residual, store.
- *   act: 0 none | 1 relu | 2 gelu(erf) | 3 multiply by relu'(aux) | 4 multiply by gelu'(aux)
+ *   act: 0 none | 1 relu | 2 gelu(erf) | 3 multiply by relu'(aux) | 4 multiply by gelu'(aux) | 5, 6 fused cross entropy (below)
  *   atomic=1 (fp32 out only): atomicAdd into out; required when splits>1 (split-K over `splits` CTAs).
  * Dropout everywhere in this ABI is counter-based: p16 = round(p*65536), element kept iff a 16-bit hash of
  * (seed, element index) >= p16, kept values scaled by 65536/(65536-p16); p16 = 0 disables it. */
@@ -55,6 +55,13 @@ typedef struct vc_gemm_args {
   int32_t splits;
   int32_t tile_n;   /* 0 = auto, else 64/128/256 */
   uint32_t drop_seed, drop_p16;  /* dropout after act, before +residual; keep iff rnd16(seed, row*N+col) >= p16 */
+  /* ---- LM head fused with the label-smoothed cross entropy (modeling_t5.py:1714-1721): the fp32 logits never exist.
+   * act 5 (statistics pass): nothing is stored to `out`; every 128-row x tile_n block contributes, per row and per
+   *   64*(tile_n/128)-column half block, a partial (max, sum exp(z - max), sum z) to ce_stats[row][slot][3] with
+   *   slot = 2*(col/tile_n) + half, and the logit of the row's label to ce_zy[row].  tile_n must be given (128 or 256).
+   * act 6 (gradient pass): out (bf16) = d loss / d logits = (exp(z - ce_lse[row]) - s/V - (1-s)[col == label]) / *ce_nvalid,
+   *   zero rows for label -100.  vc_ce_combine turns the partials into ce_lse and the loss in between. */
+  const int64_t* ce_labels; float* ce_stats; float* ce_zy; const float* ce_lse; const float* ce_nvalid; float ce_smoothing;
 } vc_gemm_args;
 int vc_gemm_bf16(const vc_gemm_args* args, void* stream);
 
@@ -142,6 +149,10 @@ int vc_add_pos_bwd(const float* dx, float* dpos, int B, int T, int C, int P, uin
  * dlogits (bf16, optional) = d loss / d logits for upstream gradient 1. */
 int vc_cross_entropy(const float* logits, int64_t ld, const int64_t* labels, const float* n_valid, float smoothing,
                      float* loss_out, void* dlogits_bf16, int64_t ldd, int n, int V, void* stream);
+/* Combines the partials of the act-5 GEMM: lse[row] = log sum_c exp(z_c); loss_out[0] = mean over rows with label != -100 of
+ * (1-s)*(lse - z_label) + s*(lse - mean_c z_c)  (F.cross_entropy(ignore_index=-100, label_smoothing=s)). */
+int vc_ce_combine(const float* ce_stats, int n_slots, const float* ce_zy, const int64_t* labels, const float* n_valid,
+                  float smoothing, int V, float* lse_out, float* loss_out, int M, void* stream);
 /* ---- helpers: column sums (bias gradients), strided fp32->bf16 cast, row-block copy into the [video;text] memory. */
 int vc_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream);
 int vc_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int M, int N, float scale, void* stream);

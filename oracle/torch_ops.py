@@ -15,7 +15,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_RELU_BWD, ACT_GELU_BWD = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_RELU_BWD, ACT_GELU_BWD, ACT_CE_STATS, ACT_CE_GRAD = 0, 1, 2, 3, 4, 5, 6
 _MASKED = -3.0e38
 
 
@@ -84,10 +84,25 @@ class TorchOps:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, pre_out=None,
-             aux=None, alpha=1.0, alpha_dev=None, splits=1, atomic=False, tile_n=0, drop=NO_DROP):
+             aux=None, alpha=1.0, alpha_dev=None, splits=1, atomic=False, tile_n=0, drop=NO_DROP, ce=None):
         a = A.float().t() if a_mn else A.float()
         b = B.float() if b_mn else B.float().t()
         acc = (a @ b) * alpha
+        if act == ACT_CE_STATS:      # fused LM head + CE, statistics pass: per-row (max, sum exp, sum z) in slot 0
+            st, lab = ce["stats"], ce["labels"].reshape(-1)
+            st.zero_()
+            st[:, :, 0] = float("-inf")
+            m = acc.max(-1).values
+            st[:, 0, 0], st[:, 0, 1], st[:, 0, 2] = m, torch.exp(acc - m[:, None]).sum(-1), acc.sum(-1)
+            ce["zy"].copy_(acc.gather(1, lab.clamp(min=0)[:, None]).squeeze(1))
+            return None
+        if act == ACT_CE_GRAD:
+            lab = ce["labels"].reshape(-1)
+            g = torch.exp(acc - ce["lse"][:, None]) - ce["smoothing"] / acc.shape[1]
+            g[torch.arange(acc.shape[0], device=g.device), lab.clamp(min=0)] -= (1 - ce["smoothing"])
+            g = g * (lab != -100)[:, None] / ce["n_valid"].reshape(())
+            out.copy_(g.to(out.dtype))
+            return out
         if alpha_dev is not None:
             acc = acc * alpha_dev.float()
         if bias is not None:
@@ -304,6 +319,17 @@ class TorchOps:
             g[torch.arange(n, device=g.device), lab.clamp(min=0)] -= (1 - smoothing)
             g = g * valid[:, None] / nv
             dlogits.copy_(g.to(dlogits.dtype))
+
+    def ce_combine(self, stats, zy, labels, n_valid, smoothing, V, lse_out, loss_out):
+        m = stats[:, :, 0].max(-1).values
+        s = (stats[:, :, 1] * torch.exp(stats[:, :, 0] - m[:, None])).sum(-1)
+        t = stats[:, :, 2].sum(-1)
+        lse = m + torch.log(s)
+        lse_out.copy_(lse)
+        lab = labels.reshape(-1)
+        row = (1 - smoothing) * (lse - zy) + smoothing * (lse - t / V)
+        loss_out.fill_(0.0)
+        loss_out.add_((row * (lab != -100)).sum() / n_valid.reshape(()))
 
     def colsum_bf16(self, x, out):
         out.add_(x.float().sum(0))

@@ -12,10 +12,13 @@ is present, and tests/golden/*.pt hold vectors minted from the real reference
 by oracle/make_golden.py, against which this file is checked everywhere.
 The reference itself ships no tests/golden vectors for this path,
 so parity is pinned to the reference's own outputs, not to reference tests.
-EXCEPTION — PARITY UNPINNED: beam_search_decode() restates transformers==4.28.0's
-beam search (third-party, absent from /root/reference, not installable offline);
-only its num_beams=1 == greedy property and the greedy loop itself (checked
-against the reference's cached decoder) are pinned.
+beam_search_decode() restates transformers==4.28.0's beam search (third-party,
+absent from /root/reference, 4.28 itself not installable offline).  It is pinned
+to the nearest real implementation that runs here: stock HuggingFace `generate`
+of transformers 5.5 on a small trained T5 decoder (oracle/make_golden_beam.py ->
+tests/golden/beam_hf.pt, tests/test_oracle_cpu.py) — exact on every case at the
+reference's settings, with the two 4.28->5.5 differences found stated in that test
+(fill value after eos; still-running beams when max_length is reached).
 
 Each function cites the reference lines it restates (paths under /root/reference).
 
@@ -424,7 +427,7 @@ def greedy_decode_cached(sd, cfg, memory, mem_mask, max_new_tokens=256, emulate_
 # --------------------------------------------------------------------------------------
 # Beam search (vid2seq.py:150-162 with num_beams>1 -> transformers==4.28.0 GenerationMixin.beam_search +
 # BeamSearchScorer; third-party code that is NOT under /root/reference and not installable here, so this restates the
-# published algorithm: PARITY UNPINNED for this function — no reference test or golden vector exercises it).
+# published 4.28 algorithm; pinned against stock HF generate of transformers 5.5, tests/golden/beam_hf.pt).
 # --------------------------------------------------------------------------------------
 class _BeamHyps:
     """One batch item's n-best list (transformers 4.28 BeamHypotheses, early_stopping=False)."""

@@ -192,6 +192,36 @@ def test_attn_bwd(cuda_ops, torch_ops, case):
             assert rel(f, f_r) < 1.5e-2, rel(f, f_r)
 
 
+@pytest.mark.parametrize("M,V,K,tn", [(4096, 32200, 768, 256), (300, 1012, 768, 128), (130, 1100, 256, 256)])
+def test_fused_lm_head_cross_entropy(cuda_ops, M, V, K, tn):
+    """LM head fused with F.cross_entropy(ignore_index=-100, label_smoothing=0.1) (modeling_t5.py:1714-1721): statistics
+    GEMM (act 5) + vc_ce_combine + gradient GEMM (act 6) vs torch on the materialised logits; ragged vocabularies."""
+    import torch.nn.functional as F
+    g = gen(M + V)
+    seq = (torch.randn(M, K, generator=g) * 0.4).to(DEV).bfloat16()
+    W = (torch.randn(V, K, generator=g) * 0.4).to(DEV).bfloat16()
+    labels = torch.randint(0, V, (M,), generator=g)
+    labels[torch.rand(M, generator=g) < 0.2] = -100
+    labels[0], labels[1] = V - 1, 0
+    labels = labels.to(DEV)
+    n_valid = (labels != -100).sum().float().reshape(1)
+    stats = torch.empty(M, 2 * ((V + tn - 1) // tn), 3, device=DEV)
+    zy, lse, loss = torch.empty(M, device=DEV), torch.empty(M, device=DEV), torch.empty(1, device=DEV)
+    Vp = (V + 7) // 8 * 8
+    dlogits = torch.zeros(M, Vp, device=DEV, dtype=torch.bfloat16)[:, :V]
+    ce = dict(labels=labels, n_valid=n_valid, smoothing=0.1, stats=stats, zy=zy, lse=lse)
+    cuda_ops.gemm(seq, W, None, act=5, tile_n=tn, ce=ce)
+    cuda_ops.ce_combine(stats, zy, labels, n_valid, 0.1, V, lse, loss)
+    cuda_ops.gemm(seq, W, dlogits, act=6, tile_n=tn, ce=ce)
+    z = (seq.float() @ W.float().t()).requires_grad_(True)
+    ref = F.cross_entropy(z, labels, ignore_index=-100, label_smoothing=0.1)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 2e-5 * abs(ref.item()), (loss.item(), ref.item())
+    assert (lse - torch.logsumexp(z.detach(), -1)).abs().max().item() < 2e-4
+    assert rel(dlogits, z.grad) < BF16_TOL, rel(dlogits, z.grad)
+    assert float(dlogits[labels == -100].abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize("drop", [(0, 0), (0xBEEF, 6554)], ids=["nodrop", "drop0.1"])
 def test_attn_skip_padded_query_tiles(cuda_ops, torch_ops, drop):
     """q_like_k (text-encoder self-attention): 128-query tiles past a sequence's last token are skipped.  Rows of real

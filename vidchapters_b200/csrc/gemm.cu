@@ -163,6 +163,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+      if (p.act == ACT_CE_STATS) {
+        // fused cross entropy, statistics pass: nothing is stored; this warp's half of the tile's columns is folded into
+        // (max, sum exp, sum z) of its rows and written to the row's slot of this (column block, half)
+        float cm = -INFINITY, cs = 0.f, ct = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          const int cc = half * kChunks + c;
+          ce_stats_chunk(p, tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16), row, row_ok, n0 + cc * 32, alpha, cm, cs, ct);
+        }
+        if (row_ok) {
+          float* dst = p.ce_stats + ((long long)row * p.ce_slots + (n0 / BN) * 2 + half) * 3;
+          dst[0] = cm; dst[1] = cs; dst[2] = ct;
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int cc = half * kChunks + c;  // chunk index inside the tile
@@ -240,9 +254,18 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   VC_CHECK(a->lda % 8 == 0 && a->ldb % 8 == 0, "vc_gemm_bf16: lda/ldb must be multiples of 8 elements (16 B)");
   VC_CHECK(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->B & 15) == 0 && ((uintptr_t)a->out & 15) == 0,
            "vc_gemm_bf16: A/B/out must be 16-byte aligned");
+  VC_CHECK(a->out || a->act == 5, "vc_gemm_bf16: null out");
   VC_CHECK(a->ldo % (a->out_fp32 ? 4 : 8) == 0, "vc_gemm_bf16: ldo alignment");
   VC_CHECK(!a->atomic || a->out_fp32, "vc_gemm_bf16: atomic accumulate needs fp32 out");
-  VC_CHECK(a->act >= 0 && a->act <= 4, "vc_gemm_bf16: bad act %d", a->act);
+  VC_CHECK(a->act >= 0 && a->act <= 6, "vc_gemm_bf16: bad act %d", a->act);
+  if (a->act == ACT_CE_STATS || a->act == ACT_CE_GRAD) {
+    VC_CHECK(a->ce_labels && a->ce_nvalid, "vc_gemm_bf16: fused cross entropy needs ce_labels / ce_nvalid");
+    VC_CHECK(!a->bias && !a->residual && a->drop_p16 == 0 && (a->splits <= 1) && !a->atomic && !a->a_mn_major,
+             "vc_gemm_bf16: fused cross entropy is a plain alpha*A.B^T epilogue");
+    if (a->act == ACT_CE_STATS) VC_CHECK(a->ce_stats && a->ce_zy && (a->tile_n == 128 || a->tile_n == 256),
+                                         "vc_gemm_bf16: act 5 needs ce_stats, ce_zy and an explicit tile_n (128/256)");
+    else VC_CHECK(a->ce_lse && !a->out_fp32 && a->out, "vc_gemm_bf16: act 6 needs ce_lse and a bf16 out");
+  }
   VC_CHECK((a->act != 3 && a->act != 4) || a->aux, "vc_gemm_bf16: act %d needs aux", a->act);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
@@ -275,7 +298,10 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   p.alpha = a->alpha;
   p.alpha_dev = a->alpha_dev;
   p.drop_seed = a->drop_seed; p.drop_p16 = a->drop_p16; p.drop_salt = drop_salt_ptr();
-  p.tma_epi = tma_epi_mode() && (a->ldr % 4 == 0);
+  p.ce_labels = reinterpret_cast<const long long*>(a->ce_labels); p.ce_stats = a->ce_stats; p.ce_zy = a->ce_zy;
+  p.ce_lse = a->ce_lse; p.ce_nvalid = a->ce_nvalid; p.ce_smoothing = a->ce_smoothing;
+  p.ce_slots = 2 * p.n_blocks;
+  p.tma_epi = tma_epi_mode() && (a->ldr % 4 == 0) && a->act != ACT_CE_STATS;
   p.aux_tma = p.tma_epi && epi_aux_by_tma(a);
   EpiMaps em;
   if (p.tma_epi) {
@@ -300,6 +326,7 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
     if (BN2) {
       GemmParams p2 = p;
       p2.n_blocks = (a->N + BN2 - 1) / BN2;
+      p2.ce_slots = 2 * p2.n_blocks;
       return launch_gemm_pair(a, BN2, em, p2, st);
     }
   }

@@ -210,6 +210,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+      if (p.act == ACT_CE_STATS) {
+        // fused cross entropy, statistics pass: nothing is stored; this warp's half of the tile's columns is folded into
+        // (max, sum exp, sum z) of its rows and written to the row's slot of this (column block, half)
+        float cm = -INFINITY, cs = 0.f, ct = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          const int cc = half * kChunks + c;
+          ce_stats_chunk(p, tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16), row, row_ok, n0 + cc * 32, alpha, cm, cs, ct);
+        }
+        if (row_ok) {
+          float* dst = p.ce_stats + ((long long)row * p.ce_slots + (n0 / BN) * 2 + half) * 3;
+          dst[0] = cm; dst[1] = cs; dst[2] = ct;
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int cc = half * kChunks + c;

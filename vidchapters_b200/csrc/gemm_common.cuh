@@ -32,7 +32,82 @@ struct GemmParams {
   const uint32_t* drop_salt;     // optional device salt XORed into drop_seed
   int tma_epi;                   // 1: epilogue I/O staged through shared memory and moved by TMA (see below)
   int aux_tma;                   // 1: the activation-backward operand `aux` arrives by TMA too (EpiMaps::resid maps it)
+  // fused LM head + label-smoothed cross entropy (act 5: per-row partial statistics, act 6: d loss / d logits)
+  const long long* ce_labels;
+  float* ce_stats;               // [M][ce_slots][3]
+  float* ce_zy;                  // [M]
+  const float* ce_lse;           // [M]
+  const float* ce_nvalid;        // device scalar
+  float ce_smoothing;
+  int ce_slots;                  // 2 * n_blocks
 };
+
+constexpr int ACT_CE_STATS = 5, ACT_CE_GRAD = 6;
+
+// act 5: one 32-column chunk of one row folded into the running (max, sum exp, sum z) of the thread's row.
+__device__ __forceinline__ void ce_stats_chunk(const GemmParams& p, uint32_t taddr, int row, bool row_ok, int col0, float alpha,
+                                               float& m, float& s, float& t) {
+  float v[32];
+  tmem_ld32(taddr, v);
+  const long long y = row_ok ? p.ce_labels[row] : -1;
+  tmem_ld_wait();
+  const int ncols = min(32, p.N - col0);
+  if (!row_ok || ncols <= 0) return;
+  constexpr float kL2e = 1.4426950408889634f;
+  float cm = -INFINITY, cs = 0.f, ct = 0.f;
+  if (ncols == 32) {          // whole chunk in range (all but the last column block of a ragged vocabulary)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { v[j] *= alpha; cm = fmaxf(cm, v[j]); }
+    const float m_new = fmaxf(m, cm);
+    const float neg = -m_new * kL2e;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { cs += fast_exp2(fmaf(v[j], kL2e, neg)); ct += v[j]; }
+    s = s * fast_exp2((m - m_new) * kL2e) + cs;     // first chunk: m = -inf -> factor 0
+    m = m_new;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] *= alpha;
+      if (j < ncols) cm = fmaxf(cm, v[j]);
+    }
+    const float m_new = fmaxf(m, cm);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) { cs += __expf(v[j] - m_new); ct += v[j]; }
+    }
+    s = s * __expf(m - m_new) + cs;
+    m = m_new;
+  }
+  t += ct;
+  if (y >= col0 && y < col0 + ncols) {
+    float zy = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) zy = (col0 + j == y) ? v[j] : zy;
+    p.ce_zy[row] = zy;
+  }
+}
+
+// act 6: logits chunk -> d loss / d logits (in place)
+__device__ __forceinline__ void ce_grad_chunk(const GemmParams& p, float* v, int row, bool row_ok, int col0) {
+  const long long y = row_ok ? p.ce_labels[row] : -100;
+  const float lse = row_ok ? p.ce_lse[row] : 0.f;
+  const float inv_nv = 1.0f / __ldg(p.ce_nvalid);
+  const float sm = p.ce_smoothing / (float)p.N;
+  if (y < 0) {   // ignore_index
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    return;
+  }
+  constexpr float kL2e = 1.4426950408889634f;
+  const float neg = -lse * kL2e, off = -sm * inv_nv;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = fmaf(fast_exp2(fmaf(v[j], kL2e, neg)), inv_nv, off);
+  if (y >= col0 && y < col0 + 32) {      // the one label column of this row, if it falls into this chunk
+    const float hot = (1.0f - p.ce_smoothing) * inv_nv;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (col0 + j == y) ? v[j] - hot : v[j];
+  }
+}
 
 // Tensor maps of the epilogue's global operands (32 x 32 boxes; fp32: SWIZZLE_128B, bf16: SWIZZLE_64B).
 struct EpiMaps {
@@ -66,7 +141,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
   #pragma unroll
               for (int j = 0; j < 8; ++j) rs[j] = rp[j];
             }
-            if (p.act >= 3) {
+            if (p.act == 3 || p.act == 4) {
               const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ld_aux + col0);
   #pragma unroll
               for (int j = 0; j < 4; ++j) ax[j] = __ldg(ap + j);
@@ -108,6 +183,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
           } else if (p.act == 2) {
   #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == ACT_CE_GRAD) {
+            ce_grad_chunk(p, v, row, row_ok, col0);
           } else if (p.act >= 3) {
             if (!full) {  // ragged tail: gather the aux values element-wise
               const __nv_bfloat16* axp = p.aux + (long long)row * p.ld_aux + col0;
@@ -217,7 +294,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
   }
   __syncwarp();
   uint4 ax[4];
-  if (p.act >= 3 && !p.aux_tma) {
+  if ((p.act == 3 || p.act == 4) && !p.aux_tma) {
     if (full) {
       const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ld_aux + col0);
 #pragma unroll
@@ -276,6 +353,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
   } else if (p.act == 2) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == ACT_CE_GRAD) {
+    ce_grad_chunk(p, v, row, in_rows, col0);
   } else if (p.act >= 3) {
     if (p.aux_tma) {
       mbar_wait(wbar, wphase);
@@ -335,7 +414,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
 
 // act-backward GEMMs (no residual): the `resid` map slot carries the bf16 `aux` matrix instead.
 inline bool epi_aux_by_tma(const vc_gemm_args* a) {
-  return a->act >= 3 && a->aux && !a->residual && !(a->act == 2 && a->pre_out) && a->ld_aux % 8 == 0 &&
+  return (a->act == 3 || a->act == 4) && a->aux && !a->residual && !(a->act == 2 && a->pre_out) && a->ld_aux % 8 == 0 &&
          ((uintptr_t)a->aux & 15) == 0;
 }
 

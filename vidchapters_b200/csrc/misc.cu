@@ -247,6 +247,41 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const long 
   }
 }
 
+// ---- fused LM head + cross entropy: combine the per-(row, column half block) partials of the act-5 GEMM
+//      (max, sum exp(z - max), sum z) into lse[row] and the label-smoothed loss (modeling_t5.py:1721).
+__global__ void __launch_bounds__(256) ce_combine_kernel(const float* __restrict__ stats, int n_slots, const float* __restrict__ zy,
+                                                        const long long* __restrict__ labels, const float* __restrict__ n_valid_p,
+                                                        float eps, int V, float* __restrict__ lse_out, float* __restrict__ loss_out,
+                                                        int M) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* st = stats + (long long)row * n_slots * 3;
+  float m = -INFINITY;
+  for (int i = lane; i < n_slots; i += 32) m = fmaxf(m, st[i * 3]);
+  m = warp_max_f(m);
+  float s = 0.f, t = 0.f;
+  for (int i = lane; i < n_slots; i += 32) {
+    const float mi = st[i * 3];
+    if (mi != -INFINITY) s += st[i * 3 + 1] * __expf(mi - m);
+    t += st[i * 3 + 2];
+  }
+  s = warp_sum_f(s);
+  t = warp_sum_f(t);
+  if (lane == 0) {
+    const float lse = m + logf(s);
+    lse_out[row] = lse;
+    const long long y = labels[row];
+    if (y >= 0) {
+      const float nll = y < V ? lse - zy[row] : NAN;   // label >= V: caller bug, poison the loss (see cross_entropy_kernel)
+      const float smooth = lse - t / (float)V;
+      atomicAdd(loss_out, ((1.0f - eps) * nll + eps * smooth) / *n_valid_p);
+    }
+  }
+}
+
 // ---- column sums of a bf16 matrix (bias gradients of the ViT Linears): out[n] += sum_m x[m][n]
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
                                                          float* __restrict__ out, int M, int N, int rows_per_block) {
@@ -357,6 +392,15 @@ extern "C" int vc_cross_entropy(const float* logits, int64_t ld, const int64_t* 
   VC_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ST(stream)));
   VC_CUDA(launch_kernel(cross_entropy_kernel, dim3(n), dim3(256), 0, ST(stream), logits, ld, (const long long*)labels, n_valid, smoothing, loss_out,
                                                   (__nv_bfloat16*)dlogits_bf16, ldd, V));
+  VC_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+extern "C" int vc_ce_combine(const float* ce_stats, int n_slots, const float* ce_zy, const int64_t* labels, const float* n_valid,
+                             float smoothing, int V, float* lse_out, float* loss_out, int M, void* stream) {
+  VC_CHECK(M > 0 && n_slots > 0 && ce_stats && ce_zy && labels && n_valid && lse_out && loss_out, "vc_ce_combine: bad arguments");
+  VC_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), ST(stream)));
+  VC_CUDA(launch_kernel(ce_combine_kernel, dim3((M + 7) / 8), dim3(256), 0, ST(stream), ce_stats, n_slots, ce_zy,
+                        (const long long*)labels, n_valid, smoothing, V, lse_out, loss_out, M));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -27,7 +27,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .config import layout_order, param_shapes, vocab_size
-from .ops import ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD, NO_DROP, drop_spec
+from .ops import ACT_CE_GRAD, ACT_CE_STATS, ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD, NO_DROP, drop_spec
 
 _ALIGN = 64  # elements; keeps every parameter 256 B (fp32) / 128 B (bf16) aligned for TMA
 
@@ -182,6 +182,7 @@ class Vid2SeqEngine:
         # the fork/join become graph dependencies.  -3.7 % step time (profiles/README.md); VIDCHAP_DUAL_STREAM=0 disables.
         import os
         self.dual_stream = os.environ.get("VIDCHAP_DUAL_STREAM", "1") != "0" and self.device.type == "cuda"
+        self.fused_ce = os.environ.get("VIDCHAP_FUSED_CE", "1") != "0"
         self._side_stream = None
         self._build_specs()
 
@@ -606,11 +607,27 @@ class Vid2SeqEngine:
                      out_scale=d ** -0.5, drop=d_fin_d)
         ctx.update(d_emb_d=d_emb_d, d_fin_d=d_fin_d)
         Vp = (self.V + 7) // 8 * 8   # leading dimension padded to 16 B (vc.py's vocab 32100 is not a multiple of 8)
-        logits = self._e(B * S, Vp)[:, :self.V]
-        ops.gemm(seq, self.pb("t5_model.shared.weight"), logits)
         loss = self._e(1)
         dlogits = self._e(B * S, Vp, dtype=bf)[:, :self.V]
-        ops.cross_entropy(logits, labels.view(-1), n_valid, self.label_smoothing, loss, dlogits)
+        W = self.pb("t5_model.shared.weight")
+        if want_logits or not self.fused_ce:
+            # debug path / VIDCHAP_FUSED_CE=0: materialise the fp32 logits, then the stand-alone CE kernel
+            logits = self._e(B * S, Vp)[:, :self.V]
+            ops.gemm(seq, W, logits)
+            ops.cross_entropy(logits, labels.view(-1), n_valid, self.label_smoothing, loss, dlogits)
+        else:
+            # LM head fused with the label-smoothed cross entropy (modeling_t5.py:1714-1721): the (B*S, V) fp32 logits
+            # never exist.  GEMM 1 keeps only per-row partial (max, sum exp, sum z) per column block; a tiny kernel turns
+            # them into lse + loss; GEMM 2 recomputes the logits tile by tile and writes d loss / d logits (bf16), the
+            # operand of the two backward GEMMs, straight from its epilogue.
+            logits = None
+            tn = 256
+            stats = self._e(B * S, 2 * ((self.V + tn - 1) // tn), 3)
+            zy, lse = self._e(B * S), self._e(B * S)
+            ce = dict(labels=labels.view(-1), n_valid=n_valid, smoothing=self.label_smoothing, stats=stats, zy=zy, lse=lse)
+            ops.gemm(seq, W, None, act=ACT_CE_STATS, tile_n=tn, ce=ce)
+            ops.ce_combine(stats, zy, labels.view(-1), n_valid, self.label_smoothing, self.V, lse, loss)
+            ops.gemm(seq, W, dlogits, act=ACT_CE_GRAD, tile_n=tn, ce=ce)
         ctx.update(memory=memory, mem_mask=mem_mask, dec_in=dec_in, dec_x=y, dec_rstd=rstd_d, seq=seq, dlogits=dlogits,
                    lut_d=lut_d, vid_f32=vid_f32)
         if want_logits:

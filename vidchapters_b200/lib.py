@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvidchap.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class GemmArgs(C.Structure):
@@ -30,6 +30,8 @@ class GemmArgs(C.Structure):
         ("splits", C.c_int32),
         ("tile_n", C.c_int32),
         ("drop_seed", C.c_uint32), ("drop_p16", C.c_uint32),
+        ("ce_labels", C.c_void_p), ("ce_stats", C.c_void_p), ("ce_zy", C.c_void_p), ("ce_lse", C.c_void_p),
+        ("ce_nvalid", C.c_void_p), ("ce_smoothing", C.c_float),
     ]
 
 
@@ -80,6 +82,7 @@ SIGNATURES = {
     "vc_add_pos": [P, P, P, I, I, I, I, U, U, P],
     "vc_add_pos_bwd": [P, P, I, I, I, I, U, U, P],
     "vc_cross_entropy": [P, I64, P, P, F, P, P, I64, I, I, P],
+    "vc_ce_combine": [P, I, P, P, P, F, I, P, P, I, P],
     "vc_colsum_bf16": [P, I64, P, I, I, P],
     "vc_cast_f32_bf16": [P, I64, P, I64, I, I, F, P],
     "vc_copy_rows_bf16": [P, P, I, I, I, I, I, P],

@@ -12,7 +12,7 @@ import torch
 
 from . import lib as _lib
 
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_RELU_BWD, ACT_GELU_BWD = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_RELU_BWD, ACT_GELU_BWD, ACT_CE_STATS, ACT_CE_GRAD = 0, 1, 2, 3, 4, 5, 6
 NO_DROP = (0, 0)   # (seed, p16): dropout spec; p16 = round(p * 65536), 0 = off
 
 
@@ -58,24 +58,42 @@ class CudaOps:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, A, B, out, *, a_mn=False, b_mn=False, bias=None, residual=None, act=ACT_NONE, pre_out=None,
-             aux=None, alpha=1.0, alpha_dev=None, splits=1, atomic=False, tile_n=0, drop=NO_DROP):
-        """out[M,N] = epi(alpha * op(A) @ op(B)^T).  A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn)."""
+             aux=None, alpha=1.0, alpha_dev=None, splits=1, atomic=False, tile_n=0, drop=NO_DROP, ce=None):
+        """out[M,N] = epi(alpha * op(A) @ op(B)^T).  A: [M,K] (or [K,M] if a_mn); B: [N,K] (or [K,N] if b_mn).
+        ce: dict(labels, n_valid, smoothing, stats, zy | lse) for the fused LM-head + cross-entropy epilogues (act 5 / 6;
+        act 5 stores nothing: out=None)."""
         _chk_cuda(A, B, out, bias, residual, pre_out, aux)
         assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
-        assert A.dim() == 2 and B.dim() == 2 and out.dim() == 2
-        assert A.stride(1) == 1 and B.stride(1) == 1 and out.stride(1) == 1
+        assert A.dim() == 2 and B.dim() == 2 and (out is None or out.dim() == 2)
+        assert A.stride(1) == 1 and B.stride(1) == 1 and (out is None or out.stride(1) == 1)
         M, K = (A.shape[1], A.shape[0]) if a_mn else (A.shape[0], A.shape[1])
         N, Kb = (B.shape[1], B.shape[0]) if b_mn else (B.shape[0], B.shape[1])
         assert K == Kb, (A.shape, B.shape, a_mn, b_mn)
-        assert out.shape[0] == M and out.shape[1] == N, (out.shape, M, N)
         a = _lib.GemmArgs()
         a.A, a.B = A.data_ptr(), B.data_ptr()
         a.lda, a.ldb = A.stride(0), B.stride(0)
         a.M, a.N, a.K = M, N, K
         a.a_mn_major, a.b_mn_major = int(a_mn), int(b_mn)
-        a.out, a.ldo = out.data_ptr(), out.stride(0)
-        a.out_fp32 = int(out.dtype == torch.float32)
-        assert out.dtype in (torch.float32, torch.bfloat16)
+        if ce is not None:
+            assert act in (ACT_CE_STATS, ACT_CE_GRAD)
+            _chk_cuda(ce["labels"], ce["n_valid"], ce.get("stats"), ce.get("zy"), ce.get("lse"))
+            assert ce["labels"].dtype == torch.int64 and ce["labels"].numel() == M
+            a.ce_labels, a.ce_nvalid, a.ce_smoothing = ce["labels"].data_ptr(), ce["n_valid"].data_ptr(), float(ce["smoothing"])
+            if act == ACT_CE_STATS:
+                st = ce["stats"]
+                assert tile_n in (128, 256) and st.is_contiguous() and st.dtype == torch.float32
+                assert st.shape == (M, 2 * ((N + tile_n - 1) // tile_n), 3) and ce["zy"].numel() == M
+                a.ce_stats, a.ce_zy = st.data_ptr(), ce["zy"].data_ptr()
+            else:
+                a.ce_lse = ce["lse"].data_ptr()
+        if out is None:
+            assert act == ACT_CE_STATS
+            a.out, a.ldo, a.out_fp32 = None, (N + 7) // 8 * 8, 0
+        else:
+            assert out.shape[0] == M and out.shape[1] == N, (out.shape, M, N)
+            a.out, a.ldo = out.data_ptr(), out.stride(0)
+            a.out_fp32 = int(out.dtype == torch.float32)
+            assert out.dtype in (torch.float32, torch.bfloat16)
         a.atomic = int(atomic)
         a.bias = None if bias is None else bias.data_ptr()
         if residual is not None:
@@ -234,6 +252,14 @@ class CudaOps:
         _lib.check(self.lib.vc_cross_entropy(_ptr(logits), logits.stride(0), _ptr(labels), _ptr(n_valid), smoothing,
                                              _ptr(loss_out), _ptr(dlogits), 0 if dlogits is None else dlogits.stride(0),
                                              n, V, self._stream()))
+        self.launches += 1
+
+    def ce_combine(self, stats, zy, labels, n_valid, smoothing, V, lse_out, loss_out):
+        """Partials of the act-5 LM-head GEMM -> lse [M] and the label-smoothed mean loss (modeling_t5.py:1721)."""
+        _chk_cuda(stats, zy, labels, n_valid, lse_out, loss_out)
+        M, n_slots, _ = stats.shape
+        _lib.check(self.lib.vc_ce_combine(_ptr(stats), n_slots, _ptr(zy), _ptr(labels), _ptr(n_valid), smoothing, V,
+                                          _ptr(lse_out), _ptr(loss_out), M, self._stream()))
         self.launches += 1
 
     def colsum_bf16(self, x, out):
