@@ -346,9 +346,37 @@ def clip_adam_renorm_(params: Dict[str, torch.Tensor], grads: Dict[str, torch.Te
     return total
 
 
-def greedy_decode(sd, cfg, memory, mem_mask, max_new_tokens=256, emulate_bf16=False):
+def process_scores(scores, ids, repetition_penalty=1.0, min_length=1, eos_id=1):
+    """The two HF logits processors `Vid2Seq.generate` can switch on (vid2seq.py:150-162 -> transformers 4.28
+    RepetitionPenaltyLogitsProcessor, MinLengthLogitsProcessor): tokens already in `ids` (start token included) get
+    score*p if negative else score/p; eos is forbidden while len(ids) < min_length.  `scores` are raw logits in greedy /
+    sampling and log-probabilities in beam search, as in HF."""
+    if repetition_penalty != 1.0:
+        sc = scores.gather(1, ids)
+        sc = torch.where(sc < 0, sc * repetition_penalty, sc / repetition_penalty)
+        scores = scores.scatter(1, ids, sc)
+    if ids.shape[1] < min_length:
+        scores = scores.clone()
+        scores[:, eos_id] = -float("inf")
+    return scores
+
+
+def top_p_filter(scores, top_p, temperature=1.0):
+    """HF TemperatureLogitsWarper + TopPLogitsWarper (min_tokens_to_keep=1): the smallest set of tokens whose probability
+    mass reaches top_p keeps its logits, everything else becomes -inf."""
+    scores = scores / temperature
+    srt, idx = torch.sort(scores, descending=False, dim=-1)
+    cum = srt.softmax(-1).cumsum(-1)
+    remove = cum <= (1 - top_p)
+    remove[..., -1:] = False
+    return scores.masked_fill(remove.scatter(1, idx, remove), -float("inf"))
+
+
+def greedy_decode(sd, cfg, memory, mem_mask, max_new_tokens=256, emulate_bf16=False, repetition_penalty=1.0, min_length=1,
+                  sample=None):
     """Greedy restatement of vid2seq.py:150-162 with num_beams=1 (HF-4.28 generate semantics):
-    start id 0, argmax, per-sequence stop at eos=1 then emit pad 0, stop when all done.  Uncached (O(S^2))."""
+    start id 0, argmax, per-sequence stop at eos=1 then emit pad 0, stop when all done.  Uncached (O(S^2)).
+    sample=(top_p, temperature, generator): nucleus sampling (do_sample=True) instead of the argmax."""
     ar = Arith(emulate_bf16)
     B = memory.shape[0]
     ids = torch.zeros(B, 1, dtype=torch.long, device=memory.device)
@@ -357,7 +385,12 @@ def greedy_decode(sd, cfg, memory, mem_mask, max_new_tokens=256, emulate_bf16=Fa
     for _ in range(max_new_tokens):
         mask = torch.ones_like(ids, dtype=torch.bool)
         seq = t5_decoder(sd, cfg, ids, mask, memory, mem_mask, ar)[:, -1:] * (d ** -0.5)
-        nxt = ar.linear(seq, sd["t5_model.shared.weight"])[:, 0].argmax(-1)
+        scores = process_scores(ar.linear(seq, sd["t5_model.shared.weight"])[:, 0].float(), ids, repetition_penalty, min_length)
+        if sample is None:
+            nxt = scores.argmax(-1)
+        else:
+            probs = top_p_filter(scores, sample[0], sample[1]).softmax(-1)
+            nxt = torch.multinomial(probs, 1, generator=sample[2]).squeeze(1)
         nxt = torch.where(done, torch.zeros_like(nxt), nxt)
         ids = torch.cat([ids, nxt[:, None]], 1)
         done = done | (nxt == 1)
@@ -453,7 +486,7 @@ class _BeamHyps:
 
 
 def beam_search_decode(sd, cfg, memory, mem_mask, num_beams=4, max_new_tokens=256, length_penalty=1.0,
-                       emulate_bf16=False, eos_id=1, pad_id=0):
+                       emulate_bf16=False, eos_id=1, pad_id=0, repetition_penalty=1.0, min_length=1, num_return=1):
     """HF-4.28 beam search as called by Vid2Seq.generate: decoder_start 0, log_softmax scores, top 2*num_beams per
     batch item, eos candidates ranked below num_beams are dropped, finished hypotheses scored by
     sum_logprobs / len**length_penalty, early_stopping=False heuristic, max_new_tokens stop, best hypothesis + eos.
@@ -474,7 +507,8 @@ def beam_search_decode(sd, cfg, memory, mem_mask, num_beams=4, max_new_tokens=25
         mask = torch.ones_like(ids, dtype=torch.bool)
         seq = t5_decoder(sd, cfg, ids, mask, mem, mm, ar)[:, -1:] * (d ** -0.5)
         logits = ar.linear(seq, sd["t5_model.shared.weight"])[:, 0].float()
-        scores = torch.log_softmax(logits, dim=-1).cpu() + beam_scores[:, None]
+        scores = process_scores(torch.log_softmax(logits, dim=-1), ids, repetition_penalty, min_length, eos_id).cpu() \
+            + beam_scores[:, None]
         V = scores.shape[-1]
         top_s, top_i = torch.topk(scores.view(B, nb * V), 2 * nb, dim=1, largest=True, sorted=True)
         top_b, top_t = top_i // V, top_i % V
@@ -508,10 +542,11 @@ def beam_search_decode(sd, cfg, memory, mem_mask, num_beams=4, max_new_tokens=25
         if not done[b]:
             for j in range(nb):
                 hyps[b].add(ids[b * nb + j].clone().cpu(), float(beam_scores[b * nb + j]))
-        best = sorted(hyps[b].beams, key=lambda x: x[0])[-1][1]
-        out.append(best)
+        ranked = sorted(hyps[b].beams, key=lambda x: x[0])
+        for j in range(num_return):            # num_return_sequences: the n best hypotheses, best first
+            out.append(ranked[-1 - j][1])
     sent_max = min(max(len(h) for h in out) + 1, max_length)
-    dec = torch.full((B, sent_max), pad_id, dtype=torch.long)
+    dec = torch.full((B * num_return, sent_max), pad_id, dtype=torch.long)
     for b, h in enumerate(out):
         dec[b, :len(h)] = h
         if len(h) < sent_max:

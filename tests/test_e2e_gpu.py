@@ -461,3 +461,60 @@ def build_init(cfg, _cache={}):
     if key not in _cache:
         _cache[key] = {k: v.cuda() for k, v in init_state_dict(cfg, 0).items()}
     return _cache[key]
+
+
+def test_generate_options_cuda_match_oracle():
+    """Vid2Seq.generate's remaining kwargs on the CUDA path (vid2seq.py:100-167 -> HF generate): repetition_penalty and
+    min_length (greedy and beam search), num_captions (n best beams), nucleus sampling (top_p -> 0 must reproduce greedy;
+    a fixed torch seed reproduces itself; every sampled row is a valid sequence)."""
+    from oracle import vid2seq_oracle as O
+    from vidchapters_b200 import Vid2SeqAdam
+    fx = torch.load(os.path.join(GOLD, "tiny.pt"), weights_only=False)
+    cfg = fx["cfg"]
+    video, inp, out = fx["video"].cuda(), fx["input_ids"].cuda(), fx["output_ids"].cuda()
+    it = {"input_ids": inp, "attention_mask": inp != 0}
+    ot = {"input_ids": out, "attention_mask": out != 0}
+
+    class TokD(Tok):
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return [" ".join(str(int(t)) for t in row if not (skip_special_tokens and int(t) in (0, 1))) for row in ids]
+
+    m = build(cfg)
+    m.train()
+    opt = Vid2SeqAdam(m, lr=2e-3, clip_max_norm=1.0, world_size=1)
+    for _ in range(40):
+        ld, _ = m(video, it, ot); opt.zero_grad(); ld["loss"].backward(); opt.step()
+    m.eval()
+    m.t5_tokenizer = TokD(cfg["base_vocab"] + cfg["num_bins"])
+    sd = {k: v.detach().clone() for k, v in m._params.items()}
+    memory, mem_mask, B, E = m.engine.encode(video, inp, inp != 0)
+    mem32 = memory.float().view(B, E, -1)
+    for kw in (dict(repetition_penalty=2.0), dict(min_length=14), dict(repetition_penalty=1.3, min_length=10)):
+        m.generate(video, it, num_beams=1, max_length=16, **kw)
+        seq = m.last_generated_ids
+        ref = O.greedy_decode(sd, cfg, mem32, mem_mask.long(), max_new_tokens=16, emulate_bf16=True, **kw).to(seq.device)
+        n = min(seq.shape[1], ref.shape[1])
+        assert torch.equal(seq[:, :n], ref[:, :n]), (kw, seq, ref)
+        m.generate(video, it, num_beams=4, max_length=16, **kw)
+        seq = m.last_generated_ids
+        ref = O.beam_search_decode(sd, cfg, mem32, mem_mask.long(), num_beams=4, max_new_tokens=16, emulate_bf16=True, **kw).to(seq.device)
+        n = min(seq.shape[1], ref.shape[1])
+        assert torch.equal(seq[:, :n], ref[:, :n]), (kw, seq, ref)
+    texts = m.generate(video, it, num_beams=4, max_length=16, num_captions=3)
+    assert len(texts) == 3 * B
+    ref = O.beam_search_decode(sd, cfg, mem32, mem_mask.long(), num_beams=4, max_new_tokens=16, emulate_bf16=True, num_return=3)
+    seq = m.last_generated_ids
+    n = min(seq.shape[1], ref.shape[1])
+    assert torch.equal(seq[:, :n].cpu(), ref[:, :n])
+    m.generate(video, it, num_beams=1, max_length=16)
+    greedy = m.last_generated_ids.clone()
+    m.generate(video, it, use_nucleus_sampling=True, num_beams=0, top_p=1e-4, max_length=16)     # nucleus = the argmax only
+    n = min(greedy.shape[1], m.last_generated_ids.shape[1])
+    assert torch.equal(m.last_generated_ids[:, :n], greedy[:, :n])
+    torch.manual_seed(5)
+    t1 = m.generate(video, it, use_nucleus_sampling=True, num_beams=0, top_p=0.95, temperature=2.0, max_length=16, num_captions=2)
+    s1 = m.last_generated_ids.clone()
+    torch.manual_seed(5)
+    m.generate(video, it, use_nucleus_sampling=True, num_beams=0, top_p=0.95, temperature=2.0, max_length=16, num_captions=2)
+    assert len(t1) == 2 * B and torch.equal(s1, m.last_generated_ids)
+    assert bool((s1[:, 0] == 0).all()) and int(s1.max()) < cfg["base_vocab"] + cfg["num_bins"]

@@ -201,3 +201,38 @@ def test_beam_search_oracle_pinned_to_hf_generate():
         with torch.no_grad():
             ids = O.beam_search_decode(sd, cfg, mem, mask, num_beams=nb, max_new_tokens=12, length_penalty=lp)
         _same_or_known_difference(ids, ref, 12, ("live", nb, lp))
+
+
+def test_generate_options_oracle_pinned_to_hf_generate():
+    """repetition_penalty, min_length, num_return_sequences (vid2seq.py:150-162 kwargs) in the oracle's greedy and beam
+    search vs stock HF generate (transformers 5.5) on the small trained decoder; the nucleus filter vs HF's warpers."""
+    fx = torch.load(os.path.join(GOLD, "beam_hf.pt"), weights_only=False)
+    cfg, sd, mask = fx["cfg"], fx["sd"], fx["mask"]
+    try:
+        from oracle.make_golden_beam import hf_model
+        from transformers.modeling_outputs import BaseModelOutput
+        from transformers.generation.logits_process import TemperatureLogitsWarper, TopPLogitsWarper
+        hf = hf_model(cfg, sd)
+    except Exception:
+        pytest.skip("needs a transformers with stock T5 + generate")
+    mem = fx["memory"]["perturbed"]
+    enc = lambda: BaseModelOutput(last_hidden_state=mem)
+    with torch.no_grad():
+        for kw in (dict(repetition_penalty=1.7), dict(min_length=6), dict(repetition_penalty=1.3, min_length=4)):
+            ref = hf.generate(encoder_outputs=enc(), attention_mask=mask, num_beams=1, max_new_tokens=12, do_sample=False, **kw)
+            ids = O.greedy_decode(sd, cfg, mem, mask, max_new_tokens=12, **kw)
+            assert _until_eos(ids) == _until_eos(ref), (kw, ids.tolist(), ref.tolist())
+            ref = hf.generate(encoder_outputs=enc(), attention_mask=mask, num_beams=4, max_new_tokens=12, do_sample=False,
+                              early_stopping=False, length_penalty=1.0, **kw)
+            ids = O.beam_search_decode(sd, cfg, mem, mask, num_beams=4, max_new_tokens=12, **kw)
+            _same_or_known_difference(ids, ref, 12, ("opts", kw))
+        ref = hf.generate(encoder_outputs=enc(), attention_mask=mask, num_beams=4, max_new_tokens=12, do_sample=False,
+                          early_stopping=False, num_return_sequences=3)
+        ids = O.beam_search_decode(sd, cfg, mem, mask, num_beams=4, max_new_tokens=12, num_return=3)
+        assert ids.shape[0] == ref.shape[0] == 3 * mem.shape[0]
+        _same_or_known_difference(ids, ref, 12, "num_return_sequences")
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(5, 120, generator=g) * 3
+    ours = O.top_p_filter(z, 0.9, 0.7)
+    theirs = TopPLogitsWarper(top_p=0.9)(None, TemperatureLogitsWarper(0.7)(None, z))
+    assert torch.equal(torch.isinf(ours), torch.isinf(theirs)) and torch.allclose(ours[~torch.isinf(ours)], theirs[~torch.isinf(theirs)])

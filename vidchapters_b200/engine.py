@@ -929,7 +929,7 @@ class Vid2SeqEngine:
         ops.gemm(h, self.pb("t5_model.shared.weight"), logits)
         return logits
 
-    def _greedy_setup(self, memory, mem_mask, B, E, S, use_graph):
+    def _greedy_setup(self, memory, mem_mask, B, E, S, use_graph, select_on_device=True):
         """Cross-attention K/V of every layer (modeling_t5.py:516-524), self-attention caches, the decode state and ONE
         decode step captured as a CUDA graph (the step position is a device scalar, so the launch sequence is fixed)."""
         ops, H, inner = self.ops, self.H, self.inner
@@ -954,10 +954,13 @@ class Vid2SeqEngine:
                   done=torch.zeros(B, dtype=torch.uint8, device=dev), caches=caches, graph=None)
         buf = self._decode_buffers(B)
 
+        st["logits"] = buf["logits"]
+
         def step():
             logits = self._decode_step_logits(st["ids"], buf, caches, kvmem, mem_mask, bias_d, st["pos"], B, S, E)
-            ops.greedy_next(logits, st["done"], st["ids"], st["seq"], st["pos"], 1, 0)
-            ops.step_advance(st["pos"])
+            if select_on_device:      # argmax + eos/pad bookkeeping + position advance inside the captured step
+                ops.greedy_next(logits, st["done"], st["ids"], st["seq"], st["pos"], 1, 0)
+                ops.step_advance(st["pos"])
 
         def rewind():
             st["pos"].zero_(); st["ids"].zero_(); st["seq"].zero_(); st["done"].zero_()
@@ -979,7 +982,22 @@ class Vid2SeqEngine:
             rewind()
         return st
 
-    def generate_greedy(self, memory, mem_mask, B, E, max_new_tokens=256, use_graph=None, check_every=16):
+    @staticmethod
+    def process_scores(scores, seq, cur_len, repetition_penalty, min_length, eos_id=1):
+        """HF-4.28 RepetitionPenaltyLogitsProcessor + MinLengthLogitsProcessor on [n, V] scores given the token history
+        seq[:, :cur_len] (start token included) — the two processors `Vid2Seq.generate`'s kwargs can switch on."""
+        if repetition_penalty != 1.0:
+            hist = seq[:, :cur_len]
+            sc = scores.gather(1, hist)
+            sc = torch.where(sc < 0, sc * repetition_penalty, sc / repetition_penalty)
+            scores = scores.scatter(1, hist, sc)
+        if cur_len < min_length:
+            scores = scores.clone()
+            scores[:, eos_id] = -float("inf")
+        return scores
+
+    def generate_greedy(self, memory, mem_mask, B, E, max_new_tokens=256, use_graph=None, check_every=16,
+                        repetition_penalty=1.0, min_length=1, sample=None):
         """Greedy decoding with a KV cache (HF-4.28 greedy semantics: start id 0, argmax, sequences that emitted eos=1
         continue with pad=0, stop when all are done or after max_new_tokens).  Returns int64 [B, 1 + n] ids including
         the start token, like `t5_model.generate` (model/vid2seq.py:150-162 with num_beams=1).
@@ -987,6 +1005,8 @@ class Vid2SeqEngine:
         S = int(max_new_tokens)
         if use_graph is None:
             use_graph = self.device.type == "cuda" and getattr(self.ops, "name", "") == "cuda"
+        if repetition_penalty != 1.0 or min_length > 1 or sample is not None:
+            return self._generate_host_select(memory, mem_mask, B, E, S, use_graph, repetition_penalty, min_length, sample)
         st = self._greedy_setup(memory, mem_mask, B, E, S, use_graph)
         n = 0
         while n < S:
@@ -998,6 +1018,41 @@ class Vid2SeqEngine:
                 st["step"]()
             n += 1
         return st["seq"][:, :n + 1].clone()
+
+    def _generate_host_select(self, memory, mem_mask, B, E, S, use_graph, repetition_penalty, min_length, sample):
+        """Greedy / nucleus-sampling decoding with HF's logits processors: the decode step (all the arithmetic up to the
+        next-token logits) is the same captured launch sequence; the token choice — repetition penalty, min_length, then
+        argmax or temperature + top-p + multinomial (`sample` = (top_p, temperature), torch's random stream) — is a few
+        torch ops on the [B, V] logits per step."""
+        ops = self.ops
+        st = self._greedy_setup(memory, mem_mask, B, E, S, use_graph, select_on_device=False)
+        seq, done = st["seq"], st["done"].bool()
+        n = 0
+        while n < S:
+            if st["graph"] is not None:
+                st["graph"].replay()
+            else:
+                st["step"]()
+            scores = self.process_scores(st["logits"].float(), seq, n + 1, repetition_penalty, min_length)
+            if sample is None:
+                nxt = scores.argmax(-1)
+            else:
+                top_p, temperature = sample
+                scores = scores / temperature
+                srt, idx = torch.sort(scores, descending=False, dim=-1)
+                remove = srt.softmax(-1).cumsum(-1) <= (1 - top_p)
+                remove[..., -1:] = False
+                scores = scores.masked_fill(remove.scatter(1, idx, remove), -float("inf"))
+                nxt = torch.multinomial(scores.softmax(-1), 1).squeeze(1)
+            nxt = torch.where(done, torch.zeros_like(nxt), nxt)
+            done = done | (nxt == 1)
+            seq[:, n + 1] = nxt
+            st["ids"].copy_(nxt)
+            ops.step_advance(st["pos"])
+            n += 1
+            if bool(done.all().item()):
+                break
+        return seq[:, :n + 1].clone()
 
     @torch.no_grad()
     def time_greedy_loop(self, memory, mem_mask, B, E, max_new_tokens=256):
@@ -1018,7 +1073,7 @@ class Vid2SeqEngine:
         return e0.elapsed_time(e1)
 
     def generate_beam(self, memory, mem_mask, B, E, num_beams=4, max_new_tokens=256, length_penalty=1.0, use_graph=None,
-                      eos_id=1, pad_id=0):
+                      eos_id=1, pad_id=0, repetition_penalty=1.0, min_length=1, num_return=1):
         """Beam search with a KV cache (model/vid2seq.py:150-162 with num_beams > 1, i.e. the reference's default
         num_beams=4: HF-4.28 `beam_search` + `BeamSearchScorer`, early_stopping=False, length_penalty as given).
         Device: one decode step for all B*num_beams hypotheses (the greedy step's launch sequence), `vc_beam_topk`
@@ -1053,9 +1108,13 @@ class Vid2SeqEngine:
         top_b = torch.zeros(B, K2, dtype=torch.int32, device=dev)
         buf = self._decode_buffers(Bn)
 
+        processed = repetition_penalty != 1.0 or min_length > 1
+        seq_dev = torch.zeros(Bn, S + 1, dtype=torch.int64, device=dev) if processed else None   # token history per beam
+
         def step(par):
             logits = self._decode_step_logits(ids, buf, caches[par], kvmem, mask_x, bias_d, pos, Bn, S, E)
-            ops.beam_topk(logits, beam_scores, nb, top_s, top_t, top_b)
+            if not processed:     # log-softmax + beam scores + top 2*num_beams in one kernel
+                ops.beam_topk(logits, beam_scores, nb, top_s, top_t, top_b)
             ops.step_advance(pos)
 
         def rewind():
@@ -1106,8 +1165,15 @@ class Vid2SeqEngine:
                 graphs[par].replay()
             else:
                 step(par)
-            ts, tt, tb = top_s.cpu(), top_t.cpu(), top_b.cpu()      # one small D2H + sync per step
             cur_len = len(seqs[0])
+            if processed:
+                # HF applies the logits processors to the LOG-PROBABILITIES in beam search, then adds the beam scores
+                sc = self.process_scores(torch.log_softmax(buf["logits"].float(), -1), seq_dev, cur_len, repetition_penalty,
+                                         min_length, eos_id) + beam_scores[:, None]
+                V_ = sc.shape[1]
+                s_, i_ = torch.topk(sc.view(B, nb * V_), K2, dim=1, largest=True, sorted=True)
+                top_s.copy_(s_); top_t.copy_((i_ % V_).to(torch.int32)); top_b.copy_((i_ // V_).to(torch.int32))
+            ts, tt, tb = top_s.cpu(), top_t.cpu(), top_b.cpu()      # one small D2H + sync per step
             n_scores = [0.0] * Bn
             n_tokens = [pad_id] * Bn
             n_index = [0] * Bn
@@ -1134,6 +1200,9 @@ class Vid2SeqEngine:
             ids.copy_(torch.tensor(n_tokens, dtype=torch.int64), non_blocking=False)
             beam_scores.copy_(torch.tensor(n_scores, dtype=torch.float32))
             beam_idx.copy_(torch.tensor(n_index, dtype=torch.int32))
+            if processed:
+                seq_dev.copy_(seq_dev[beam_idx.long()])
+                seq_dev[:, cur_len] = ids
             n_rows = cur_len                   # cache rows written so far: positions 0 .. cur_len-1
             for li in range(nl):
                 ops.kv_reorder(caches[par][li], caches[1 - par][li], beam_idx, n_rows)
@@ -1144,9 +1213,11 @@ class Vid2SeqEngine:
             if not done[b]:
                 for j in range(nb):
                     add_hyp(b, seqs[b * nb + j], final_scores[b * nb + j])
-            best.append(sorted(hyps[b], key=lambda t: t[0])[-1][1])
+            ranked = sorted(hyps[b], key=lambda t: t[0])
+            for j in range(num_return):            # num_return_sequences: the n best hypotheses, best first
+                best.append(ranked[-1 - j][1])
         sent_max = min(max(len(t) for t in best) + 1, max_length)
-        out = torch.full((B, sent_max), pad_id, dtype=torch.int64)
+        out = torch.full((B * num_return, sent_max), pad_id, dtype=torch.int64)
         for b, t in enumerate(best):
             out[b, :len(t)] = torch.tensor(t, dtype=torch.int64)
             if len(t) < sent_max:

@@ -313,25 +313,42 @@ class Vid2Seq(nn.Module):
     @torch.no_grad()
     def generate(self, video, input_tokenized, use_nucleus_sampling=False, num_beams=4, max_length=256, min_length=1,
                  top_p=0.9, repetition_penalty=1.0, length_penalty=1.0, num_captions=1, temperature=1):
-        """Greedy (num_beams=1) and beam-search (num_beams 2..8, the reference default is 4) decoding run on the B200
-        path with a KV cache and a CUDA-graphed decode step; the n-best bookkeeping follows HF-4.28's BeamSearchScorer
-        (early_stopping=False).  Nucleus sampling, repetition penalties and several returned captions (HF-4.28
-        `generate` features, third-party code the reference delegates to) are not built and raise."""
-        if use_nucleus_sampling or num_beams < 1 or num_beams > 8 or num_captions != 1 or repetition_penalty != 1.0 \
-                or min_length > 1:
-            raise NotImplementedError("vidchapters_b200.Vid2Seq.generate implements greedy and beam-search decoding "
-                                      "(1 <= num_beams <= 8, repetition_penalty 1.0, min_length 1, one caption)")
+        """Same kwargs as the reference (model/vid2seq.py:100-167), which forwards them to HF-4.28 `generate`:
+        greedy (num_beams=1), beam search (2..8 beams; the reference default is 4) and nucleus sampling
+        (`use_nucleus_sampling`, i.e. dvc.py's `--num_beams 0`) run on the B200 path with a KV cache and a CUDA-graphed
+        decode step; `repetition_penalty`, `min_length`, `temperature`, `top_p`, `length_penalty` and `num_captions`
+        (num_return_sequences) follow HF's semantics (processors pinned against stock HF generate in
+        tests/test_oracle_cpu.py).  Sampling draws from torch's random stream of the model's device.  Not built (raise):
+        beam-sampling (sampling with num_beams > 1) and more than 8 beams."""
+        if num_beams > 8 or num_beams < 0 or num_captions < 1:
+            raise NotImplementedError("vidchapters_b200.Vid2Seq.generate: 0 <= num_beams <= 8, num_captions >= 1")
+        if use_nucleus_sampling and num_beams > 1:
+            raise NotImplementedError("beam-sampling (use_nucleus_sampling with num_beams > 1) is not built")
+        if not use_nucleus_sampling and num_beams == 0:
+            raise ValueError("num_beams=0 selects nucleus sampling in dvc.py (use_nucleus_sampling=True)")
+        if not use_nucleus_sampling and num_captions > 1 and (num_beams == 1 or num_captions > num_beams):
+            raise ValueError("num_captions > 1 needs beam search (num_captions <= num_beams) or sampling, as in HF generate")
         with _dev_guard(self._flat.device):
             self._refresh_shadow()
             eng = self.engine
             ids = input_tokenized["input_ids"] if self.use_speech else None
             mask = input_tokenized["attention_mask"] if self.use_speech else None
             memory, mem_mask, B, E = eng.encode(video, ids, mask)
-            if num_beams == 1:
-                seq = eng.generate_greedy(memory, mem_mask, B, E, max_new_tokens=max_length)
+            if use_nucleus_sampling:
+                if num_captions > 1:       # HF expands every input num_return_sequences times before sampling
+                    d_ = memory.shape[1]
+                    memory = memory.view(B, E, d_).repeat_interleave(num_captions, 0).reshape(B * num_captions * E, d_).contiguous()
+                    mem_mask = mem_mask.repeat_interleave(num_captions, 0).contiguous()
+                    B = B * num_captions
+                seq = eng.generate_greedy(memory, mem_mask, B, E, max_new_tokens=max_length, repetition_penalty=repetition_penalty,
+                                          min_length=min_length, sample=(float(top_p), float(temperature)))
+            elif num_beams == 1:
+                seq = eng.generate_greedy(memory, mem_mask, B, E, max_new_tokens=max_length,
+                                          repetition_penalty=repetition_penalty, min_length=min_length)
             else:
                 seq = eng.generate_beam(memory, mem_mask, B, E, num_beams=num_beams, max_new_tokens=max_length,
-                                        length_penalty=length_penalty)
+                                        length_penalty=length_penalty, repetition_penalty=repetition_penalty,
+                                        min_length=min_length, num_return=num_captions)
         self.last_generated_ids = seq
         return self.t5_tokenizer.batch_decode(seq, skip_special_tokens=True)
 
