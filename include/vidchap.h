@@ -92,6 +92,9 @@ typedef struct vc_attn_args {
    * key are padding — no consumer can observe them (as keys they get an exactly-zero probability everywhere) — so whole
    * 128-query tiles of them are skipped: out rows = 0 (forward), no contribution (backward).  0 = compute every row. */
   int32_t q_like_k;
+  /* incremental decoding with beam search (Lq == 1 only): sequence b reads the K/V of batch b / kv_batch_div, so the
+   * num_beams hypotheses of one video share ONE copy of the cross-attention K/V (0 or 1: every sequence has its own). */
+  int32_t kv_batch_div;
 } vc_attn_args;
 int vc_attn_fwd(const vc_attn_args* args, void* stream);
 
@@ -164,6 +167,13 @@ int vc_kv_append(const void* src, int64_t lds, void* cache, int B, int cap, int 
 int vc_greedy_next(const float* logits, int64_t ld, int V, uint8_t* done, int64_t* ids_out, int64_t* seq, int seq_ld,
                    const int32_t* pos_dev, int64_t eos_id, int64_t pad_id, int B, void* stream);
 int vc_step_advance(int32_t* pos_dev, void* stream);
+/* One linear layer of a decode step, M = batch rows (any M; 64 rows per CTA): out[M,N] = epi(A[M,K] . W[N,K]^T), W bf16.
+ * A: bf16 [M][lda] (a_fp32 = 0) or the fp32 residual stream (a_fp32 = 1), optionally through the T5 RMS norm
+ * (norm_w != NULL: x * rsqrt(mean x^2 + eps) * norm_w * out_scale, K <= 1024) — T5LayerNorm + nn.Linear in ONE launch
+ * (modeling_t5.py:254-277 + :305,310,528-536,581).  Epilogue: relu, + residual (fp32 out, may alias), bf16 / fp32 store. */
+int vc_decode_linear(const void* A, int64_t lda, int a_fp32, const float* norm_w, float eps, float out_scale, const void* W,
+                     int64_t ldw, void* out, int64_t ldo, int out_fp32, const float* residual, int64_t ldr, int relu, int M,
+                     int N, int K, void* stream);
 /* Beam search (vid2seq.py:150-162 with num_beams > 1; HF-4.28 GenerationMixin.beam_search, third-party): for every batch
  * item the 2*num_beams best  log_softmax(logits[b*num_beams + r])[v] + beam_scores[b*num_beams + r]  over (r, v), sorted
  * descending -> out_scores / out_tokens (v) / out_beams (r), each [B, 2*num_beams].  num_beams <= 8. */

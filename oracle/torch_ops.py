@@ -151,7 +151,11 @@ class TorchOps:
 
     def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0,
-                 bias_len=0, q_like_k=False):
+                 bias_len=0, q_like_k=False, kv_batch_div=0):
+        if kv_batch_div > 1:      # beams of one video share its K/V: expand for this checker
+            kvr_ = kv_batch_rows or Lk
+            k = k.view(B // kv_batch_div, kvr_, -1).repeat_interleave(kv_batch_div, 0).reshape(B * kvr_, -1)
+            v = v.view(B // kv_batch_div, kvr_, -1).repeat_interleave(kv_batch_div, 0).reshape(B * kvr_, -1)
         # q_like_k (skip padding-only query tiles) is a pure work-skipping hint: this checker computes every row
         qoff = q_offset + (int(q_offset_dev.item()) if q_offset_dev is not None else 0)
         s = self._scores(q, k, q_col, k_col, B, H, Lq, Lk, bias_rel, kmask, causal, scale, qoff, kv_batch_rows,
@@ -343,6 +347,17 @@ class TorchOps:
     # ------------------------------------------------------------------ incremental decoding
     def kv_append(self, src, cache, pos_dev):
         cache[:, int(pos_dev.item())].copy_(src)
+
+    def decode_linear(self, A, W, out, *, norm_w=None, eps=1e-6, out_scale=1.0, residual=None, relu=False):
+        a = A.float()
+        if norm_w is not None:
+            a = a * torch.rsqrt((a * a).mean(-1, keepdim=True) + eps) * out_scale * norm_w
+        acc = a.to(torch.bfloat16).float() @ W.float().t()
+        if relu:
+            acc = torch.relu(acc)
+        if residual is not None:
+            acc = acc + residual
+        out.copy_(acc.to(out.dtype))
 
     def greedy_next(self, logits, done, ids_out, seq, pos_dev, eos_id=1, pad_id=0):
         nxt = logits.argmax(-1)

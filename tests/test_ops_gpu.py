@@ -192,6 +192,69 @@ def test_attn_bwd(cuda_ops, torch_ops, case):
             assert rel(f, f_r) < 1.5e-2, rel(f, f_r)
 
 
+@pytest.mark.parametrize("M,N,K,mode", [(64, 2304, 768, "norm"), (64, 768, 768, "resid"), (64, 3072, 768, "norm_relu"),
+                                        (64, 768, 3072, "resid"), (256, 1536, 1024, "norm"), (50, 1000, 768, "resid"),
+                                        (7, 776, 4096, "plain")])
+def test_decode_linear(cuda_ops, torch_ops, M, N, K, mode):
+    """vc_decode_linear (decode2.cu): T5 RMS norm + nn.Linear (+ReLU / +residual) of one decode step in one launch."""
+    g = gen(M + N + K)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV).bfloat16()
+    x = torch.randn(M, K, generator=g).to(DEV)
+    nw = (1 + 0.1 * torch.randn(K, generator=g)).to(DEV)
+    if mode.startswith("norm"):
+        out, ref = (torch.zeros(M, N, device=DEV, dtype=torch.bfloat16) for _ in range(2))
+        kw = dict(norm_w=nw, eps=1e-6, out_scale=0.5, relu=mode.endswith("relu"))
+        cuda_ops.decode_linear(x, W, out, **kw)
+        torch_ops.decode_linear(x, W, ref, **kw)
+        assert rel(out, ref) < BF16_TOL
+    elif mode == "resid":
+        a = x.bfloat16()
+        res = torch.randn(M, N, generator=g).to(DEV)
+        out, ref = res.clone(), res.clone()
+        cuda_ops.decode_linear(a, W, out, residual=out)          # in place, as the decode step uses it
+        torch_ops.decode_linear(a, W, ref, residual=ref.clone())
+        assert rel(out, ref) < F32_TOL
+    else:
+        a = x.bfloat16()
+        out, ref = torch.zeros(M, N, device=DEV), torch.zeros(M, N, device=DEV)
+        cuda_ops.decode_linear(a, W, out)
+        torch_ops.decode_linear(a, W, ref)
+        assert rel(out, ref) < F32_TOL
+
+
+@pytest.mark.parametrize("kind", ["self", "cross", "cross_beams"])
+def test_attn_single_query_decode(cuda_ops, torch_ops, kind):
+    """Single-query attention over a KV cache (decode2.cu::attn_decode_kernel): causal self-attention at a device-side
+    position with the relative bias row, cross-attention with a key mask, and beams sharing one copy of the K/V."""
+    g = gen(31)
+    H, inner = 12, 768
+    if kind == "self":
+        B, S, pos = 5, 256, 77
+        q = (torch.randn(B, inner, generator=g) * 0.5).to(DEV).bfloat16()
+        cache = (torch.randn(B * S, 2 * inner, generator=g) * 0.5).to(DEV).bfloat16()
+        bias = torch.randn(H, 2 * S - 1, generator=g).to(DEV)
+        pos_dev = torch.tensor([pos], dtype=torch.int32, device=DEV)
+        kw = dict(q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=1, Lk=S, lse2=None, bias_rel=bias, kmask=None, causal=True,
+                  scale=1.0, q_offset_dev=pos_dev, kv_batch_rows=S, bias_zero=S - 1, bias_len=2 * S - 1)
+        out, ref = (torch.zeros(B, inner, device=DEV, dtype=torch.bfloat16) for _ in range(2))
+        cuda_ops.attn_fwd(q, cache, cache, out=out, **kw)
+        torch_ops.attn_fwd(q, cache, cache, out=ref, **kw)
+    else:
+        nb = 4 if kind == "cross_beams" else 1
+        Bv, E = 3, 1100
+        B = Bv * nb
+        q = (torch.randn(B, inner, generator=g) * 0.5).to(DEV).bfloat16()
+        kv = (torch.randn(Bv * E, 2 * inner, generator=g) * 0.5).to(DEV).bfloat16()
+        lens = torch.tensor([1100, 640, 357])
+        kmask = (torch.arange(E)[None, :] < lens[:, None]).to(torch.uint8).repeat_interleave(nb, 0).contiguous().to(DEV)
+        kw = dict(q_col=0, k_col=0, v_col=inner, B=B, H=H, Lq=1, Lk=E, lse2=None, bias_rel=None, kmask=kmask, causal=False,
+                  scale=1.0, kv_batch_div=nb if nb > 1 else 0)
+        out, ref = (torch.zeros(B, inner, device=DEV, dtype=torch.bfloat16) for _ in range(2))
+        cuda_ops.attn_fwd(q, kv, kv, out=out, **kw)
+        torch_ops.attn_fwd(q, kv, kv, out=ref, **kw)
+    assert rel(out, ref) < 8e-3, rel(out, ref)
+
+
 @pytest.mark.parametrize("M,V,K,tn", [(4096, 32200, 768, 256), (300, 1012, 768, 128), (130, 1100, 256, 256)])
 def test_fused_lm_head_cross_entropy(cuda_ops, M, V, K, tn):
     """LM head fused with F.cross_entropy(ignore_index=-100, label_smoothing=0.1) (modeling_t5.py:1714-1721): statistics

@@ -355,6 +355,7 @@ using namespace vc;
 
 namespace vc {
 int launch_attn_fwd_pair(const vc_attn_args* a, cudaStream_t st);   // attn_fwd2.cu
+int launch_attn_decode(const vc_attn_args* a, cudaStream_t st);     // decode2.cu
 }
 
 extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
@@ -366,6 +367,10 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VC_CHECK(a->scale > 0.f, "vc_attn_fwd: scale must be positive");
   VC_CHECK(!a->q_like_k || (a->Lq == a->Lk && a->kmask), "vc_attn_fwd: q_like_k needs self-attention with a key mask");
+  // one query per sequence (incremental decoding): stream the KV cache (decode2.cu); VIDCHAP_ATTN_DECODE=0 = A/B switch
+  static const bool dec_on = [] { const char* e = getenv("VIDCHAP_ATTN_DECODE"); return !(e && e[0] == '0'); }();
+  if (dec_on && a->Lq == 1 && a->drop_p16 == 0 && a->lse2 == nullptr && !a->q_like_k) return launch_attn_decode(a, st);
+  VC_CHECK(a->kv_batch_div <= 1, "vc_attn_fwd: kv_batch_div needs the single-query decode kernel");
   // training shapes: two query tiles per CTA sharing one K/V stream (attn_fwd2.cu); VIDCHAP_ATTN_FWD_PAIR=0 = A/B switch
   static const bool pair_on = [] { const char* e = getenv("VIDCHAP_ATTN_FWD_PAIR"); return !(e && e[0] == '0'); }();
   if (pair_on && a->Lq > 128 && a->q_offset == 0 && a->q_offset_dev == nullptr && a->kv_batch_rows == 0 && a->bias_len == 0)

@@ -131,7 +131,7 @@ extern "C" int vc_set_dropout_salt(const uint32_t* dev_ptr) {
   vc::g_drop_salt = dev_ptr;
   return VC_OK;
 }
-extern "C" int vc_version(void) { return 8; }
+extern "C" int vc_version(void) { return 9; }
 extern "C" const char* vc_last_error(void) { return vc::g_err; }
 extern "C" int vc_device_check(void) {
   int dev = 0;

@@ -183,6 +183,8 @@ class Vid2SeqEngine:
         import os
         self.dual_stream = os.environ.get("VIDCHAP_DUAL_STREAM", "1") != "0" and self.device.type == "cuda"
         self.fused_ce = os.environ.get("VIDCHAP_FUSED_CE", "1") != "0"
+        # decode steps: norm + linear fused skinny kernels (decode2.cu) instead of norm kernel + tcgen05 GEMM at M = batch
+        self.decode_skinny = os.environ.get("VIDCHAP_DECODE_LINEAR", "1") != "0"
         self._side_stream = None
         self._build_specs()
 
@@ -895,35 +897,55 @@ class Vid2SeqEngine:
         bf, d, inner = torch.bfloat16, self.d, self.inner
         Vp = (self.V + 7) // 8 * 8
         return dict(x=self._e(Bn, d), h=self._e(Bn, d, dtype=bf), q=self._e(Bn, inner, dtype=bf),
-                    kvn=self._e(Bn, 2 * inner, dtype=bf), ctxb=self._e(Bn, inner, dtype=bf),
-                    act=self._e(Bn, self.dff, dtype=bf), logits=self._e(Bn, Vp)[:, :self.V])
+                    kvn=self._e(Bn, 2 * inner, dtype=bf), qkv=self._e(Bn, 3 * inner, dtype=bf),
+                    ctxb=self._e(Bn, inner, dtype=bf), act=self._e(Bn, self.dff, dtype=bf),
+                    logits=self._e(Bn, Vp)[:, :self.V])
 
-    def _decode_step_logits(self, ids, buf, caches, kvmem, mem_mask, bias_d, pos, Bn, S, E):
+    def _decode_step_logits(self, ids, buf, caches, kvmem, mem_mask, bias_d, pos, Bn, S, E, kv_div=0):
         """One incremental decoder step for Bn sequences (modeling_t5.py:484-525,551-556 with past_key_values): embeds
         `ids`, appends this position's K/V to `caches`, attends to positions <= *pos and to the encoder memory, and
-        leaves the next-token logits in buf["logits"].  A fixed launch sequence (the position is a device scalar)."""
+        leaves the next-token logits in buf["logits"].  A fixed launch sequence (the position is a device scalar).
+        Per layer: [RMS norm + fused q,k,v] -> cache append -> single-query attention -> [o + residual] -> [RMS norm + q]
+        -> single-query cross-attention -> [o + residual] -> [RMS norm + wi + ReLU] -> [wo + residual]: nine launches,
+        the bracketed ones vc_decode_linear (decode2.cu).  kv_div: beams of one video share its cross-attention K/V."""
         ops, d, H, inner = self.ops, self.d, self.H, self.inner
-        x, h, q, kvn, ctxb, act, logits = (buf[k] for k in ("x", "h", "q", "kvn", "ctxb", "act", "logits"))
+        x, h, q, kvn, qkv, ctxb, act, logits = (buf[k] for k in ("x", "h", "q", "kvn", "qkv", "ctxb", "act", "logits"))
         ops.embed_fwd(ids, self.p("t5_model.shared.weight"), x)
+        skinny = self.decode_skinny
         for li, (sa, ca, ff) in enumerate(self.dec_blocks):
-            ops.norm_fwd(0, x, self.pv(sa.norm_w), None, out_bf16=h, eps=1e-6)
-            ops.gemm(h, self.pb(sa.qkv_w), q)                                   # q rows of the fused [q;k;v]
-            k_name = sa.qkv_w.replace(".q.weight", ".k.weight")
-            ops.gemm(h, self.pb(k_name, 2 * inner), kvn)                         # adjacent k,v weights
-            ops.kv_append(kvn, caches[li], pos)
+            if skinny:
+                ops.decode_linear(x, self.pb(sa.qkv_w, 3 * inner), qkv, norm_w=self.pv(sa.norm_w), eps=1e-6)
+                ops.kv_append(qkv[:, inner:], caches[li], pos)
+                q_src = qkv
+            else:
+                ops.norm_fwd(0, x, self.pv(sa.norm_w), None, out_bf16=h, eps=1e-6)
+                ops.gemm(h, self.pb(sa.qkv_w), q)                                   # q rows of the fused [q;k;v]
+                k_name = sa.qkv_w.replace(".q.weight", ".k.weight")
+                ops.gemm(h, self.pb(k_name, 2 * inner), kvn)                         # adjacent k,v weights
+                ops.kv_append(kvn, caches[li], pos)
+                q_src = q
             c2 = caches[li].view(Bn * S, 2 * inner)
-            ops.attn_fwd(q, c2, c2, q_col=0, k_col=0, v_col=inner, B=Bn, H=H, Lq=1, Lk=S, out=ctxb, lse2=None,
+            ops.attn_fwd(q_src, c2, c2, q_col=0, k_col=0, v_col=inner, B=Bn, H=H, Lq=1, Lk=S, out=ctxb, lse2=None,
                          bias_rel=bias_d, kmask=None, causal=True, scale=1.0, q_offset_dev=pos, kv_batch_rows=S,
                          bias_zero=S - 1, bias_len=2 * S - 1)
-            ops.gemm(ctxb, self.pb(sa.o_w), x, residual=x)
-            ops.norm_fwd(0, x, self.pv(ca.norm_w), None, out_bf16=h, eps=1e-6)
-            ops.gemm(h, self.pb(ca.q_w), q)
+            if skinny:
+                ops.decode_linear(ctxb, self.pb(sa.o_w), x, residual=x)
+                ops.decode_linear(x, self.pb(ca.q_w), q, norm_w=self.pv(ca.norm_w), eps=1e-6)
+            else:
+                ops.gemm(ctxb, self.pb(sa.o_w), x, residual=x)
+                ops.norm_fwd(0, x, self.pv(ca.norm_w), None, out_bf16=h, eps=1e-6)
+                ops.gemm(h, self.pb(ca.q_w), q)
             ops.attn_fwd(q, kvmem[li], kvmem[li], q_col=0, k_col=0, v_col=inner, B=Bn, H=H, Lq=1, Lk=E, out=ctxb,
-                         lse2=None, bias_rel=None, kmask=mem_mask, causal=False, scale=1.0)
-            ops.gemm(ctxb, self.pb(ca.o_w), x, residual=x)
-            ops.norm_fwd(0, x, self.pv(ff.norm_w), None, out_bf16=h, eps=1e-6)
-            ops.gemm(h, self.pb(ff.w1), act, act=ACT_RELU)
-            ops.gemm(act, self.pb(ff.w2), x, residual=x)
+                         lse2=None, bias_rel=None, kmask=mem_mask, causal=False, scale=1.0, kv_batch_div=kv_div)
+            if skinny:
+                ops.decode_linear(ctxb, self.pb(ca.o_w), x, residual=x)
+                ops.decode_linear(x, self.pb(ff.w1), act, norm_w=self.pv(ff.norm_w), eps=1e-6, relu=True)
+                ops.decode_linear(act, self.pb(ff.w2), x, residual=x)
+            else:
+                ops.gemm(ctxb, self.pb(ca.o_w), x, residual=x)
+                ops.norm_fwd(0, x, self.pv(ff.norm_w), None, out_bf16=h, eps=1e-6)
+                ops.gemm(h, self.pb(ff.w1), act, act=ACT_RELU)
+                ops.gemm(act, self.pb(ff.w2), x, residual=x)
         ops.norm_fwd(0, x, self.pv("t5_model.decoder.final_layer_norm.weight"), None, out_bf16=h, eps=1e-6,
                      out_scale=d ** -0.5)
         ops.gemm(h, self.pb("t5_model.shared.weight"), logits)
@@ -1087,13 +1109,13 @@ class Vid2SeqEngine:
         Bn, K2 = B * nb, 2 * nb
         if use_graph is None:
             use_graph = dev.type == "cuda" and getattr(ops, "name", "") == "cuda"
-        # every beam of a batch item attends to the same memory (HF expands encoder outputs num_beams times)
-        mem_x = memory.view(B, E, d).repeat_interleave(nb, 0).reshape(Bn * E, d).contiguous()
+        # every beam of a batch item attends to the same memory (HF expands encoder outputs num_beams times): the K/V
+        # projections are computed ONCE per video and the single-query attention kernel maps beam -> video (kv_batch_div)
         mask_x = mem_mask.repeat_interleave(nb, 0).contiguous()
         kvmem = []
         for sa, ca, ff in self.dec_blocks:
-            kv = self._e(Bn * E, 2 * inner, dtype=bf)
-            ops.gemm(mem_x, self.pb(ca.kv_w, 2 * inner), kv)
+            kv = self._e(B * E, 2 * inner, dtype=bf)
+            ops.gemm(memory, self.pb(ca.kv_w, 2 * inner), kv)
             kvmem.append(kv)
         nl = len(self.dec_blocks)
         caches = [[torch.zeros(Bn, S, 2 * inner, dtype=bf, device=dev) for _ in range(nl)] for _ in range(2)]
@@ -1112,7 +1134,7 @@ class Vid2SeqEngine:
         seq_dev = torch.zeros(Bn, S + 1, dtype=torch.int64, device=dev) if processed else None   # token history per beam
 
         def step(par):
-            logits = self._decode_step_logits(ids, buf, caches[par], kvmem, mask_x, bias_d, pos, Bn, S, E)
+            logits = self._decode_step_logits(ids, buf, caches[par], kvmem, mask_x, bias_d, pos, Bn, S, E, kv_div=nb)
             if not processed:     # log-softmax + beam scores + top 2*num_beams in one kernel
                 ops.beam_topk(logits, beam_scores, nb, top_s, top_t, top_b)
             ops.step_advance(pos)

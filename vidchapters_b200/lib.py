@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvidchap.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class GemmArgs(C.Structure):
@@ -51,6 +51,7 @@ class AttnArgs(C.Structure):
         ("q_offset", C.c_int32), ("q_offset_dev", C.c_void_p), ("kv_batch_rows", C.c_int32),
         ("bias_zero", C.c_int32), ("bias_len", C.c_int32),
         ("q_like_k", C.c_int32),
+        ("kv_batch_div", C.c_int32),
     ]
 
 
@@ -93,6 +94,7 @@ SIGNATURES = {
     "vc_kv_append": [P, I64, P, I, I, I, P, P],
     "vc_greedy_next": [P, I64, I, P, P, P, I, P, I64, I64, I, P],
     "vc_step_advance": [P, P],
+    "vc_decode_linear": [P, I64, I, P, F, F, P, I64, P, I64, I, P, I64, I, I, I, I, P],
     "vc_beam_topk": [P, I64, I, P, I, I, P, P, P, P],
     "vc_kv_reorder": [P, P, P, I, I, I, I, P],
     "vc_set_dropout_salt": [P],

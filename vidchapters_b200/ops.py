@@ -117,12 +117,14 @@ class CudaOps:
 
     # ------------------------------------------------------------------ attention
     def _attn_args(self, q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale,
-                   drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0, bias_len=0, q_like_k=False):
+                   drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0, bias_len=0, q_like_k=False,
+                   kv_batch_div=0):
         _chk_cuda(q, k, v, out, lse2, bias_rel, kmask)
         for t in (q, k, v, out):
             assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
         kvr = kv_batch_rows or Lk
-        assert q.shape[0] == B * Lq and k.shape[0] == B * kvr and v.shape[0] == B * kvr and out.shape[0] == B * Lq
+        Bkv = B // max(kv_batch_div, 1)
+        assert q.shape[0] == B * Lq and k.shape[0] == Bkv * kvr and v.shape[0] == Bkv * kvr and out.shape[0] == B * Lq
         if kmask is not None:
             assert kmask.dtype == torch.uint8 and kmask.shape == (B, Lk) and kmask.is_contiguous()
         if bias_rel is not None:
@@ -144,13 +146,14 @@ class CudaOps:
         a.q_offset_dev = None if q_offset_dev is None else q_offset_dev.data_ptr()
         assert not q_like_k or (Lq == Lk and kmask is not None)
         a.q_like_k = int(bool(q_like_k))
+        a.kv_batch_div = int(kv_batch_div)
         return a
 
     def attn_fwd(self, q, k, v, *, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel=None, kmask=None,
                  causal=False, scale=1.0, drop=NO_DROP, q_offset=0, q_offset_dev=None, kv_batch_rows=0, bias_zero=0,
-                 bias_len=0, q_like_k=False):
+                 bias_len=0, q_like_k=False, kv_batch_div=0):
         a = self._attn_args(q, k, v, q_col, k_col, v_col, B, H, Lq, Lk, out, lse2, bias_rel, kmask, causal, scale, drop,
-                            q_offset, q_offset_dev, kv_batch_rows, bias_zero, bias_len, q_like_k)
+                            q_offset, q_offset_dev, kv_batch_rows, bias_zero, bias_len, q_like_k, kv_batch_div)
         _lib.check(self.lib.vc_attn_fwd(C.byref(a), self._stream()))
         self.launches += 1
 
@@ -287,6 +290,21 @@ class CudaOps:
         B, cap, Cc = cache.shape
         assert src.shape == (B, Cc) and src.stride(1) == 1 and cache.is_contiguous() and pos_dev.dtype == torch.int32
         _lib.check(self.lib.vc_kv_append(_ptr(src), src.stride(0), _ptr(cache), B, cap, Cc, _ptr(pos_dev), self._stream()))
+        self.launches += 1
+
+    def decode_linear(self, A, W, out, *, norm_w=None, eps=1e-6, out_scale=1.0, residual=None, relu=False):
+        """out[M,N] = epi(A[M,K] @ W[N,K]^T) for the M = batch rows of a decode step; A bf16, or the fp32 residual stream
+        with the T5 RMS norm fused (norm_w); relu / + residual (fp32 out, may alias out) epilogues."""
+        _chk_cuda(A, W, out, norm_w, residual)
+        M, K = A.shape
+        N = W.shape[0]
+        assert W.dtype == torch.bfloat16 and W.shape[1] == K and W.stride(1) == 1 and A.stride(1) == 1 and out.stride(1) == 1
+        assert A.dtype in (torch.float32, torch.bfloat16) and out.dtype in (torch.float32, torch.bfloat16)
+        assert out.shape == (M, N) and (residual is None or (residual.dtype == torch.float32 and residual.stride(1) == 1))
+        _lib.check(self.lib.vc_decode_linear(_ptr(A), A.stride(0), int(A.dtype == torch.float32), _ptr(norm_w), eps, out_scale,
+                                             _ptr(W), W.stride(0), _ptr(out), out.stride(0), int(out.dtype == torch.float32),
+                                             _ptr(residual), 0 if residual is None else residual.stride(0), int(relu), M, N,
+                                             K, self._stream()))
         self.launches += 1
 
     def greedy_next(self, logits, done, ids_out, seq, pos_dev, eos_id=1, pad_id=0):
