@@ -145,3 +145,31 @@ def test_data_parallel_nccl_overlapped_equals_flat_allreduce():
                        timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "DP_CHECK_OK" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_model_on_second_device_while_first_is_current():
+    """dvc.py without --distributed only does `model.to(device)`: a model on cuda:1 driven while cuda:0 is the current
+    device must launch on cuda:1 (every entry point runs under the model's device) and give the cuda:0 result."""
+    from vidchapters_b200 import Vid2SeqAdam
+    fx = torch.load(os.path.join(GOLD, "tiny.pt"), weights_only=False)
+    cfg = fx["cfg"]
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.cuda.set_device(0)
+        from vidchapters_b200 import Vid2Seq
+        tok = Tok(cfg["base_vocab"] + cfg["num_bins"])
+        m = Vid2Seq("t5-base", num_features=cfg["num_features"], embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                    heads=cfg["heads"], mlp_dim=cfg["mlp_dim"], vis_drop=0.0, tokenizer=tok, enc_drop=0.0, dec_drop=0.0,
+                    num_bins=cfg["num_bins"], t5_config=cfg, seed=0).to(dev)
+        m.train()
+        opt = Vid2SeqAdam(m, lr=3e-4, clip_max_norm=0.1, world_size=1)
+        video, inp, out = fx["video"].to(dev), fx["input_ids"].to(dev), fx["output_ids"].to(dev)
+        ld, _ = m(video, {"input_ids": inp, "attention_mask": inp != 0}, {"input_ids": out, "attention_mask": out != 0})
+        opt.zero_grad()
+        ld["loss"].backward()
+        opt.step()
+        assert torch.cuda.current_device() == 0
+        res.append((ld["loss"].item(), m._params["t5_model.decoder.final_layer_norm.weight"].detach().cpu()))
+    assert abs(res[0][0] - res[1][0]) < 1e-5 * abs(res[0][0])
+    assert rel(res[1][1], res[0][1]) < 1e-4
