@@ -331,10 +331,11 @@ def test_attn_skip_padded_query_tiles(cuda_ops, torch_ops, drop):
     assert rel(f, f_r) < 1.5e-2
 
 
-@pytest.mark.parametrize("kind,D", [(0, 768), (1, 768), (0, 1024), (0, 256)])
-def test_norms(cuda_ops, torch_ops, kind, D):
+@pytest.mark.parametrize("kind,D,L", [(0, 768, 50), (1, 768, 50), (0, 1024, 50), (0, 256, 50), (0, 768, 3001), (1, 768, 2500),
+                                      (1, 1024, 1777)])
+def test_norms(cuda_ops, torch_ops, kind, D, L):
     g = gen(kind + D)
-    B, L, T = 3, 50, 10
+    B, T = 3, 10
     M = B * L
     x = torch.randn(M, D, generator=g).to(DEV)
     w = (1 + 0.1 * torch.randn(D, generator=g)).to(DEV)

@@ -55,5 +55,17 @@ if which in ("all", "gemm"):
         ops.gemm(A, W, C, act=1)                                    # forward wi + relu
         ops.gemm(C, W, dA, b_mn=True)                               # dgrad
         ops.gemm(C, A, dW, a_mn=True, b_mn=True, atomic=True, splits=5)  # wgrad
+if which in ("gemm_wi", "gemm_resid"):
+    from vidchapters_b200.ops import drop_spec
+    M = 16000
+    N, K = (3072, 768) if which == "gemm_wi" else (768, 768)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn(N, K, generator=g) * 0.05).to(dev).bfloat16()
+    if which == "gemm_wi":
+        C = torch.zeros(M, N, device=dev, dtype=torch.bfloat16); kw = dict(act=1, drop=drop_spec(0.1, 7))
+    else:
+        C = torch.zeros(M, N, device=dev); kw = dict(residual=torch.randn(M, N, device=dev), drop=drop_spec(0.1, 7))
+    for _ in range(4):
+        ops.gemm(A, W, C, **kw)
 torch.cuda.synchronize()
 print("done")

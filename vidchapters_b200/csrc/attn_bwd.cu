@@ -522,34 +522,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (the "D" term of the softmax backward)
+// One warp per row, rows grid-strided; a lane owns 8 consecutive elements of each 256-wide slab (4 heads) and issues the
+// loads of all slabs of the row (H <= 16: up to 8 x 16 B per lane) before the first use.
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo, const __nv_bfloat16* __restrict__ dout, long long lddo,
                   int do_col, float* __restrict__ delta, float* __restrict__ dq_acc, long long ld_dq, int B, int H, int Lq) {
   pdl_wait();
   pdl_trigger();
-  // one warp per (row, 4 heads at a time): lane handles 8 consecutive elements of a 256-wide slab
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= (long long)B * Lq) return;
-  const int b = (int)(row / Lq), q = (int)(row % Lq);
-  // also clears this row of the fp32 dQ accumulator the main kernel adds into (saves a separate fill launch)
-  for (int c = lane * 4; c < H * 64; c += 128) *reinterpret_cast<float4*>(dq_acc + row * ld_dq + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int h0 = 0; h0 < H; h0 += 4) {
-    const int col = h0 * 64 + lane * 8;
-    float s = 0.f;
-    if (col < H * 64) {
-      const uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + col);
-      const uint4 g = *reinterpret_cast<const uint4*>(dout + row * lddo + do_col + col);
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+  const long long rows = (long long)B * Lq;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nslab = (H + 3) >> 2;
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    const int b = (int)(row / Lq), q = (int)(row % Lq);
+    uint4 a[4], g[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) s += bf16_lo(aw[e]) * bf16_lo(gw[e]) + bf16_hi(aw[e]) * bf16_hi(gw[e]);
+    for (int sl = 0; sl < 4; ++sl) {
+      const int col = sl * 256 + lane * 8;
+      const bool ok = sl < nslab && col < H * 64;
+      a[sl] = ok ? *reinterpret_cast<const uint4*>(o + row * ldo + col) : make_uint4(0, 0, 0, 0);
+      g[sl] = ok ? *reinterpret_cast<const uint4*>(dout + row * lddo + do_col + col) : make_uint4(0, 0, 0, 0);
     }
-    // reduce over the 8 lanes that share a head
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    const int hh = h0 + (lane >> 3);
-    if ((lane & 7) == 0 && hh < H) delta[((long long)b * H + hh) * Lq + q] = s;
+    // also clears this row of the fp32 dQ accumulator the main kernel adds into (saves a separate fill launch)
+    for (int c = lane * 4; c < H * 64; c += 128) *reinterpret_cast<float4*>(dq_acc + row * ld_dq + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) {
+      if (sl < nslab) {
+        const uint32_t aw[4] = {a[sl].x, a[sl].y, a[sl].z, a[sl].w}, gw[4] = {g[sl].x, g[sl].y, g[sl].z, g[sl].w};
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s += bf16_lo(aw[e]) * bf16_lo(gw[e]) + bf16_hi(aw[e]) * bf16_hi(gw[e]);
+        // reduce over the 8 lanes that share a head
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        const int hh = sl * 4 + (lane >> 3);
+        if ((lane & 7) == 0 && hh < H) delta[((long long)b * H + hh) * Lq + q] = s;
+      }
+    }
   }
 }
 
@@ -570,7 +580,9 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   // delta = rowsum(dO * O)
   {
     const long long rows = (long long)f->B * f->Lq;
-    VC_CUDA(launch_kernel(attn_delta_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, (const __nv_bfloat16*)f->out,
+    VC_CHECK(f->H <= 16, "vc_attn_bwd: H=%d > 16", f->H);
+    const long long want = (rows + 7) / 8, cap = (long long)num_sms() * 8;
+    VC_CUDA(launch_kernel(attn_delta_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, st, (const __nv_bfloat16*)f->out,
                           f->ldo, (const __nv_bfloat16*)a->dout, a->ld_do, a->do_col, a->delta, a->dq_acc, a->ld_dq, f->B, f->H,
                           f->Lq));
     VC_CUDA(cudaGetLastError());

@@ -301,6 +301,8 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   p.ce_labels = reinterpret_cast<const long long*>(a->ce_labels); p.ce_stats = a->ce_stats; p.ce_zy = a->ce_zy;
   p.ce_lse = a->ce_lse; p.ce_nvalid = a->ce_nvalid; p.ce_smoothing = a->ce_smoothing;
   p.ce_slots = 2 * p.n_blocks;
+  static const int dbg = [] { const char* e = getenv("VIDCHAP_GEMM_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg;
   p.tma_epi = tma_epi_mode() && (a->ldr % 4 == 0) && a->act != ACT_CE_STATS;
   p.aux_tma = p.tma_epi && epi_aux_by_tma(a);
   EpiMaps em;

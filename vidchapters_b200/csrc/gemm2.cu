@@ -48,11 +48,15 @@ __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {  // arrives on `b
                ::"r"(smem_u32(bar)), "h"((uint16_t)3)
                : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {  // arrive on `bar` of cluster CTA `cta`
+// Arrive on `bar` of cluster CTA `cta`.  Default (.release.cta) semantics on purpose: the only thing the waiter (the MMA
+// issuer) consumes is "these TMEM columns have been read", which tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+// order; a .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR per tile per warp (12 % of the epilogue warps'
+// stall samples in profiles/r02_gemm_epilogue.md).
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
@@ -65,18 +69,22 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+constexpr int kEpiWarps2 = 8;    // pair kernel: 2 warps per TMEM lane quadrant, each owns half of the tile's columns (16 warps with
+                                 // one pipeline stage less measured slower: the mainloop needs the depth)
+constexpr int kThreads2 = 128 + 32 * kEpiWarps2;
+
 template <int BN>
 struct Gemm2Cfg {
   static constexpr int kABytes = 128 * BK * 2;        // this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * BK * 2;   // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (192 * 1024) / kStageBytes;  // BN=256: 6, BN=128: 8
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps2 * kEpiStageBytes + 1024 + 512;
   static constexpr int kTmemCols = 2 * BN;
 };
 
 template <int BN, bool A_MN, bool B_MN, bool TMA_EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ EpiMaps em, const GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
@@ -88,13 +96,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;   // 8 x 4 KB staging tiles of the TMA epilogue
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiWarps * kEpiStageBytes);
+  uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;   // one 4 KB staging tile per epilogue warp (TMA epilogue)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiWarps2 * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* epi_bar = tmem_empty + 2;   // [8] one per epilogue warp (residual tile landed)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + kEpiWarps);
+  uint64_t* epi_bar = tmem_empty + 2;   // one per epilogue warp (residual tile landed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + kEpiWarps2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,9 +122,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 512);  // leader's: 256 epilogue threads of each CTA
+      mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps2);  // leader's: the epilogue threads of both CTAs
     }
-    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&epi_bar[i], 1);
+    for (int i = 0; i < kEpiWarps2; ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
@@ -198,8 +206,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
-    constexpr int kChunks = BN / 64;
+    const int part = (warp - 4) >> 2;          // which share of the tile's columns
+    constexpr int kChunks = BN / 32 / (kEpiWarps2 / 4);
     int acc = 0;
     uint32_t acc_phase = 0, epi_phase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -213,20 +221,22 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (p.act == ACT_CE_STATS) {
         // fused cross entropy, statistics pass: nothing is stored; this warp's half of the tile's columns is folded into
         // (max, sum exp, sum z) of its rows and written to the row's slot of this (column block, half)
+        // (two slots per column block, as in the single-CTA kernel: parts 0 and 1 take a half each, 2 and 3 only arrive)
+        const int half = part;
         float cm = -INFINITY, cs = 0.f, ct = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < kChunks; ++c) {
-          const int cc = half * kChunks + c;
+        for (int c = 0; c < (part < 2 ? BN / 64 : 0); ++c) {
+          const int cc = half * (BN / 64) + c;
           ce_stats_chunk(p, tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16), row, row_ok, n0 + cc * 32, alpha, cm, cs, ct);
         }
-        if (row_ok) {
+        if (row_ok && part < 2) {
           float* dst = p.ce_stats + ((long long)row * p.ce_slots + (n0 / BN) * 2 + half) * 3;
           dst[0] = cm; dst[1] = cs; dst[2] = ct;
         }
-      } else
+      } else if (!(p.dbg & 1))
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
-        const int cc = half * kChunks + c;
+        const int cc = part * kChunks + c;
         const uint32_t taddr = tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16);
         if constexpr (TMA_EPI)
           gemm_epilogue_chunk_tma(p, em, taddr, m0 + q * 32, lane, n0 + cc * 32, alpha, epi_stage + (warp - 4) * kEpiStageBytes,
@@ -259,7 +269,7 @@ static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  VC_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(384), Cfg::kSmemBytes, st, tmA, tmB, em, p));
+  VC_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(kThreads2), Cfg::kSmemBytes, st, tmA, tmB, em, p));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -40,6 +40,7 @@ struct GemmParams {
   const float* ce_nvalid;        // device scalar
   float ce_smoothing;
   int ce_slots;                  // 2 * n_blocks
+  int dbg;                       // measurement only (VIDCHAP_GEMM_DBG): 1 = epilogue skips its chunks, 2 = skips the stores
 };
 
 constexpr int ACT_CE_STATS = 5, ACT_CE_GRAD = 6;
@@ -405,7 +406,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (lane == 0 && !(p.dbg & 2)) {
     if (p.atomic) tma_reduce_add_2d(&em.out, stage, col0, row0);
     else tma_store_2d(&em.out, stage, col0, row0);
     bulk_commit();

@@ -298,17 +298,32 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 }
 
 // ---- fp32 -> bf16 cast with independent row strides (e.g. dQ accumulator -> the q columns of the dQKV matrix)
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
-                                     long long ldd, int M, int N, float scale) {
+// HBM-bound: every thread keeps four independent 16-byte loads in flight and the grid is a few CTAs per SM (one load per
+// thread in one-shot CTAs ran at ~2 TB/s: the CTA turnover, not the memory system, set the pace).
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd, int M, int N,
+                     float scale) {
   pdl_wait();
   pdl_trigger();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // index over M * N/4
   const int n4 = N / 4;
-  if (i < (long long)M * n4) {
-    const int r = (int)(i / n4), c = (int)(i % n4) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(src + (long long)r * lds + c);
-    *reinterpret_cast<uint2*>(dst + (long long)r * ldd + c) =
-        make_uint2(pack_bf16x2(v.x * scale, v.y * scale), pack_bf16x2(v.z * scale, v.w * scale));
+  const long long total = (long long)M * n4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float4 v[4];
+    long long off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      const bool ok = i < total;
+      const int r = ok ? (int)(i / n4) : 0, c = ok ? (int)(i % n4) * 4 : 0;
+      off[u] = ok ? (long long)r * ldd + c : -1;
+      v[u] = ok ? *reinterpret_cast<const float4*>(src + (long long)r * lds + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (off[u] >= 0)
+        *reinterpret_cast<uint2*>(dst + off[u]) =
+            make_uint2(pack_bf16x2(v[u].x * scale, v[u].y * scale), pack_bf16x2(v[u].z * scale, v[u].w * scale));
   }
 }
 
@@ -415,8 +430,9 @@ extern "C" int vc_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_
                                 void* stream) {
   VC_CHECK(N % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "vc_cast_f32_bf16: alignment");
   const long long total = (long long)M * (N / 4);
-  VC_CUDA(launch_kernel(cast_f32_bf16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), src, lds, (__nv_bfloat16*)dst, ldd, M, N,
-                                                                               scale));
+  const long long want = (total + 1023) / 1024, cap = (long long)num_sms() * 8;
+  VC_CUDA(launch_kernel(cast_f32_bf16_kernel, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, ST(stream), src, lds,
+                        (__nv_bfloat16*)dst, ldd, M, N, scale));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -21,6 +21,7 @@ GEMM is stored bf16; activations needed by the backward are kept (4 GB at config
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -279,7 +280,11 @@ class Vid2SeqEngine:
         if not self.dual_stream:
             return None, None
         if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream(device=self.device)
+            # equal priorities by default: giving the visual encoder's (small) kernels a high-priority stream was
+            # measured SLOWER on config 2 (29.4 vs 28.3 ms/step) although its backward tail is exposed at equal priority
+            # — the text encoder's persistent GEMMs lose more than the tail costs.  VIDCHAP_SIDE_PRIORITY=1 to A/B.
+            prio = -1 if os.environ.get("VIDCHAP_SIDE_PRIORITY", "0") == "1" else 0
+            self._side_stream = torch.cuda.Stream(device=self.device, priority=prio)
         main = torch.cuda.current_stream(self.device)
         self._side_stream.wait_stream(main)
         return main, self._side_stream

@@ -95,8 +95,8 @@ class GraphedTrainStep:
         eng = m.engine
         eng.drop_rates = dict(vis=m.vis_drop, enc=m.enc_drop, dec=m.dec_drop)
         ids, out = self.input_ids, self.output_ids
+        eng.zero_grad()            # before the forward: the 1.2 GB fill hides under the two-stream encoder phase
         loss, ectx = eng.forward(self.video, ids, ids != 0, out, out != 0, training=m.training)
-        eng.zero_grad()
         eng.backward(ectx, phase=phase)
         if phase == 0:
             eng.loss_slot.copy_(loss.view(1))   # rides through the all-reduce of the last gradient region (dvc.py:103)
