@@ -182,7 +182,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int cc = half * kChunks + c;  // chunk index inside the tile
         const uint32_t taddr = tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16);
         if constexpr (TMA_EPI)
-          gemm_epilogue_chunk_tma(p, em, taddr, m0 + q * 32, lane, n0 + cc * 32, alpha, epi_stage + (warp - 4) * kEpiStageBytes,
+          gemm_epilogue_chunk_tma<EF_ALL>(p, em, taddr, m0 + q * 32, lane, n0 + cc * 32, alpha, epi_stage + (warp - 4) * kEpiStageBytes,
                                   &epi_bar[warp - 4], epi_phase);
         else
           gemm_epilogue_chunk(p, taddr, row, row_ok, n0 + cc * 32, alpha);
@@ -303,6 +303,7 @@ extern "C" int vc_gemm_bf16(const vc_gemm_args* a, void* stream) {
   p.ce_slots = 2 * p.n_blocks;
   static const int dbg = [] { const char* e = getenv("VIDCHAP_GEMM_DBG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg;
+  p.epi_preset = epi_preset_for(a);
   p.tma_epi = tma_epi_mode() && (a->ldr % 4 == 0) && a->act != ACT_CE_STATS;
   p.aux_tma = p.tma_epi && epi_aux_by_tma(a);
   EpiMaps em;

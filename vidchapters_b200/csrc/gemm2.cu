@@ -233,16 +233,31 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float* dst = p.ce_stats + ((long long)row * p.ce_slots + (n0 / BN) * 2 + half) * 3;
           dst[0] = cm; dst[1] = cs; dst[2] = ct;
         }
-      } else if (!(p.dbg & 1))
+      } else if (!(p.dbg & 1)) {
+        const uint32_t tcol = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+        if constexpr (TMA_EPI) {
+          uint8_t* stage = epi_stage + (warp - 4) * kEpiStageBytes;
+#define VC_EPI_PRESET(I)                                                                                                \
+  case I:                                                                                                               \
+    _Pragma("unroll 1") for (int c = 0; c < kChunks; ++c) {                                                             \
+      const int cc = part * kChunks + c;                                                                                \
+      gemm_epilogue_chunk_tma<epi_preset_mask(I)>(p, em, tcol + cc * 32, m0 + q * 32, lane, n0 + cc * 32, alpha, stage, \
+                                                  &epi_bar[warp - 4], epi_phase);                                       \
+    }                                                                                                                   \
+    break;
+          switch (p.epi_preset) {
+            VC_EPI_PRESET(0) VC_EPI_PRESET(1) VC_EPI_PRESET(2) VC_EPI_PRESET(3) VC_EPI_PRESET(4)
+            default:
+            VC_EPI_PRESET(5)
+          }
+#undef VC_EPI_PRESET
+        } else {
 #pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        const int cc = part * kChunks + c;
-        const uint32_t taddr = tmem_base + acc * BN + cc * 32 + ((uint32_t)(q * 32) << 16);
-        if constexpr (TMA_EPI)
-          gemm_epilogue_chunk_tma(p, em, taddr, m0 + q * 32, lane, n0 + cc * 32, alpha, epi_stage + (warp - 4) * kEpiStageBytes,
-                                  &epi_bar[warp - 4], epi_phase);
-        else
-          gemm_epilogue_chunk(p, taddr, row, row_ok, n0 + cc * 32, alpha);
+          for (int c = 0; c < kChunks; ++c) {
+            const int cc = part * kChunks + c;
+            gemm_epilogue_chunk(p, tcol + cc * 32, row, row_ok, n0 + cc * 32, alpha);
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive_cta(&tmem_empty[acc], 0);  // the leader's barrier (remote arrive from the peer CTA)

@@ -40,7 +40,8 @@ struct GemmParams {
   const float* ce_nvalid;        // device scalar
   float ce_smoothing;
   int ce_slots;                  // 2 * n_blocks
-  int dbg;                       // measurement only (VIDCHAP_GEMM_DBG): 1 = epilogue skips its chunks, 2 = skips the stores
+  int dbg;                       // measurement only (VIDCHAP_GEMM_DBG=1): the epilogue skips its chunks (tools/time_gemm_epi.py)
+  int epi_preset;                // index into epi_preset_mask(): which compiled epilogue the pair kernel runs
 };
 
 constexpr int ACT_CE_STATS = 5, ACT_CE_GRAD = 6;
@@ -274,6 +275,26 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, uint32_
 __device__ __forceinline__ uint32_t epi_off_f32(int t, int g) { return t * 128 + ((g ^ (t & 7)) << 4); }        // SWIZZLE_128B
 __device__ __forceinline__ uint32_t epi_off_bf16(int t, int g) { return t * 64 + ((g ^ ((t >> 1) & 3)) << 4); }  // SWIZZLE_64B
 
+// Compile-time feature set of an epilogue instantiation: a bit that is clear removes the code of that feature (and the
+// constant-bank loads and uniform branches that select it at run time); a bit that is set leaves the run-time test in.
+// The pair kernel carries a handful of presets for the train step's hot GEMMs next to the all-features instantiation
+// (epi_preset_for() below): ncu had the epilogue warps of the generic code issue-bound at ~340 instructions per 32 x 32
+// chunk, longer than the K = 768 mainloop of the same tile (profiles/r02_gemm_epilogue.md).
+enum : uint32_t {
+  EF_BIAS = 1u, EF_RELU = 2u, EF_GELU = 4u, EF_ACT_BWD = 8u, EF_CE_GRAD = 16u, EF_DROP = 32u, EF_RESID = 64u,
+  EF_F32 = 128u, EF_BF16 = 256u, EF_ATOMIC = 512u, EF_ALL = 1023u
+};
+constexpr int kEpiPresets = 6;
+__host__ __device__ constexpr uint32_t epi_preset_mask(int i) {
+  return i == 0 ? (EF_BF16 | EF_DROP)                            // Q/K/V projections, plain dgrads
+       : i == 1 ? (EF_BF16 | EF_RELU | EF_DROP)                  // wi + ReLU (+ dropout)
+       : i == 2 ? (EF_F32 | EF_RESID | EF_DROP)                  // o / wo projections into the fp32 residual stream
+       : i == 3 ? (EF_BF16 | EF_ACT_BWD | EF_DROP)               // dgrad through ReLU / GELU (saved pre-activation)
+       : i == 4 ? (EF_F32 | EF_ATOMIC)                           // wgrad (split-K reduce-add) and plain fp32 outputs
+       : EF_ALL;
+}
+
+template <uint32_t F>
 __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, const EpiMaps& em, uint32_t taddr, int row0,
                                                         int lane, int col0, float alpha, uint8_t* stage, uint64_t* wbar,
                                                         uint32_t& wphase) {
@@ -281,22 +302,29 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
   tmem_ld32(taddr, v);
   const int row = row0 + lane;
   const bool in_rows = row < p.M;
-  const bool full = in_rows && col0 + 32 <= p.N;
-  const bool two_stores = p.act == 2 && p.pre_out;  // the staging tile is used for the pre-activation copy first
+  const bool out_f32 = !(F & EF_BF16) ? true : !(F & EF_F32) ? false : p.out_fp32 != 0;
+  const bool has_resid = (F & EF_RESID) && p.residual;
+  const bool act_bwd = (F & EF_ACT_BWD) && (p.act == 3 || p.act == 4);
+  const bool aux_tma = act_bwd && p.aux_tma;
+  const bool two_stores = (F & EF_GELU) && p.act == 2 && p.pre_out;  // the staging tile carries the pre-activation copy first
+  // dropout scale folded into alpha where everything between the two is linear or ReLU
+  constexpr bool kFoldDrop = (F & EF_DROP) && !(F & (EF_BIAS | EF_GELU | EF_CE_GRAD));
+  const uint32_t drop_p16 = (F & EF_DROP) ? p.drop_p16 : 0u;
+  if (kFoldDrop && drop_p16) alpha *= drop_scale(drop_p16);
   if (lane == 0) {
     bulk_wait_read0();  // the previous chunk's store has finished reading this staging tile
-    if (p.residual && !two_stores) {
+    if (has_resid && !two_stores) {
       mbar_arrive_expect_tx(wbar, 4096);
       tma_load_2d(stage, &em.resid, wbar, col0, row0);
-    } else if (p.aux_tma) {   // saved pre-activation block (bf16 32 x 32): whole lines instead of 32 scattered rows
+    } else if (aux_tma) {   // saved pre-activation block (bf16 32 x 32): whole lines instead of 32 scattered rows
       mbar_arrive_expect_tx(wbar, 2048);
       tma_load_2d(stage, &em.resid, wbar, col0, row0);
     }
   }
   __syncwarp();
   uint4 ax[4];
-  if ((p.act == 3 || p.act == 4) && !p.aux_tma) {
-    if (full) {
+  if (act_bwd && !aux_tma) {
+    if (in_rows && col0 + 32 <= p.N) {
       const uint4* ap = reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ld_aux + col0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) ax[j] = __ldg(ap + j);
@@ -316,7 +344,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
   tmem_ld_wait();
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] *= alpha;
-  if (p.bias) {
+  if ((F & EF_BIAS) && p.bias) {
     if (col0 + 32 <= p.N) {
       const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
@@ -341,23 +369,23 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
       tma_store_2d(&em.pre, stage, col0, row0);
       bulk_commit();
       bulk_wait_read0();
-      if (p.residual) {  // only now may the residual block land in the staging tile
+      if (has_resid) {  // only now may the residual block land in the staging tile
         mbar_arrive_expect_tx(wbar, 4096);
         tma_load_2d(stage, &em.resid, wbar, col0, row0);
       }
     }
     __syncwarp();
   }
-  if (p.act == 1) {
+  if ((F & EF_RELU) && p.act == 1) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-  } else if (p.act == 2) {
+  } else if ((F & EF_GELU) && p.act == 2) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.act == ACT_CE_GRAD) {
+  } else if ((F & EF_CE_GRAD) && p.act == ACT_CE_GRAD) {
     ce_grad_chunk(p, v, row, in_rows, col0);
-  } else if (p.act >= 3) {
-    if (p.aux_tma) {
+  } else if (act_bwd) {
+    if (aux_tma) {
       mbar_wait(wbar, wphase);
       wphase ^= 1;
 #pragma unroll
@@ -380,11 +408,12 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
       }
     }
   }
-  if (p.drop_p16) {
-    drop_apply<32>(v, drop_row_key(drop_salted(p.drop_seed, p.drop_salt), (unsigned long long)row), p.drop_p16, (uint32_t)col0,
-                   drop_scale(p.drop_p16));
+  if (drop_p16) {
+    const uint32_t key = drop_row_key(drop_salted(p.drop_seed, p.drop_salt), (unsigned long long)row);
+    if (kFoldDrop) drop_select<32>(v, key, drop_p16, (uint32_t)col0);
+    else drop_apply<32>(v, key, drop_p16, (uint32_t)col0, drop_scale(drop_p16));
   }
-  if (p.residual) {
+  if (has_resid) {
     mbar_wait(wbar, wphase);
     wphase ^= 1;
 #pragma unroll
@@ -393,7 +422,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
       v[g * 4 + 0] += r.x; v[g * 4 + 1] += r.y; v[g * 4 + 2] += r.z; v[g * 4 + 3] += r.w;
     }
   }
-  if (p.out_fp32) {
+  if (out_f32) {
 #pragma unroll
     for (int g = 0; g < 8; ++g)
       *reinterpret_cast<float4*>(stage + epi_off_f32(lane, g)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
@@ -406,11 +435,31 @@ __device__ __forceinline__ void gemm_epilogue_chunk_tma(const GemmParams& p, con
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0 && !(p.dbg & 2)) {
-    if (p.atomic) tma_reduce_add_2d(&em.out, stage, col0, row0);
+  if (lane == 0) {
+    if ((F & EF_ATOMIC) && p.atomic) tma_reduce_add_2d(&em.out, stage, col0, row0);
     else tma_store_2d(&em.out, stage, col0, row0);
     bulk_commit();
   }
+}
+
+// Feature bits one call needs, and the first (narrowest) preset that covers them.
+inline uint32_t epi_features(const vc_gemm_args* a) {
+  uint32_t f = a->out_fp32 ? EF_F32 : EF_BF16;
+  if (a->bias) f |= EF_BIAS;
+  if (a->act == 1) f |= EF_RELU;
+  if (a->act == 2) f |= EF_GELU;
+  if (a->act == 3 || a->act == 4) f |= EF_ACT_BWD;
+  if (a->act == ACT_CE_GRAD) f |= EF_CE_GRAD;
+  if (a->drop_p16) f |= EF_DROP;
+  if (a->residual) f |= EF_RESID;
+  if (a->atomic) f |= EF_ATOMIC;
+  return f;
+}
+inline int epi_preset_for(const vc_gemm_args* a) {
+  const uint32_t need = epi_features(a);
+  for (int i = 0; i < kEpiPresets; ++i)
+    if ((need & ~epi_preset_mask(i)) == 0) return i;
+  return kEpiPresets - 1;
 }
 
 // act-backward GEMMs (no residual): the `resid` map slot carries the bf16 `aux` matrix instead.
