@@ -98,6 +98,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int k0 = kt * kBT;
 
+  if (threadIdx.x == 0) VC_TRACE(1900, 200);
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) __trap();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
@@ -110,39 +111,89 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     fence_barrier_init();
   }
   const int nqt_all = (p.Lq + kBT - 1) / kBT;
+  const int qt0 = p.causal ? min(kt, nqt_all) : 0;  // causal: query tiles before the key tile see nothing of it
   if (threadIdx.x < 51) s_nonuni_v[threadIdx.x] = 0;   // (all flag arrays)
   if (threadIdx.x == 51) *s_last_key = -1;
+  if (warp == 1) tmem_alloc(tmem_slot, 512);   // before the dependency wait: touches no global memory
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
   pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is read from here on
   pdl_trigger();
+  if (threadIdx.x == 0) VC_TRACE(1901, 201);
+  // The key/value tile and the first query tile are requested BEFORE the mask / bias set-up below, so their L2 latency
+  // runs underneath it (with only two query tiles per CTA — cross-attention — the set-up was ~half of the CTA's life).
+  // Every CTA has at least one query tile unless the causal mask hides them all (qt0 == nqt_all).
+  const bool early_q = qt0 < nqt_all;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(kv_full, 32768);
+    tma_load_3d(sK, &tmK, kv_full, p.k_col + h * kBD, k0, b);
+    tma_load_3d(sV, &tmV, kv_full, p.v_col + h * kBD, k0, b);
+    if (early_q) {
+      mbar_arrive_expect_tx(&qd_full[0], 32768);
+      tma_load_3d(sQ, &tmQ, &qd_full[0], p.q_col + h * kBD, qt0 * kBT, b);
+      tma_load_3d(sDO, &tmDO, &qd_full[0], p.do_col + h * kBD, qt0 * kBT, b);
+    }
+  }
   const int n_rel = p.Lq + kBT;  // relative positions touched by this CTA: (k - q + Lq - 1) - rel_base in [0, Lq+127)
   const int rel_base = k0;       // slot = (k - k0) + (Lq - 1 - q)
-  if (p.dbias_rel) {
-    for (int i = threadIdx.x; i < kBwdRelMax; i += blockDim.x) s_rel[i] = 0.f;
-    for (int i = threadIdx.x; i < 16 * 24; i += blockDim.x) s_tsum[i] = 0.f;
-  }
-  {  // always filled + padded so the per-element loop below is branch-free (see attn_fwd.cu)
+  // Set-up by the compute warps only (threads 64..): warp 0's elected thread is busy issuing the loads above and the
+  // CTA-wide barrier below waits for the slowest thread.  The mask bytes are requested before anything is stored so the
+  // global round trips overlap.
+  const int su = (int)threadIdx.x - 64, sn = (int)blockDim.x - 64;
+  if (su >= 0) {
+    const unsigned char* km = p.kmask ? p.kmask + (long long)b * p.Lk : nullptr;
+    unsigned char my_key = 1;
+    if (su < 128 && km && k0 + su < p.Lk) my_key = km[k0 + su];
+    int last = -1;
+    if (km && !p.causal) {
+      for (int i = su; i < p.Lk; i += sn)
+        if (km[i] != 0) last = i;
+    }
+    const bool row0_att = (km && p.causal && su == 0) ? km[0] != 0 : false;
+    if (p.dbias_rel) {
+      for (int i = su; i < kBwdRelMax; i += sn) s_rel[i] = 0.f;
+      for (int i = su; i < 16 * 24; i += sn) s_tsum[i] = 0.f;
+    }
+    // always filled + padded so the per-element loop below is branch-free (see attn_fwd.cu)
     const float* brow_g = p.bias_rel ? p.bias_rel + (long long)h * (p.Lq + p.Lk - 1) : nullptr;
     const int n_pad = ((p.Lq + kBT - 1) / kBT) * kBT + kBT;  // covers slot (k-k0) + (Lq-1-q) for every q of every tile
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
+    for (int i = su; i < n_pad; i += sn)
       s_bias[i] = (brow_g && rel_base + i < p.Lq + p.Lk - 1) ? __ldg(brow_g + rel_base + i) * kBLog2e : 0.f;
-    if (threadIdx.x < 128) {
-      const int k = k0 + (int)threadIdx.x;
-      const float pen = (k >= p.Lk) ? -INFINITY : ((p.kmask && p.kmask[(long long)b * p.Lk + k] == 0) ? kBMasked : INFINITY);
-      s_pen[threadIdx.x] = pen;
+    if (su < 128) {
+      const int k = k0 + su;
+      const float pen = (k >= p.Lk) ? -INFINITY : (my_key == 0 ? kBMasked : INFINITY);
+      s_pen[su] = pen;
       if (pen != INFINITY) *s_anypen = 1;
       else *s_tile_att = 1;
     }
-    if (!p.kmask) {
-      if (threadIdx.x == 0) *s_row_att = 1;
+    if (!km) {
+      if (su == 0) *s_row_att = 1;
     } else if (p.causal) {
-      if (threadIdx.x == 0 && p.kmask[(long long)b * p.Lk] != 0) *s_row_att = 1;
+      if (row0_att) *s_row_att = 1;
     } else {
-      int last = -1;
-      for (int i = threadIdx.x; i < p.Lk; i += blockDim.x)
-        if (p.kmask[(long long)b * p.Lk + i] != 0) last = i;
       last = __reduce_max_sync(0xffffffffu, last);
       if (lane == 0 && last >= 0) { *s_row_att = 1; atomicMax(s_last_key, last); }
+    }
+  }
+  // Uniform-tile flags.  Query tile t touches window slots [max(w0,0), w0+254], w0 = Lq-128-128t.  With T5's buckets every
+  // tile further than 128 positions from the diagonal sees ONE bias value (one bucket): s2 = acc*scale + c without any
+  // per-element lookup, and d(bias) of the tile is one sum instead of 255 diagonal sums.  (Read from global memory, not
+  // from s_bias, so that the set-up needs a single CTA-wide barrier; without a bias every tile is uniform.)
+  if (p.bias_rel) {
+    const float* brow_g = p.bias_rel + (long long)h * (p.Lq + p.Lk - 1);
+    const int lim = p.Lq + p.Lk - 1;
+    for (int idx = su; idx >= 0 && idx < nqt_all * 256; idx += sn) {
+      const int t = idx >> 8, w0 = p.Lq - kBT - t * kBT;
+      const int i = max(w0, 0) + 1 + (idx & 255);
+      if (i <= w0 + 254) {
+        const int gi = rel_base + i;
+        const float b1 = gi < lim ? __ldg(brow_g + gi) : 0.f, b0 = gi - 1 < lim ? __ldg(brow_g + gi - 1) : 0.f;
+        if (b1 != b0) s_nonuni_v[t] = 1;
+        if (p.dbias_rel) {
+          if (!p.bucket_lut || gi >= lim || __ldg(p.bucket_lut + gi) != __ldg(p.bucket_lut + gi - 1)) s_nonuni_b[t] = 1;
+        }
+      }
     }
   }
   __syncthreads();
@@ -155,41 +206,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint4* d2 = reinterpret_cast<uint4*>(p.dk + ((long long)b * p.Lk + kk) * p.ld_dk + p.dk_col + h * kBD + half * 32);
       for (int g = 0; g < 4; ++g) { d1[g] = make_uint4(0, 0, 0, 0); d2[g] = make_uint4(0, 0, 0, 0); }
     }
+    if (threadIdx.x == 0) {   // the early loads must have landed before this CTA's shared memory is given away
+      mbar_wait(kv_full, 0);
+      if (early_q) mbar_wait(&qd_full[0], 0);
+    }
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc(*tmem_slot, 512);
+    }
     return;
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  // Uniform-tile flags.  Query tile t touches window slots [max(w0,0), w0+254], w0 = Lq-128-128t.  With T5's buckets every
-  // tile further than 128 positions from the diagonal sees ONE bias value (one bucket): s2 = acc*scale + c without any
-  // per-element lookup, and d(bias) of the tile is one sum instead of 255 diagonal sums.
-  for (int idx = threadIdx.x; idx < nqt_all * 256; idx += blockDim.x) {
-    const int t = idx >> 8, w0 = p.Lq - kBT - t * kBT;
-    const int i = max(w0, 0) + 1 + (idx & 255);
-    if (i <= w0 + 254) {
-      if (s_bias[i] != s_bias[i - 1]) s_nonuni_v[t] = 1;
-      if (p.dbias_rel) {
-        const int gi = rel_base + i;
-        if (!p.bucket_lut || gi >= p.Lq + p.Lk - 1 || __ldg(p.bucket_lut + gi) != __ldg(p.bucket_lut + gi - 1)) s_nonuni_b[t] = 1;
-      }
-    }
-  }
-  __syncthreads();
+  if (threadIdx.x == 0) VC_TRACE(1902, 202);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320, tDQ = tmem_base + 384;
 
-  const int qt0 = p.causal ? min(kt, nqt_all) : 0;  // causal: query tiles before the key tile see nothing of it
   // q_like_k: query rows past the sequence's last token are padding whose upstream gradient is exactly zero (nothing
   // downstream can observe them), so their tiles add nothing to dK / dV / d(bias) and their dQ stays zero: skip them
   const int nqt_end = (p.q_like_k && *s_last_key >= 0) ? min(nqt_all, *s_last_key / kBT + 1) : nqt_all;
   const int nqt = max(nqt_end - qt0, 0);
 
   if (warp == 0 && lane == 0) {
-    mbar_arrive_expect_tx(kv_full, 32768);
-    tma_load_3d(sK, &tmK, kv_full, p.k_col + h * kBD, k0, b);
-    tma_load_3d(sV, &tmV, kv_full, p.v_col + h * kBD, k0, b);
-    for (int i = 0; i < nqt; ++i) {
+    for (int i = 1; i < nqt; ++i) {   // (tile 0 and K/V were requested at the top)
       const int st = i & 1;
       mbar_wait(&qd_empty[st], ((i >> 1) & 1) ^ 1);
       mbar_arrive_expect_tx(&qd_full[st], 32768);
@@ -201,6 +238,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr uint32_t id_t = make_idesc_bf16(128, 64, 1, 1);    // dV, dK: A MN-major (P^T / dS^T), B MN-major, N=64
     constexpr uint32_t id_q = make_idesc_bf16(128, 64, 0, 1);    // dQ    : A K-major (dS), B MN-major (K), N=64
     mbar_wait(kv_full, 0);
+    VC_TRACE(1903, 203);
     const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK), 0, 1024);
     const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV), 0, 1024);
     // Software pipeline: S/dP of tile i+1 are issued BEFORE dV/dK/dQ of tile i (the score buffers are free as soon as the
@@ -463,10 +501,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       stage_dq(nqt - 1);
     }
-    if (NCW == 16 ? lane == 0 : ct == 0) bulk_wait_all();
-    // ---- dV, dK: rows = keys of this tile, stored by warps 2..9.  (Their last dq_full wait also covers the final dV/dK MMAs.)
+    if (warp == 2 && lane == 0) VC_TRACE(1904, 204);
+    // ---- dV, dK: rows = keys of this tile.  (The last dq_full wait also covers the final dV/dK MMAs.)  16 compute warps:
+    // every warp stores its 32 rows x 16 columns of both; 8 warps: warps 2..9 store 32 columns each.
     const int kk = k0 + r;
-    if (!io_warp) {
+    if (NCW == 16 && nqt > 0) {
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        __nv_bfloat16* base = which == 0 ? p.dv : p.dk;
+        const long long ld = which == 0 ? p.ld_dv : p.ld_dk;
+        const int col = which == 0 ? p.dv_col : p.dk_col;
+        float v[16];
+        tmem_ld16((which == 0 ? tDV : tDK) + lane_off + part * 16, v);
+        tmem_ld_wait();
+        if (which == 0 && p.drop_p16) {   // dropout scale of the probabilities, applied once per output instead of per element
+#pragma unroll
+          for (int g = 0; g < 16; ++g) v[g] *= drop_sc;
+        }
+        if (kk < p.Lk) {
+          uint4* dst = reinterpret_cast<uint4*>(base + ((long long)b * p.Lk + kk) * ld + col + h * kBD + part * 16);
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            dst[g] = make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+        }
+      }
+    } else if (!io_warp) {
     } else if (nqt > 0) {
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
@@ -497,8 +557,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int g = 0; g < 4; ++g) dst[g] = make_uint4(0, 0, 0, 0);
       }
     }
+    // the dQ staging blocks only have to be READ by the TMA unit before the CTA exits (the adds complete with the grid);
+    // waited for here, after the dV/dK stores, so that the two overlap
+    if (NCW == 16 ? lane == 0 : ct == 0) bulk_wait_read0();
   }
 
+  if (warp == 2 && lane == 0) VC_TRACE(1905, 205);
   tc_fence_before();
   __syncthreads();
   if (p.dbias_rel && threadIdx.x < nqt_all) {   // one-bucket tiles: total of the 16 warps -> the tile's slot (k = k0, q = q0)
@@ -519,6 +583,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (threadIdx.x == 0) VC_TRACE(1906, 206);
 }
 
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (the "D" term of the softmax backward)
