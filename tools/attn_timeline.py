@@ -59,7 +59,7 @@ bw()
 torch.cuda.synchronize()
 ops.lib.vc_debug_set_trace(None)
 t = trace.cpu().tolist()
-ev = [(v >> 48, v & 0xFFFFFFFFFFFF, i) for i, v in enumerate(t) if v]
+ev = [(v >> 48, v & 0xFFFFFFFFFFFF, i) for i, v in enumerate(t) if v and (v >> 48) < 200]   # (CTA-life events: attn_bwd_cta_life.py)
 t0 = min(e[1] for e in ev)
 names = {7: "tile_sum done", 8: "  dq: tmem ld ok", 9: "  dq: sts+fence", 10: "  dq: tma issued", 1: "iter top", 2: "s_full ok", 3: "math+pack done", 4: "dq_full(i-1) ok", 5: "stores+arrive pds", 6: "dQ(i-1) staged",
          100: "mma: wait pds", 101: "mma: pds ok", 102: "mma: scores(i+1) issued", 103: "mma: dq_read ok", 104: "mma: dV/dK/dQ issued"}
