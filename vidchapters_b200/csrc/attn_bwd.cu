@@ -677,11 +677,10 @@ extern "C" int vc_attn_bwd(const vc_attn_bwd_args* a, void* stream) {
   p.q_like_k = f->q_like_k;
   p.trace = debug_trace_ptr();
   VC_CHECK(!f->q_like_k || (f->Lq == f->Lk && f->kmask && !f->causal), "vc_attn_bwd: q_like_k needs non-causal self-attention with a key mask");
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.need()) {
     VC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
     VC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
-    attr = true;
   }
   dim3 grid((f->Lk + kBT - 1) / kBT, f->H, f->B);
   if (ncw == 8) VC_CUDA(launch_kernel(attn_bwd_kernel<8>, grid, dim3(320), (size_t)kAttnBwdSmem, st, tmQ, tmK, tmV, tmDO, tmDQ, p));

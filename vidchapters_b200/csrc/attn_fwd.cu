@@ -396,11 +396,10 @@ extern "C" int vc_attn_fwd(const vc_attn_args* a, void* stream) {
   const int lk_pad = ((a->Lk + kTK - 1) / kTK) * kTK;
   VC_CHECK(a->scale > 0.f, "vc_attn_fwd: scale must be positive");
   const int smem_bytes = kAttnFwdTiles + (lk_pad + 128) * 4 + lk_pad * 4 + kAttnFwdTail;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.need()) {
     VC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kAttnFwdTiles + (kAttnMaxLk + 128) * 4 + kAttnMaxLk * 4 + kAttnFwdTail));
-    attr = true;
   }
   dim3 grid((a->Lq + kTQ - 1) / kTQ, a->H, a->B);
   VC_CUDA(launch_kernel(attn_fwd_kernel, grid, dim3(320), (size_t)smem_bytes, st, tmQ, tmK, tmV, p));

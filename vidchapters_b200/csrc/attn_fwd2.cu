@@ -435,10 +435,9 @@ int launch_attn_fwd_pair(const vc_attn_args* a, cudaStream_t st) {
   p.trace = debug_trace_ptr();
   VC_CHECK(a->Lk <= kP2MaxLk, "vc_attn_fwd: Lk=%d exceeds the %d keys the bias/mask staging supports", a->Lk, kP2MaxLk);
   const int lk_pad = ((a->Lk + kP2TK - 1) / kP2TK) * kP2TK;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.need()) {
     VC_CUDA(cudaFuncSetAttribute(attn_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_fwd2_smem(kP2MaxLk)));
-    attr = true;
   }
   dim3 grid((a->Lq + 2 * kP2TQ - 1) / (2 * kP2TQ), a->H, a->B);
   VC_CUDA(launch_kernel(attn_fwd_pair_kernel, grid, dim3(576), (size_t)attn_fwd2_smem(lk_pad), st, tmQ, tmK, tmV, p));

@@ -40,6 +40,19 @@ int make_tmap_2d_ex(CUtensorMap* out, const void* base, int elt_bytes, uint64_t 
 
 int num_sms();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: a process that launches on cuda:1 after cuda:0 must
+// set it again there (a single static flag made the first >48 KB launch on the second device fail with "invalid argument").
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // Programmatic dependent launch for every kernel of the library (VIDCHAP_PDL=0 turns it off for A/B runs); see
 // ptx.cuh::pdl_wait.  Inside stream capture the attribute becomes a programmatic dependency edge of the CUDA graph.
 bool pdl_enabled();

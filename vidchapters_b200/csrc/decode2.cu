@@ -305,10 +305,9 @@ int launch_attn_decode(const vc_attn_args* a, cudaStream_t st) {
   p.scale_log2e = a->scale * kDLog2e;
   p.q_offset = a->q_offset; p.q_offset_dev = a->q_offset_dev;
   VC_CHECK(a->Lk <= 12000, "vc_attn_fwd (decode): Lk=%d exceeds the score staging", a->Lk);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.need()) {
     VC_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48000));
-    attr = true;
   }
   VC_CUDA(launch_kernel(attn_decode_kernel, dim3(a->H, a->B), dim3(256), (size_t)a->Lk * 4, st, p));
   VC_CUDA(cudaGetLastError());
@@ -333,10 +332,9 @@ extern "C" int vc_decode_linear(const void* A, int64_t lda, int a_fp32, const fl
   p.W = (const __nv_bfloat16*)W; p.ldw = ldw; p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32;
   p.residual = residual; p.ldr = ldr; p.relu = relu; p.M = M; p.N = N; p.K = K;
   const size_t smem = (size_t)(64 + 16) * kDLStride * 2;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.need()) {
     VC_CUDA(cudaFuncSetAttribute(decode_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   VC_CUDA(launch_kernel(decode_linear_kernel, dim3((N + 15) / 16, (M + 63) / 64), dim3(512), smem, reinterpret_cast<cudaStream_t>(stream), p));
   VC_CUDA(cudaGetLastError());

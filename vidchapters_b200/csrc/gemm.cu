@@ -207,10 +207,9 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const E
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, TMA_EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   VC_CUDA(launch_kernel(kern, dim3(grid), dim3(384), Cfg::kSmemBytes, st, tmA, tmB, em, p));
   VC_CUDA(cudaGetLastError());

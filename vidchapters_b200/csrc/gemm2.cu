@@ -279,10 +279,9 @@ static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                         cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, TMA_EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     VC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
   }
   VC_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(kThreads2), Cfg::kSmemBytes, st, tmA, tmB, em, p));
   VC_CUDA(cudaGetLastError());

@@ -320,11 +320,10 @@ static cudaError_t launch_norm_bwd_wide(cudaStream_t st, const void* g, const fl
                                         uint32_t p1) {
   auto kern = norm_bwd_wide_kernel<NV, LN, GB>;
   const int smem = (LN ? 2 : 1) * 8 * NV * 32 * (int)sizeof(float4);
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;  // per instantiation
+  if (attr_done.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   // whole rows per warp, balanced: every warp of the grid gets the same number of rows (+-1 on the last CTA)
   const int blocks = (M + 7) / 8, cap = num_sms() * 2;
