@@ -85,7 +85,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.t_mark = gpu_index, [], None, 0.0
+
+    def mark(self):
+        """Start of the timed region: only samples read after this count.  (The sampler itself is started BEFORE the
+        warm-up: nvidia-smi's start-up enumerates the devices under the driver lock and stalled the first timed
+        generate() call — which allocates, captures and instantiates a graph — by up to seconds when it overlapped.)"""
+        self.t_mark = time.time()
 
     def start(self):
         try:
@@ -98,11 +104,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
+        self.rows = [r for t, r in self.rows if t >= self.t_mark]
         sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -332,11 +339,12 @@ def run_train(args):
     ms_eager, _ = D.timed(lambda: eager_step(True, True), n_eager)
     # graphed public API (GraphedTrainStep): forward+backward replayed as CUDA graph(s), optimiser tail eager
     gstep = GraphedTrainStep(model, opt, video_d, inp_d, out_d, warmup_steps=0)
-    for _ in range(args.warmup):
-        gstep(video_h, inp_h, out_h).item()
     sampler = ClockSampler(D.local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        gstep(video_h, inp_h, out_h).item()
+    sampler.mark()
     launches0 = ops.launches
     ms_dev, loss_dev = D.timed(lambda: gstep(), args.steps)                                    # inputs resident in HBM
     launches = ops.launches - launches0
@@ -474,11 +482,12 @@ def run_decode(args):
 
     args.warmup = max(args.warmup, 3)
     steps = min(args.steps, 5)
-    for _ in range(args.warmup):
-        gen_dev()
     sampler = ClockSampler(D.local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        gen_dev()
+    sampler.mark()
     launches0 = ops.launches
     ms_dev, ids = D.timed(gen_dev, steps)
     launches = ops.launches - launches0

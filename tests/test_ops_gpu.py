@@ -467,6 +467,37 @@ def test_dropout_gemm_epilogue(cuda_ops, torch_ops):
         assert 0.05 < zeros < 0.6   # ~10% dropped (more with relu)
 
 
+@pytest.mark.parametrize("preset", ["plain_bf16", "relu_bf16", "resid_f32", "relu_bwd_bf16", "gelu_bwd_bf16", "plain_f32"])
+@pytest.mark.parametrize("drop", [False, True])
+def test_gemm_epilogue_presets(cuda_ops, torch_ops, preset, drop):
+    """The pair kernel's narrow epilogue instantiations (gemm_common.cuh epi_preset_mask): each call below needs only
+    the features of one preset, so the host picks it instead of the all-features path the other epilogue tests take."""
+    M, N, K = 1000, 1536, 768          # M >= 256: CTA-pair kernel; ragged last row block
+    g = gen(31)
+    A = (torch.randn(M, K, generator=g) * 0.3).to(DEV).bfloat16()
+    B = (torch.randn(N, K, generator=g) * 0.3).to(DEV).bfloat16()
+    resid = torch.randn(M, N, generator=g).to(DEV)
+    aux = torch.randn(M, N, generator=g).to(DEV).bfloat16()
+    bf = preset.endswith("bf16")
+    kw = dict(drop=DROP) if drop else {}
+    if preset == "relu_bf16":
+        kw.update(act=1)
+    elif preset == "resid_f32":
+        kw.update(residual=resid, alpha=0.5)
+    elif preset == "relu_bwd_bf16":
+        kw.update(act=3, aux=aux)
+    elif preset == "gelu_bwd_bf16":
+        kw.update(act=4, aux=aux)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16 if bf else torch.float32)
+    ref = torch.empty_like(out)
+    cuda_ops.gemm(A, B, out, **kw)
+    torch_ops.gemm(A, B, ref, **kw)
+    assert rel(out, ref) < (BF16_TOL if bf else 1e-4)
+    if drop and preset != "resid_f32":
+        zeros = (out.float().abs() < 1e-12).float().mean().item()
+        assert 0.05 < zeros < 0.65   # ~10 % dropped (about half more behind ReLU / its gradient)
+
+
 @pytest.mark.parametrize("case", [ATTN_CASES[1], ATTN_CASES[2], ATTN_CASES[4], ATTN_CASES[7]])
 def test_dropout_attention(cuda_ops, torch_ops, case):
     B, H, Lq, Lk, causal, wb, wm, scale, sa = case

@@ -58,7 +58,8 @@ struct AttnBwdParams {
 constexpr int kBwdSmemTiles = 16384 * 2 /*K,V*/ + 2 * 16384 /*Q ring*/ + 2 * 16384 /*dO ring*/ + 32768 /*P*/ + 32768 /*dS*/;
 constexpr int kBwdRelMax = 2304;  // floats per relative-position window: ceil(Lq/128)*128 + 128 <= 2304 (Lq <= 2176)
 constexpr int kBwdTsum = 16 * 24 * 4;   // per compute warp x query tile: d(bias) total of a one-bucket tile
-constexpr int kAttnBwdSmem = kBwdSmemTiles + 32768 + 2 * kBwdRelMax * 4 + 512 + 512 + kBwdTsum;  // + dQ staging + d(bias)/bias windows + key ceilings
+constexpr int kBwdStat = 2 * 512 * 8;   // per compute thread x 2 stages: (lse2, delta) of its query row
+constexpr int kAttnBwdSmem = kBwdSmemTiles + 32768 + 2 * kBwdRelMax * 4 + 512 + 512 + kBwdTsum + kBwdStat;  // + dQ staging + d(bias)/bias windows + key ceilings
 
 template <int NCW>   // compute warps: 8 (two 32-column chunks of the tile per thread) or 16 (one chunk per thread)
 __global__ void __launch_bounds__(64 + NCW * 32, 1)
@@ -93,6 +94,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   int* s_row_att = s_anypen + 2;                          // [1] some key of this batch row attends (causal: key 0 does)
   int* s_last_key = s_anypen + 3;                         // [1] last attended key of this batch row (q_like_k), -1: none
   float* s_tsum = reinterpret_cast<float*>(bars + 64);    // [16 warps][24 query tiles]
+  float2* s_stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(s_tsum) + kBwdTsum);   // [2][512]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -353,27 +355,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_read);
     };
-    // per-row statistics of the next query tile are fetched one tile ahead (their L2 latency was 14 % of the kernel's
-    // stall samples when loaded at the top of the tile, profiles/r02_attn_source_counters.md)
-    float lse2_n = INFINITY, delta_n = 0.f;
-    if (nqt > 0) {
-      const int qn = qt0 * kBT + r;
-      const long long si = ((long long)b * p.H + h) * p.Lq + (qn < p.Lq ? qn : 0);
-      lse2_n = qn < p.Lq ? p.lse2[si] : INFINITY;
-      delta_n = p.delta[si];
-    }
+    // Per-row statistics (lse2, delta) of the next query tile are fetched one tile ahead — their L2 latency was 14 % of
+    // the kernel's stall samples when loaded at the top of the tile (profiles/r02_attn_source_counters.md) — and by
+    // cp.async into the thread's own shared-memory slot: held in registers across a tile, ptxas (96 registers at 576
+    // threads) spilled them right behind the load, which waits for the load after all (~800 cycles per tile).
+    auto fetch_stats = [&](int tile_q0, int slot) {
+      const int qn = tile_q0 + r;
+      float* dst = reinterpret_cast<float*>(&s_stat[slot * 512 + ct]);
+      if (qn < p.Lq) {
+        const long long si = ((long long)b * p.H + h) * p.Lq + qn;
+        cp_async4(dst, p.lse2 + si);
+        cp_async4(dst + 1, p.delta + si);
+      } else {
+        dst[0] = INFINITY;   // rows past Lq: p = exp2(-inf) = 0
+        dst[1] = 0.f;
+      }
+      cp_async_commit();
+    };
+    if (nqt > 0) fetch_stats(qt0 * kBT, 0);
     for (int i = 0; i < nqt; ++i) {
       const int q0 = (qt0 + i) * kBT;
       const int q = q0 + r;
       const bool q_ok = q < p.Lq;
-      const float lse2 = lse2_n;          // rows past Lq: p = exp2(-inf) = 0
-      const float delta = delta_n;
-      if (i + 1 < nqt) {
-        const int qn = q + kBT;
-        const long long si = ((long long)b * p.H + h) * p.Lq + (qn < p.Lq ? qn : 0);
-        lse2_n = qn < p.Lq ? p.lse2[si] : INFINITY;
-        delta_n = p.delta[si];
-      }
+      cp_async_wait_all();
+      const float2 stat = s_stat[(i & 1) * 512 + ct];
+      const float lse2 = stat.x;
+      const float delta = stat.y;
+      if (i + 1 < nqt) fetch_stats(q0 + kBT, (i + 1) & 1);
       // indexed by k - k0; rows past Lq (zero-filled Q/dO, p forced to 0) clamp to slot 0 to stay inside the window
       const float* brow = s_bias + (q_ok ? (p.Lq - 1 - q) : 0);
       const bool causal_tile = p.causal && (k0 + kBT - 1 > q0);

@@ -54,13 +54,11 @@ __global__ void __launch_bounds__(256, 3) attn_decode_kernel(const AttnDecParams
   const int qpos = p.q_offset + (p.q_offset_dev ? __ldg(p.q_offset_dev) : 0);
   const int nk = p.causal ? min(p.Lk, qpos + 1) : p.Lk;          // causal: keys past the query do not exist yet
   const long long kvb = (long long)(b / p.kv_batch_div) * p.kv_batch_rows;
-  // q (64 bf16 = 8 x uint4), kept packed; every thread needs all of it
-  uint4 qv[8];
-  {
-    const uint4* qp = reinterpret_cast<const uint4*>(p.q + (long long)b * p.ldq + p.q_col + h * 64);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qv[i] = __ldg(qp + i);
-  }
+  // q (64 bf16 = 8 x uint4): every thread needs all of it — read as shared-memory broadcasts (held in 32 registers per
+  // thread next to two keys' worth of loads, the loop spilled at the 80 registers that 3 CTAs per SM allow)
+  __shared__ uint4 s_q[8];
+  if (tid < 8) s_q[tid] = __ldg(reinterpret_cast<const uint4*>(p.q + (long long)b * p.ldq + p.q_col + h * 64) + tid);
+  __syncthreads();
   const float* brow = p.bias_rel ? p.bias_rel + (long long)h * p.bias_len + (p.bias_zero - qpos) : nullptr;
   const uint8_t* mrow = p.kmask ? p.kmask + (long long)b * p.Lk : nullptr;
   float m_loc = -INFINITY;
@@ -70,8 +68,8 @@ __global__ void __launch_bounds__(256, 3) attn_decode_kernel(const AttnDecParams
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const uint4 kk = __ldg(kp + i);
-      const uint32_t a[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w}, c[4] = {kk.x, kk.y, kk.z, kk.w};
+      const uint4 kk = __ldg(kp + i), qq = s_q[i];
+      const uint32_t a[4] = {qq.x, qq.y, qq.z, qq.w}, c[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc = fmaf(bf16_lo(a[e]), bf16_lo(c[e]), fmaf(bf16_hi(a[e]), bf16_hi(c[e]), acc));
     }
@@ -103,11 +101,12 @@ __global__ void __launch_bounds__(256, 3) attn_decode_kernel(const AttnDecParams
 #pragma unroll
   for (int w = 0; w < 8; ++w) l += s_red[w];
   // phase 3: lane l = (key sub-index l / 8, dims 8 (l % 8) .. +8): a warp instruction reads FOUR 128-byte V rows; warp w
-  // walks keys 4 (w + 8 i) + l / 8.  Unrolled x4: 16 rows = 2 KB per warp in flight (the loop is pure HBM latency).
+  // walks keys 4 (w + 8 i) + l / 8.  Unrolled x8: 32 rows = 4 KB per warp, 96 KB per SM in flight (the loop is pure HBM
+  // latency; at x4 the V pass ran at about half the bandwidth of the K pass).
   float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int ksub = lane >> 3, dsub = (lane & 7) * 8;
   const __nv_bfloat16* vbase = p.v + kvb * p.ldv + p.v_col + h * 64 + dsub;
-#pragma unroll 4
+#pragma unroll 8
   for (int k = warp * 4 + ksub; k < nk; k += 32) {
     const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vbase + (long long)k * p.ldv));
     const float pk = s_sc[k];
@@ -164,31 +163,40 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+template <int NT>   // n8 tiles per CTA: 2 (16 output columns) or 4 (32: when N / 16 CTAs would not fit the machine in one wave)
 __global__ void __launch_bounds__(512) decode_linear_kernel(const DecLinParams p) {
   extern __shared__ __align__(16) uint8_t dl_smem[];
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(dl_smem);            // [64][kDLStride]
-  __nv_bfloat16* sW = sA + 64 * kDLStride;                                  // [16][kDLStride]
+  __nv_bfloat16* sW = sA + 64 * kDLStride;                                  // [8 * NT][kDLStride]
   pdl_wait();
   pdl_trigger();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n0 = blockIdx.x * 16, m0 = blockIdx.y * 64;
+  constexpr int NC = 8 * NT;
+  const int n0 = blockIdx.x * NC, m0 = blockIdx.y * 64;
   const int rows = min(64, p.M - m0);
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float acc[NT][4];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
   // The kernel is pure latency (a few MB per launch): 512 threads stage the operands with every load of a round issued
   // before the first use — ONE round for the 16 weight rows, one (bf16 input) or two (fp32 + norm) for the 64 input rows —
   // then warps 0..3 run the tensor-core loop.
-  for (int kc = 0; kc < p.K; kc += kDLKC) {
+  // gridDim.z > 1 (split-K, in-place residual layers with K > 1024): this CTA takes ONE 1024-wide chunk of K and adds its
+  // partial sums onto the fp32 stream with atomics — 3x the CTAs for the K = 3072 projection that ran on 48 of 148 SMs.
+  const bool split = gridDim.z > 1;
+  const int kc_begin = split ? (int)blockIdx.z * kDLKC : 0;
+  const int kc_end = split ? min(p.K, kc_begin + kDLKC) : p.K;
+  for (int kc = kc_begin; kc < kc_end; kc += kDLKC) {
     const int kw = min(kDLKC, p.K - kc);
-    if (kc > 0) __syncthreads();
-    uint4 wv[4];     // 16 rows x (kw / 8 <= 128) uint4 = <= 2048 -> 4 per thread
-    {
+    if (kc > kc_begin) __syncthreads();
+    {   // the CTA's weight rows go straight to shared memory (cp.async: no registers held across the input staging)
       const int nv = kw / 8;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = tid + 512 * j, r = i / nv, c = i % nv;
-        wv[j] = (i < 16 * nv && n0 + r < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.W + (long long)(n0 + r) * p.ldw + kc) + c)
-                                              : make_uint4(0, 0, 0, 0);
+      for (int i = tid; i < NC * nv; i += 512) {
+        const int r = i / nv, c = i % nv;
+        const bool ok = n0 + r < p.N;
+        cp_async16(sW + r * kDLStride + c * 8, reinterpret_cast<const uint4*>(p.W + (long long)(ok ? n0 + r : 0) * p.ldw + kc) + c,
+                   ok ? 16u : 0u);
       }
+      cp_async_commit();
     }
     if (p.a_fp32) {
       // warp w owns rows 4w .. 4w+3 (two at a time): lane holds columns lane + 32 i of each row, so the RMS statistic is a
@@ -246,38 +254,41 @@ __global__ void __launch_bounds__(512) decode_linear_kernel(const DecLinParams p
         if (i < 64 * nv) *reinterpret_cast<uint4*>(sA + r * kDLStride + c * 8) = v[j];
       }
     }
-    {
-      const int nv = kw / 8;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = tid + 512 * j, r = i / nv, c = i % nv;
-        if (i < 16 * nv) *reinterpret_cast<uint4*>(sW + r * kDLStride + c * 8) = wv[j];
-      }
-    }
+    cp_async_wait_all();
     __syncthreads();
     if (warp >= 4) continue;
     // ---- warp w: rows 16w..16w+15, all 16 columns: per k16 step one A fragment (x4) and both B fragments (x4)
     const uint32_t a_base = smem_u32(sA + (warp * 16 + (lane & 15)) * kDLStride + (lane >> 4) * 8);
     const uint32_t b_base = smem_u32(sW + ((lane & 7) + ((lane >> 4) << 3)) * kDLStride + ((lane >> 3) & 1) * 8);
     for (int k = 0; k < kw; k += 16) {
-      uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+      uint32_t a0, a1, a2, a3;
       ldmatrix_x4(a0, a1, a2, a3, a_base + k * 2);
-      ldmatrix_x4(b0, b1, b2, b3, b_base + k * 2);     // (b0,b1): columns 0..7 k-lo/k-hi ; (b2,b3): columns 8..15
-      mma_bf16_16816(acc[0], a0, a1, a2, a3, b0, b1);
-      mma_bf16_16816(acc[1], a0, a1, a2, a3, b2, b3);
+#pragma unroll
+      for (int t = 0; t < NT; t += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(b0, b1, b2, b3, b_base + t * 8 * kDLStride * 2 + k * 2);   // (b0,b1): columns 8t..8t+7 ; (b2,b3): 8t+8..8t+15
+        mma_bf16_16816(acc[t], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(acc[t + 1], a0, a1, a2, a3, b2, b3);
+      }
     }
   }
   // ---- epilogue (warps 0..3): thread holds rows (lane/4) and (lane/4 + 8) of its warp's 16, columns 2*(lane%4) + {0,1} of
   // each n8 tile
   if (warp >= 4) return;
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
+  for (int t = 0; t < NT; ++t) {
 #pragma unroll
     for (int hlf = 0; hlf < 2; ++hlf) {
       const int r = m0 + warp * 16 + (lane >> 2) + hlf * 8;
       const int c = n0 + t * 8 + (lane & 3) * 2;
       if (r >= p.M || c >= p.N) continue;
       float v0 = acc[t][hlf * 2], v1 = acc[t][hlf * 2 + 1];
+      if (split) {   // out already holds the residual (out == residual)
+        float* dst = reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + c;
+        atomicAdd(dst, v0);
+        atomicAdd(dst + 1, v1);
+        continue;
+      }
       if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
       if (p.residual) {
         const float2 rr = *reinterpret_cast<const float2*>(p.residual + (long long)r * p.ldr + c);
@@ -331,12 +342,26 @@ extern "C" int vc_decode_linear(const void* A, int64_t lda, int a_fp32, const fl
   p.A = A; p.lda = lda; p.a_fp32 = a_fp32; p.norm_w = norm_w; p.eps = eps; p.out_scale = out_scale;
   p.W = (const __nv_bfloat16*)W; p.ldw = ldw; p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32;
   p.residual = residual; p.ldr = ldr; p.relu = relu; p.M = M; p.N = N; p.K = K;
-  const size_t smem = (size_t)(64 + 16) * kDLStride * 2;
-  static PerDeviceOnce attr;
-  if (attr.need()) {
-    VC_CUDA(cudaFuncSetAttribute(decode_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // split-K only where the partial sums can land on the residual stream in place (fp32 atomics: the order of the <= 3 adds
+  // per element is not fixed, i.e. the last bit of the stream may differ between runs)
+  static const bool splitk_on = [] { const char* e = getenv("VIDCHAP_DECODE_SPLITK"); return !(e && e[0] == '0'); }();
+  const bool inplace = residual && (const void*)residual == (const void*)out && ldr == ldo && out_fp32 && !relu && !norm_w;
+  const int splits = (splitk_on && inplace && K > kDLKC) ? (K + kDLKC - 1) / kDLKC : 1;
+  const int mblocks = (M + 63) / 64;
+  // 32 columns per CTA when 16-column CTAs would need a second wave (N = 3072: 192 CTAs on 148 SMs, one CTA per SM)
+  const bool wide = (long long)((N + 15) / 16) * mblocks * splits > num_sms();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (wide) {
+    const size_t smem = (size_t)(64 + 32) * kDLStride * 2;
+    static PerDeviceOnce attr;
+    if (attr.need()) VC_CUDA(cudaFuncSetAttribute(decode_linear_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VC_CUDA(launch_kernel(decode_linear_kernel<4>, dim3((N + 31) / 32, mblocks, splits), dim3(512), smem, st, p));
+  } else {
+    const size_t smem = (size_t)(64 + 16) * kDLStride * 2;
+    static PerDeviceOnce attr;
+    if (attr.need()) VC_CUDA(cudaFuncSetAttribute(decode_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VC_CUDA(launch_kernel(decode_linear_kernel<2>, dim3((N + 15) / 16, mblocks, splits), dim3(512), smem, st, p));
   }
-  VC_CUDA(launch_kernel(decode_linear_kernel, dim3((N + 15) / 16, (M + 63) / 64), dim3(512), smem, reinterpret_cast<cudaStream_t>(stream), p));
   VC_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -231,6 +231,17 @@ __device__ __forceinline__ void drop_select(float* v, uint32_t row_key, uint32_t
 __device__ __forceinline__ uint32_t drop_salted(uint32_t seed, const uint32_t* salt) { return salt ? seed ^ __ldg(salt) : seed; }
 __device__ __forceinline__ float drop_scale(uint32_t p16) { return 65536.0f / (float)(65536u - p16); }
 
+// ---------------------------------------------------------------- cp.async (LDGSTS): global -> shared without a register
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// 16 bytes; src_bytes = 0 zero-fills the destination (out-of-range rows)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (common.h::
 // launch_kernel): its CTAs may become resident — and run their prologue: barrier init, TMEM allocation, tensor-map
