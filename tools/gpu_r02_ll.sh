@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_e2e_gpu.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('train', d['ms_per_step'], d['value'], d['e2e']['value'], d['loss'])"
