@@ -562,3 +562,19 @@ def test_generate_options_host_logic_matches_oracle():
         m.generate(video, tok, use_nucleus_sampling=True, num_beams=4)
     with pytest.raises(ValueError):
         m.generate(video, tok, num_beams=1, num_captions=2)
+
+
+def test_bench_clock_sampler_counts_only_samples_after_mark():
+    """bench.py starts nvidia-smi before the warm-up (its start-up under the driver lock stalled the first timed
+    generate() call) and reports only the samples read after mark(), i.e. inside the timed region."""
+    import time
+    import bench
+    s = bench.ClockSampler(0)
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "700.0", "0x0", "Not Active", "Not Active", "Not Active", cap]
+    s.rows = [(time.time() - 10.0, row(1200, "Active")), (time.time() - 5.0, row(1300, "Not Active"))]
+    s.mark()
+    s.rows += [(time.time() + 0.01, row(1900, "Not Active")), (time.time() + 0.02, row(1950, "Active")),
+               (time.time() + 0.03, row(1965, "Not Active"))]
+    out = s.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
