@@ -87,3 +87,25 @@ def teacher_forced_errors(m, cfg, video, inp, out):
     errs.append((rel(logits, o["logits"].reshape(B * S, -1)), 0.0, "final_norm+lm_head"))
     errs.sort(reverse=True)
     return errs
+
+
+# Degenerate batches shared by the oracle-vs-reference and the engine-vs-oracle edge-case tests
+EDGE_CASES = {
+    # B, T, L, S, mutate(inp, out)
+    "batch1_single_target_token": (1, 10, 9, 1, lambda inp, out: None),
+    "one_frame_one_text_token": (2, 1, 1, 5, lambda inp, out: None),
+    "empty_asr_row": (2, 10, 12, 6, lambda inp, out: (inp.__setitem__((0, slice(1, None)), 0), inp.__setitem__((0, 0), 1))),   # "</s>" only
+    "target_row_of_eos_only": (2, 10, 12, 6, lambda inp, out: (out.__setitem__((1, slice(1, None)), 0), out.__setitem__((1, 0), 1))),
+    "ragged_everything": (3, 7, 33, 19, lambda inp, out: (inp.__setitem__((0, slice(5, None)), 0), inp.__setitem__((2, slice(30, None)), 0),
+                                                        out.__setitem__((0, slice(2, None)), 0), out.__setitem__((1, slice(18, None)), 0))),
+}
+
+
+def edge_batch(name, seed=21):
+    B, T, L, S, mut = EDGE_CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    video = torch.randn(B, T, 768, generator=g)
+    inp = torch.randint(2, 1100, (B, L), generator=g)
+    out = torch.randint(2, 1100, (B, S), generator=g)
+    mut(inp, out)
+    return video, inp, out

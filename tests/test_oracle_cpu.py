@@ -90,6 +90,38 @@ def test_oracle_matches_live_reference():
         assert torch.equal(ids, ref_ids[:, :ids.shape[1]])
 
 
+from parity_util import EDGE_CASES, edge_batch  # noqa: E402
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", list(EDGE_CASES))
+def test_oracle_matches_live_reference_edge_cases(name):
+    """Degenerate batches the reference's data pipeline can produce (dataset/dvc_dataset.py: a video without speech is the
+    single token "</s>"; a one-token target; one frame): the oracle restates the real reference there too — loss,
+    logits, memory and every parameter gradient."""
+    from vidchapters_b200.config import TINY
+    cfg = dict(TINY, num_features=10)
+    m = ref_shim.build_reference_vid2seq(cfg)
+    sd = init_state_dict(cfg, 5)
+    full = dict(sd)
+    for k in ("t5_model.encoder.embed_tokens.weight", "t5_model.decoder.embed_tokens.weight", "t5_model.lm_head.weight"):
+        full[k] = sd["t5_model.shared.weight"]
+    m.load_state_dict(full, strict=True)
+    video, inp, out = edge_batch(name)
+    ld, vd = m(video, {"input_ids": inp, "attention_mask": inp != 0}, {"input_ids": out, "attention_mask": out != 0})
+    ld["loss"].backward()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0)
+    o["loss"].backward()
+    assert torch.isfinite(ld["loss"]) and abs(o["loss"].item() - ld["loss"].item()) < 1e-5 * max(1.0, abs(ld["loss"].item()))
+    assert rel(o["video"], vd["video"]) < 1e-5
+    for n, p in m.named_parameters():
+        if p.grad is None or float(p.grad.abs().sum()) == 0.0:
+            assert sdg[n].grad is None or float(sdg[n].grad.abs().sum()) == 0.0, n
+        else:
+            assert rel(sdg[n].grad, p.grad) < 1e-2, n
+
+
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
 @pytest.mark.parametrize("use_video,use_speech", [(True, False), (False, True)], ids=["no_speech", "no_video"])
 def test_oracle_matches_live_reference_modality_variants(use_video, use_speech):
