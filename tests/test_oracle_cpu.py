@@ -94,6 +94,34 @@ from parity_util import EDGE_CASES, edge_batch  # noqa: E402
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_oracle_matches_live_reference_t5_large_dims():
+    """BASELINE configs[3] per-layer shapes (d_model 1024, 16 heads, d_ff 4096, the 768 -> 1024 `proj_v2t`) at one layer per
+    stack and a small vocabulary: the oracle restates the real reference at those widths too."""
+    cfg = dict(name="t5-large-shallow", d_model=1024, d_kv=64, d_ff=4096, num_layers=1, num_heads=16, base_vocab=600,
+               num_bins=100, num_features=10, embed_dim=768, depth=1, heads=12, mlp_dim=2048)
+    m = ref_shim.build_reference_vid2seq(cfg)
+    sd = init_state_dict(cfg, 6)
+    full = dict(sd)
+    for k in ("t5_model.encoder.embed_tokens.weight", "t5_model.decoder.embed_tokens.weight", "t5_model.lm_head.weight"):
+        full[k] = sd["t5_model.shared.weight"]
+    m.load_state_dict(full, strict=True)
+    g = torch.Generator().manual_seed(11)
+    B, T, L, S = 2, 10, 29, 13
+    video = torch.randn(B, T, 768, generator=g)
+    inp = torch.randint(2, 700, (B, L), generator=g); inp[1, -6:] = 0
+    out = torch.randint(2, 700, (B, S), generator=g); out[0, -2:] = 0
+    ld, vd = m(video, {"input_ids": inp, "attention_mask": inp != 0}, {"input_ids": out, "attention_mask": out != 0})
+    ld["loss"].backward()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o = O.vid2seq_forward(sdg, cfg, video, inp, inp != 0, out, out != 0)
+    o["loss"].backward()
+    assert abs(o["loss"].item() - ld["loss"].item()) < 1e-5 * abs(ld["loss"].item())
+    assert rel(o["video"], vd["video"]) < 1e-5
+    for n, p in m.named_parameters():
+        assert rel(sdg[n].grad, p.grad) < 1e-2, n
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
 @pytest.mark.parametrize("name", list(EDGE_CASES))
 def test_oracle_matches_live_reference_edge_cases(name):
     """Degenerate batches the reference's data pipeline can produce (dataset/dvc_dataset.py: a video without speech is the
